@@ -1,0 +1,12 @@
+"""Import alias: `import hpe_b200` loads the package directory
+`human-pose-estimation_b200/` (its name is not a valid Python identifier)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "human-pose-estimation_b200")
+_spec = importlib.util.spec_from_file_location(
+    "hpe_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["hpe_b200"] = _mod
+_spec.loader.exec_module(_mod)
