@@ -98,7 +98,7 @@ def test_invariants(small_model):
     assert np.max(np.abs(Rs - np.eye(3))) < 3e-16                        # theta = 0 -> I (cos(1.7e-8) rounds in fp64)
     R32 = onp.batch_rodrigues(np.zeros((2, 3), dtype=np.float32))
     assert np.array_equal(R32, np.broadcast_to(np.eye(3, dtype=np.float32), R32.shape))   # exactly I in fp32
-    assert rel_err(verts, inter["v_posed"]) < 1e-14                      # identity pose: skinning is a no-op
+    assert rel_err(verts, inter["v_posed"]) < 1e-6       # identity pose: verts = (sum_j W_vj) v_posed, fp32-rounded weights
     A = inter["A"]
     assert np.array_equal(A[:, :, 3, :], np.broadcast_to(np.array([0, 0, 0, 1.0]), A[:, :, 3, :].shape))
     # fold used by the kernels: J = J_regressor^T v_template + (J_regressor^T shapedirs) beta
