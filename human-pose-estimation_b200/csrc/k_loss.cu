@@ -1,0 +1,378 @@
+// Loss kernels: keypoint loss, mesh-reprojection (bidirectional nearest-neighbour) loss and
+// the WGAN-GP gradient-penalty reduction.  All reductions are fixed-order (deterministic).
+//
+//   kp_reprojection_loss      src/ops.py:35-47
+//   find_nearest_neighbors    src/ops.py:60-71
+//   bidirectional_dist        src/ops.py:83-102
+//   mesh_reprojection_loss    src/ops.py:117-137
+//   compute_gradient_penalty  src/ops.py:153-172
+#include "smplb_internal.h"
+
+// Fixed-order block sum of one float per thread (blockDim.x a power of two <= 1024).
+__device__ __forceinline__ float block_sum(float v, float *red) {
+  int t = threadIdx.x;
+  red[t] = v;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (t < o) red[t] += red[t + o];
+    __syncthreads();
+  }
+  float r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------- keypoint loss
+// Stand-alone kp loss on caller-supplied predictions: per-body partial sums.
+__global__ void k_kp_loss(int B, int K, const float *__restrict__ kp_gt, const float *__restrict__ kp_pred,
+                          float *__restrict__ dkp, float *__restrict__ part, int *__restrict__ cnt) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float tl = 0.f;
+  int tc = 0;
+  for (int k = 0; k < K; ++k) {
+    size_t bk = (size_t)b * K + k;
+    float gx = kp_gt[bk * 3 + 0], gy = kp_gt[bk * 3 + 1], vis = kp_gt[bk * 3 + 2];
+    float dx = kp_pred[bk * 2 + 0] - gx, dy = kp_pred[bk * 2 + 1] - gy;
+    tl += vis * fabsf(dx) + vis * fabsf(dy);
+    tc += (vis != 0.0f) ? 2 : 0;
+    if (dkp) {
+      dkp[bk * 2 + 0] = vis * (float)((dx > 0.f) - (dx < 0.f));
+      dkp[bk * 2 + 1] = vis * (float)((dy > 0.f) - (dy < 0.f));
+    }
+  }
+  part[b] = tl;
+  cnt[b] = tc;
+}
+
+// Sum of the per-body partials: one block, fixed order.
+__global__ void __launch_bounds__(1024) k_reduce_kp(int B, const float *__restrict__ part, const int *__restrict__ cnt,
+                                                    float *__restrict__ abs_sum, long long *__restrict__ num_present) {
+  __shared__ float red[1024];
+  __shared__ long long redc[1024];
+  int t = threadIdx.x;
+  float s = 0.f;
+  long long c = 0;
+  for (int i = t; i < B; i += 1024) {
+    s += part[i];
+    c += cnt[i];
+  }
+  red[t] = s;
+  redc[t] = c;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) {
+      red[t] += red[t + o];
+      redc[t] += redc[t + o];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    *abs_sum = red[0];
+    *num_present = redc[0];
+  }
+}
+
+// loss_parts = {kp abs_sum, kp num_present (as float), mesh sum, w_kp * kp/num + w_mesh * mesh}
+__global__ void k_finalize_loss(float w_kp, float w_mesh, long long count_override, int have_mesh,
+                                const float *__restrict__ kp_sum, long long *__restrict__ kp_cnt,
+                                const float *__restrict__ mesh, float *__restrict__ out) {
+  long long local = *kp_cnt;
+  long long den = count_override > 0 ? count_override : local;
+  float kp = den > 0 ? *kp_sum / (float)den : 0.0f;
+  float ml = have_mesh ? *mesh : 0.0f;
+  out[0] = *kp_sum;
+  out[1] = (float)local;
+  out[2] = ml;
+  out[3] = w_kp * kp + w_mesh * ml;
+  *kp_cnt = den;   // the backward divides by the (possibly global) count
+}
+
+// ------------------------------------------------------------------------------- mesh loss
+// d2(a, b) exactly as the fp32 expansion of ops.py:63-65: (-2 a.b + |a|^2) + |b|^2, each sum
+// rounded separately (-2 * x is exact, so the FMA below rounds once like the TF add does).
+__device__ __forceinline__ float d2_expand(float ax, float ay, float a2, float bx, float by, float b2) {
+  float dot = __fmaf_rn(ax, bx, __fmul_rn(ay, by));
+  return __fadd_rn(__fmaf_rn(-2.0f, dot, a2), b2);
+}
+
+#define MT 256     // threads per CTA of the NN kernels
+#define MTILE 1024 // points staged per shared-memory tile
+
+// pixel -> nearest vertex (ind_AB, ops.py:68): thread = pixel a of image i, scans all vertices
+// in index order with a strict '<' so the first minimal index wins (tf.argmin).  Adds the L1
+// term |A_a - B_nn| (ops.py:98) to a per-CTA partial and the integer sign sums of its gradient
+// to cnt[i][nn][0..1].
+__global__ void __launch_bounds__(MT) k_mesh_ab(int V, const float *__restrict__ pts, const int *__restrict__ offsets,
+                                                const float *__restrict__ sil_pred, float *__restrict__ part,
+                                                int *__restrict__ cnt, int *__restrict__ ind_ab) {
+  __shared__ float4 s4[MTILE];   // (x, y, |.|^2, -) of the staged vertices: one broadcast LDS.128 per pair
+  __shared__ float red[MT];
+  int i = blockIdx.y;
+  int p0 = offsets[i], np = offsets[i + 1] - p0;
+  const float *Bv = sil_pred + (size_t)i * V * 2;
+  float total = 0.f;
+  int nchunks = (np + MT - 1) / MT;
+  for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    int a = ch * MT + threadIdx.x;
+    bool ok = a < np;
+    float ax = 0.f, ay = 0.f;
+    if (ok) {
+      ax = pts[(size_t)(p0 + a) * 2 + 0];
+      ay = pts[(size_t)(p0 + a) * 2 + 1];
+    }
+    float a2 = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));
+    float best = 3.4e38f;
+    int bi = 0;
+    for (int v0 = 0; v0 < V; v0 += MTILE) {
+      int nv = min(MTILE, V - v0);
+      __syncthreads();
+      for (int q = threadIdx.x; q < nv; q += MT) {
+        float bx = Bv[(size_t)(v0 + q) * 2 + 0], by = Bv[(size_t)(v0 + q) * 2 + 1];
+        s4[q] = make_float4(bx, by, __fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)), 0.f);
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int q = 0; q < nv; ++q) {
+        float4 bq = s4[q];
+        float d = d2_expand(ax, ay, a2, bq.x, bq.y, bq.z);
+        if (d < best) {
+          best = d;
+          bi = v0 + q;
+        }
+      }
+    }
+    if (ok) {
+      if (ind_ab) ind_ab[p0 + a] = bi;
+      float bx = Bv[(size_t)bi * 2 + 0], by = Bv[(size_t)bi * 2 + 1];
+      float dx = ax - bx, dy = ay - by;
+      total += fabsf(dx) + fabsf(dy);
+      if (cnt) {
+        // d |A_a - B_nn| / d B_nn = -sign(A_a - B_nn): an integer, accumulated exactly
+        int sxg = (dx < 0.f) - (dx > 0.f), syg = (dy < 0.f) - (dy > 0.f);
+        if (sxg) atomicAdd(&cnt[((size_t)i * V + bi) * 2 + 0], sxg);
+        if (syg) atomicAdd(&cnt[((size_t)i * V + bi) * 2 + 1], syg);
+      }
+    }
+  }
+  float bs = block_sum(total, red);
+  if (threadIdx.x == 0) part[(size_t)i * gridDim.x + blockIdx.x] = bs;
+}
+
+// vertex -> nearest pixel (ind_BA, ops.py:69): thread = vertex b, scans all pixels of image i
+// in order.  Adds the L2 term ||B_b - A_nn|| (ops.py:92) and writes its gradient (unit vector).
+__global__ void __launch_bounds__(MT) k_mesh_ba(int V, const float *__restrict__ pts, const int *__restrict__ offsets,
+                                                const float *__restrict__ sil_pred, float *__restrict__ part,
+                                                float *__restrict__ d_sil, int *__restrict__ ind_ba) {
+  __shared__ float4 s4[MTILE];
+  __shared__ float red[MT];
+  int i = blockIdx.y;
+  int p0 = offsets[i], np = offsets[i + 1] - p0;
+  int b = blockIdx.x * MT + threadIdx.x;
+  bool ok = b < V;
+  const float *Bv = sil_pred + (size_t)i * V * 2;
+  float bx = 0.f, by = 0.f;
+  if (ok) {
+    bx = Bv[(size_t)b * 2 + 0];
+    by = Bv[(size_t)b * 2 + 1];
+  }
+  float b2 = __fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by));
+  float best = 3.4e38f;
+  int ai = -1;
+  for (int a0 = 0; a0 < np; a0 += MTILE) {
+    int na = min(MTILE, np - a0);
+    __syncthreads();
+    for (int q = threadIdx.x; q < na; q += MT) {
+      float ax = pts[(size_t)(p0 + a0 + q) * 2 + 0], ay = pts[(size_t)(p0 + a0 + q) * 2 + 1];
+      s4[q] = make_float4(ax, ay, __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int q = 0; q < na; ++q) {
+      float4 aq = s4[q];
+      float d = d2_expand(aq.x, aq.y, aq.z, bx, by, b2);
+      if (d < best) {
+        best = d;
+        ai = a0 + q;
+      }
+    }
+  }
+  float dist = 0.f, gx = 0.f, gy = 0.f;
+  if (ok && ind_ba) ind_ba[(size_t)i * V + b] = ai;
+  if (ok && ai >= 0) {
+    float ax = pts[(size_t)(p0 + ai) * 2 + 0], ay = pts[(size_t)(p0 + ai) * 2 + 1];
+    float dx = bx - ax, dy = by - ay;
+    dist = sqrtf(dx * dx + dy * dy);
+    if (dist > 0.f) {   // tf.norm's gradient is NaN at exactly 0 (measure zero); 0 here
+      gx = dx / dist;
+      gy = dy / dist;
+    }
+  }
+  if (ok && d_sil) {
+    d_sil[((size_t)i * V + b) * 2 + 0] = gx;
+    d_sil[((size_t)i * V + b) * 2 + 1] = gy;
+  }
+  float bs = block_sum(dist, red);
+  if (threadIdx.x == 0) part[(size_t)i * gridDim.x + blockIdx.x] = bs;
+}
+
+// loss = sum(partials) / (3 + V)  (ops.py:129-130: silhouette_gt.shape[1] + silhouette_pred.shape[1]);
+// d_sil = (unit vectors + integer sign sums) / (3 + V).
+__global__ void __launch_bounds__(1024) k_mesh_finish(int n_ab, const float *__restrict__ part_ab, int n_ba,
+                                                      const float *__restrict__ part_ba, float denom,
+                                                      float *__restrict__ loss) {
+  __shared__ float red[1024];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n_ab; i += 1024) s += part_ab[i];
+  for (int i = threadIdx.x; i < n_ba; i += 1024) s += part_ba[i];
+  float tot = block_sum(s, red);
+  if (threadIdx.x == 0) *loss = tot / denom;
+}
+
+__global__ void k_mesh_grad_finish(size_t n, float denom, const int *__restrict__ cnt, float *__restrict__ d_sil) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  d_sil[i] = (d_sil[i] + (float)cnt[i]) / denom;
+}
+
+// ------------------------------------------------------------------------ gradient penalty
+__device__ __forceinline__ void gp_col(int t, int &which, int &n, int &col) {
+  if (t < 169) { which = 0; n = 169; col = t; }
+  else if (t < 211) { which = 1; n = 42; col = t - 169; }
+  else if (t < 221) { which = 2; n = 10; col = t - 211; }
+  else { which = 3; n = 207; col = t - 221; }
+}
+
+// Column sums over a slab of rows: part[chunk][428].
+__global__ void __launch_bounds__(448) k_gp_colsum(int M, int rows_per, const float *__restrict__ g0,
+                                                   const float *__restrict__ g1, const float *__restrict__ g2,
+                                                   const float *__restrict__ g3, float *__restrict__ part) {
+  int t = threadIdx.x;
+  if (t >= SMPLB_GP_FLOATS) return;
+  int which, n, col;
+  gp_col(t, which, n, col);
+  const float *g = which == 0 ? g0 : which == 1 ? g1 : which == 2 ? g2 : g3;
+  int m0 = blockIdx.x * rows_per, m1 = min(M, m0 + rows_per);
+  float s = 0.f;
+  for (int m = m0; m < m1; ++m) s += g[(size_t)m * n + col];
+  part[(size_t)blockIdx.x * SMPLB_GP_FLOATS + t] = s;
+}
+
+__global__ void __launch_bounds__(448) k_gp_sumparts(int nchunk, const float *__restrict__ part,
+                                                     float *__restrict__ col_sums) {
+  int t = threadIdx.x;
+  if (t >= SMPLB_GP_FLOATS) return;
+  float s = 0.f;
+  for (int c = 0; c < nchunk; ++c) s += part[(size_t)c * SMPLB_GP_FLOATS + t];
+  col_sums[t] = s;
+}
+
+// norms[i] = || col_sums_i / M ||_F; penalty = sum (1 - norm_i)^2   (ops.py:155-163)
+__device__ __forceinline__ void gp_norms(const float *__restrict__ col_sums, float invM, float *sq, float *norms) {
+  int t = threadIdx.x;
+  if (t < SMPLB_GP_FLOATS) {
+    float m = col_sums[t] * invM;
+    sq[t] = m * m;
+  }
+  __syncthreads();
+  if (t < 4) {
+    const int beg[5] = {0, 169, 211, 221, 428};
+    float s = 0.f;
+    for (int q = beg[t]; q < beg[t + 1]; ++q) s += sq[q];
+    norms[t] = sqrtf(s);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(448) k_gp_final(float invM, const float *__restrict__ col_sums,
+                                                  float *__restrict__ penalty) {
+  __shared__ float sq[448];
+  __shared__ float norms[4];
+  gp_norms(col_sums, invM, sq, norms);
+  if (threadIdx.x == 0) {
+    float p = 0.f;
+    for (int q = 0; q < 4; ++q) p += (1.0f - norms[q]) * (1.0f - norms[q]);
+    *penalty = p;
+  }
+}
+
+// d penalty / d g_i[m, col] = -2 (1 - n_i) mean_col / (n_i M_total), the same for every row m.
+__global__ void __launch_bounds__(448) k_gp_bwd(int M, int rows_per, float invM, const float *__restrict__ col_sums,
+                                                float *__restrict__ d0, float *__restrict__ d1, float *__restrict__ d2,
+                                                float *__restrict__ d3) {
+  __shared__ float sq[448];
+  __shared__ float norms[4];
+  gp_norms(col_sums, invM, sq, norms);
+  int t = threadIdx.x;
+  if (t >= SMPLB_GP_FLOATS) return;
+  int which, n, col;
+  gp_col(t, which, n, col);
+  float *d = which == 0 ? d0 : which == 1 ? d1 : which == 2 ? d2 : d3;
+  if (!d) return;
+  float nn = norms[which];
+  float coef = -2.0f * (1.0f - nn) * (col_sums[t] * invM) / nn * invM;
+  int m0 = blockIdx.x * rows_per, m1 = min(M, m0 + rows_per);
+  for (int m = m0; m < m1; ++m) d[(size_t)m * n + col] = coef;
+}
+
+// --------------------------------------------------------------------------------- launchers
+int launch_kp_loss(smplb_ctx *c, int B, int K, const float *kp_gt, const float *kp_pred, float *dkp, float *part,
+                   int *cnt) {
+  LAUNCH(c, "kp_loss", cdiv(B, 128), 128, 0, k_kp_loss, B, K, kp_gt, kp_pred, dkp, part, cnt);
+  return 0;
+}
+
+int launch_reduce_kp(smplb_ctx *c, int B, const float *part, const int *cnt, float *abs_sum, long long *num_present) {
+  LAUNCH(c, "reduce_kp", 1, 1024, 0, k_reduce_kp, B, part, cnt, abs_sum, num_present);
+  return 0;
+}
+
+int launch_finalize_loss(smplb_ctx *c, float w_kp, float w_mesh, long long count_override, int have_mesh,
+                         float *loss_parts) {
+  LAUNCH(c, "finalize_loss", 1, 1, 0, k_finalize_loss, w_kp, w_mesh, count_override, have_mesh, c->ws_scal + 0,
+         c->ws_cnt64, c->ws_scal + 2, loss_parts);
+  return 0;
+}
+
+#define MESH_AB_BLOCKS 32
+int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *offsets, int P, const float *sil_pred,
+                     float *loss, float *d_sil_pred, int *cnt_scratch, float *part_scratch, int *ind_ab, int *ind_ba) {
+  (void)P;
+  int n_ba_blocks = cdiv(V, MT);
+  float *part_ab = part_scratch;
+  float *part_ba = part_scratch + (size_t)B * MESH_AB_BLOCKS;
+  if (d_sil_pred) CUDA_TRY(cudaMemsetAsync(cnt_scratch, 0, (size_t)B * V * 2 * sizeof(int), c->stream));
+  LAUNCH(c, "mesh_nn_pixel_to_vertex", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab, V, pts, offsets, sil_pred, part_ab,
+         d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab);
+  LAUNCH(c, "mesh_nn_vertex_to_pixel", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba, V, pts, offsets, sil_pred, part_ba,
+         d_sil_pred, ind_ba);
+  float denom = (float)(3 + V);
+  LAUNCH(c, "mesh_finish", 1, 1024, 0, k_mesh_finish, B * MESH_AB_BLOCKS, part_ab, B * n_ba_blocks, part_ba, denom,
+         loss);
+  if (d_sil_pred) {
+    size_t n = (size_t)B * V * 2;
+    LAUNCH(c, "mesh_grad_finish", (unsigned)((n + 255) / 256), 256, 0, k_mesh_grad_finish, n, denom, cnt_scratch,
+           d_sil_pred);
+  }
+  return 0;
+}
+
+#define GP_ROWS 64
+int launch_gp_colsum(smplb_ctx *c, int M, const float *g0, const float *g1, const float *g2, const float *g3,
+                     float *col_sums) {
+  int nchunk = cdiv(M, GP_ROWS);
+  LAUNCH(c, "gp_colsum", nchunk, 448, 0, k_gp_colsum, M, GP_ROWS, g0, g1, g2, g3, c->ws_gp);
+  LAUNCH(c, "gp_sumparts", 1, 448, 0, k_gp_sumparts, nchunk, c->ws_gp, col_sums);
+  return 0;
+}
+
+int launch_gp_final(smplb_ctx *c, long long M_total, const float *col_sums, float *penalty) {
+  LAUNCH(c, "gp_final", 1, 448, 0, k_gp_final, 1.0f / (float)M_total, col_sums, penalty);
+  return 0;
+}
+
+int launch_gp_bwd(smplb_ctx *c, int M, long long M_total, const float *col_sums, float *d0, float *d1, float *d2,
+                  float *d3) {
+  LAUNCH(c, "gp_bwd", cdiv(M, GP_ROWS), 448, 0, k_gp_bwd, M, GP_ROWS, 1.0f / (float)M_total, col_sums, d0, d1, d2, d3);
+  return 0;
+}

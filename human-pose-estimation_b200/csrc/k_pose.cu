@@ -1,0 +1,383 @@
+// Per-body kernels: Rodrigues, folded joint regression, the 24-joint kinematic chain and
+// their backward.  One warp owns one body; lane j owns joint j.
+//
+// Reference semantics (paths relative to the reference checkout):
+//   batch_rodrigues                    src/tf_smpl/batch_lbs.py:42-64  (eps placement :52-53)
+//   batch_skew                         src/tf_smpl/batch_lbs.py:15-39
+//   batch_global_rigid_transformation  src/tf_smpl/batch_lbs.py:91-152
+//   joint regression + pose feature    src/tf_smpl/batch_smpl.py:115-127
+#include "smplb_internal.h"
+
+#define FULL 0xffffffffu
+
+// R = cos(a) I + (1 - cos a) r r^T + sin(a) [r]x with a = ||theta + 1e-8||, r = theta / a.
+// The 1e-8 is added to every component in fp32 BEFORE the norm and the numerator is the
+// un-shifted theta, exactly as batch_lbs.py:52-53.  Precise sinf/cosf/div/sqrt (no fast-math).
+__device__ __forceinline__ void rodrigues_fwd(float tx, float ty, float tz, float *R) {
+  float ex = __fadd_rn(tx, 1e-8f), ey = __fadd_rn(ty, 1e-8f), ez = __fadd_rn(tz, 1e-8f);
+  float a = sqrtf(ex * ex + ey * ey + ez * ez);
+  float rx = tx / a, ry = ty / a, rz = tz / a;
+  float c = cosf(a), s = sinf(a);
+  float oc = 1.0f - c;
+  R[0] = c + oc * rx * rx;
+  R[1] = oc * rx * ry - s * rz;
+  R[2] = oc * rx * rz + s * ry;
+  R[3] = oc * ry * rx + s * rz;
+  R[4] = c + oc * ry * ry;
+  R[5] = oc * ry * rz - s * rx;
+  R[6] = oc * rz * rx - s * ry;
+  R[7] = oc * rz * ry + s * rx;
+  R[8] = c + oc * rz * rz;
+}
+
+// d theta given G = dL/dR (validated against autograd through the
+// reference by the CPU tests).
+__device__ __forceinline__ void rodrigues_bwd(float tx, float ty, float tz, const float *G, float *dth) {
+  float ex = __fadd_rn(tx, 1e-8f), ey = __fadd_rn(ty, 1e-8f), ez = __fadd_rn(tz, 1e-8f);
+  float a = sqrtf(ex * ex + ey * ey + ez * ez);
+  float ia = 1.0f / a;
+  float rx = tx * ia, ry = ty * ia, rz = tz * ia;
+  float c = cosf(a), s = sinf(a);
+  float ax0 = G[7] - G[5], ax1 = G[2] - G[6], ax2 = G[3] - G[1];
+  float Gr0 = G[0] * rx + G[1] * ry + G[2] * rz;
+  float Gr1 = G[3] * rx + G[4] * ry + G[5] * rz;
+  float Gr2 = G[6] * rx + G[7] * ry + G[8] * rz;
+  float Tr0 = G[0] * rx + G[3] * ry + G[6] * rz;
+  float Tr1 = G[1] * rx + G[4] * ry + G[7] * rz;
+  float Tr2 = G[2] * rx + G[5] * ry + G[8] * rz;
+  float g_c = (G[0] + G[4] + G[8]) - (rx * Gr0 + ry * Gr1 + rz * Gr2);
+  float g_s = rx * ax0 + ry * ax1 + rz * ax2;
+  float oc = 1.0f - c;
+  float gr0 = oc * (Gr0 + Tr0) + s * ax0;
+  float gr1 = oc * (Gr1 + Tr1) + s * ax1;
+  float gr2 = oc * (Gr2 + Tr2) + s * ax2;
+  float g_a = -s * g_c + c * g_s;
+  float ux = ex * ia, uy = ey * ia, uz = ez * ia;
+  float k = (tx * gr0 + ty * gr1 + tz * gr2) * ia * ia;
+  float m = g_a - k;
+  dth[0] = gr0 * ia + m * ux;
+  dth[1] = gr1 * ia + m * uy;
+  dth[2] = gr2 * ia + m * uz;
+}
+
+// Level-synchronous kinematic chain in registers.  On entry lane j (< 24) holds its local
+// rotation R[9] and rest joint J[3]; on exit G[12] = (Rg row-major | tg) of its global
+// transform G_j = G_parent(j) * [R_j | J_j - J_parent(j)]  (batch_lbs.py:128-135).  Parent
+// transforms travel by warp shuffle; joints of depth d are composed in round d.
+__device__ __forceinline__ void chain_fwd(const Tree &tree, int lane, const float *R, const float *J, float *G) {
+  int j = lane < NJ ? lane : NJ - 1;
+  int p = tree.parent[j];
+  int psrc = p < 0 ? 0 : p;
+  float pJ0 = __shfl_sync(FULL, J[0], psrc), pJ1 = __shfl_sync(FULL, J[1], psrc), pJ2 = __shfl_sync(FULL, J[2], psrc);
+  float t0 = J[0], t1 = J[1], t2 = J[2];
+  if (p >= 0) {
+    t0 -= pJ0;
+    t1 -= pJ1;
+    t2 -= pJ2;
+  }
+#pragma unroll
+  for (int e = 0; e < 9; ++e) G[e] = R[e];
+  G[9] = t0;
+  G[10] = t1;
+  G[11] = t2;
+  int myd = tree.depth[j];
+  for (int d = 1; d <= tree.max_depth; ++d) {
+    float P[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) P[e] = __shfl_sync(FULL, G[e], psrc);
+    if (myd == d) {
+      float N[12];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          N[3 * r + cc] = P[3 * r + 0] * R[cc] + P[3 * r + 1] * R[3 + cc] + P[3 * r + 2] * R[6 + cc];
+        N[9 + r] = P[3 * r + 0] * t0 + P[3 * r + 1] * t1 + P[3 * r + 2] * t2 + P[9 + r];
+      }
+#pragma unroll
+      for (int e = 0; e < 12; ++e) G[e] = N[e];
+    }
+  }
+}
+
+// One warp per body: theta -> Rs, pose_feature; beta -> J (folded regression
+// J = J0 + Jdirs beta, exact algebra for batch_smpl.py:110-118); chain -> A, J_transformed.
+// Also writes the blend GEMM operand row x = [pose_feature | beta | 1 | 0 ...].
+__global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, const float *__restrict__ beta,
+                                                  const float *__restrict__ theta, const float *__restrict__ J0,
+                                                  const float *__restrict__ Jdirs, float *__restrict__ Rs,
+                                                  float *__restrict__ Jout, float *__restrict__ A,
+                                                  float *__restrict__ Jtr, float *__restrict__ x) {
+  int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  int j = lane < NJ ? lane : NJ - 1;
+  bool act = lane < NJ;
+  const float *th = theta + (size_t)b * 72 + 3 * j;
+  float R[9];
+  rodrigues_fwd(th[0], th[1], th[2], R);
+  float J[3];
+#pragma unroll
+  for (int cc = 0; cc < 3; ++cc) {
+    float acc = J0[3 * j + cc];
+    const float *jd = Jdirs + (size_t)(3 * j + cc) * NB;
+    for (int k = 0; k < NB; ++k) acc = fmaf(jd[k], beta[(size_t)b * NB + k], acc);
+    J[cc] = acc;
+  }
+  if (act) {
+    if (Rs) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rs[((size_t)b * NJ + j) * 9 + e] = R[e];
+    }
+    if (Jout) {
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) Jout[((size_t)b * NJ + j) * 3 + cc] = J[cc];
+    }
+    if (x && j >= 1) {
+      // pose_feature index (j-1)*9 + 3r + c (batch_smpl.py:126-127)
+#pragma unroll
+      for (int e = 0; e < 9; ++e) x[(size_t)b * KX + (j - 1) * 9 + e] = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+    }
+  }
+  if (x) {
+    // tail of the operand row: beta, the constant 1 that multiplies v_template, zero padding
+    for (int k = NPF + lane; k < KX; k += 32) {
+      float v = 0.0f;
+      if (k < NPF + NB) v = beta[(size_t)b * NB + (k - NPF)];
+      else if (k == NPF + NB) v = 1.0f;
+      x[(size_t)b * KX + k] = v;
+    }
+  }
+  float G[12];
+  chain_fwd(tree, lane, R, J, G);
+  if (act) {
+    // A_j = [Rg | tg - Rg J_j]  (batch_lbs.py:146-150), J_transformed = tg (:140)
+    float *a = A + ((size_t)b * NJ + j) * 12;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      a[4 * r + 0] = G[3 * r + 0];
+      a[4 * r + 1] = G[3 * r + 1];
+      a[4 * r + 2] = G[3 * r + 2];
+      a[4 * r + 3] = G[9 + r] - (G[3 * r + 0] * J[0] + G[3 * r + 1] * J[1] + G[3 * r + 2] * J[2]);
+    }
+    if (Jtr) {
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) Jtr[((size_t)b * NJ + j) * 3 + cc] = G[9 + cc];
+    }
+  }
+}
+
+// Backward of the per-body stage.  One warp per body; the reverse chain walks joints 23..1
+// with the per-joint state in shared memory (children always have larger indices than their
+// parent, batch_lbs.py:128).  Inputs: fixed-order partial sums of dL/dA from the skinning
+// backward and of dL/dx from the blend backward GEMM.
+#define PB_WARPS 4
+struct PoseBwdSmem {
+  float Rg[NJ][9], R[NJ][9], J[NJ][3];
+  float dRg[NJ][9], dR[NJ][9], dtg[NJ][3], dJ[NJ][3];
+};
+
+__global__ void __launch_bounds__(32 * PB_WARPS)
+    k_pose_bwd(int B, int NB, Tree tree, const float *__restrict__ theta, const float *__restrict__ Rs,
+               const float *__restrict__ Jin, const float *__restrict__ A, const float *__restrict__ dA_part,
+               const float *__restrict__ dx_part, int ksplit, const float *__restrict__ d_Rs,
+               const float *__restrict__ Jdirs, float *__restrict__ d_beta, float *__restrict__ d_theta) {
+  __shared__ PoseBwdSmem sm[PB_WARPS];
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int b = blockIdx.x * PB_WARPS + w;
+  if (b >= B) return;
+  PoseBwdSmem &S = sm[w];
+  if (lane < NJ) {
+    int j = lane;
+    float dA[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) dA[e] = 0.0f;
+    for (int sp = 0; sp < VSPLIT; ++sp) {
+      const float *src = dA_part + ((size_t)sp * B + b) * (NJ * 12) + j * 12;
+#pragma unroll
+      for (int e = 0; e < 12; ++e) dA[e] += src[e];
+    }
+    const float *a = A + ((size_t)b * NJ + j) * 12;
+    float J[3];
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      J[cc] = Jin[((size_t)b * NJ + j) * 3 + cc];
+      S.J[j][cc] = J[cc];
+    }
+    float Rg[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        Rg[3 * r + cc] = a[4 * r + cc];
+        S.Rg[j][3 * r + cc] = Rg[3 * r + cc];
+        S.R[j][3 * r + cc] = Rs[((size_t)b * NJ + j) * 9 + 3 * r + cc];
+        // dRg = dA_R - dA_t (x) J
+        S.dRg[j][3 * r + cc] = dA[4 * r + cc] - dA[4 * r + 3] * J[cc];
+        S.dR[j][3 * r + cc] = 0.0f;
+      }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) S.dtg[j][r] = dA[4 * r + 3];
+    // dJ = -Rg^T dA_t
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      S.dJ[j][cc] = -(Rg[cc] * dA[3] + Rg[3 + cc] * dA[7] + Rg[6 + cc] * dA[11]);
+  }
+  __syncwarp();
+  for (int i = NJ - 1; i >= 1; --i) {
+    int p = tree.parent[i];
+    if (p < 0) continue;  // a second root: nothing to propagate
+    if (lane < 9) {
+      int r = lane / 3, cc = lane % 3;
+      // dR_i = Rg_p^T dRg_i
+      S.dR[i][lane] = S.Rg[p][0 + r] * S.dRg[i][0 + cc] + S.Rg[p][3 + r] * S.dRg[i][3 + cc] + S.Rg[p][6 + r] * S.dRg[i][6 + cc];
+      // dRg_p += dRg_i R_i^T + dtg_i (x) (J_i - J_p)
+      float add = S.dRg[i][3 * r + 0] * S.R[i][3 * cc + 0] + S.dRg[i][3 * r + 1] * S.R[i][3 * cc + 1] +
+                  S.dRg[i][3 * r + 2] * S.R[i][3 * cc + 2] + S.dtg[i][r] * (S.J[i][cc] - S.J[p][cc]);
+      S.dRg[p][lane] += add;
+    } else if (lane < 12) {
+      int r = lane - 9;
+      float djr = S.Rg[p][0 + r] * S.dtg[i][0] + S.Rg[p][3 + r] * S.dtg[i][1] + S.Rg[p][6 + r] * S.dtg[i][2];
+      S.dJ[i][r] += djr;
+      S.dJ[p][r] -= djr;
+      S.dtg[p][r] += S.dtg[i][r];
+    }
+    __syncwarp();
+  }
+  // roots: dR = dRg, dJ += dtg
+  if (lane < NJ && tree.parent[lane] < 0) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) S.dR[lane][e] = S.dRg[lane][e];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) S.dJ[lane][r] += S.dtg[lane][r];
+  }
+  __syncwarp();
+  if (lane < NJ) {
+    int j = lane;
+    float G[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      float g = S.dR[j][e];
+      if (j >= 1) {
+        float acc = 0.0f;
+        for (int ks = 0; ks < ksplit; ++ks) acc += dx_part[((size_t)ks * B + b) * KX + (j - 1) * 9 + e];
+        g += acc;
+      }
+      if (d_Rs) g += d_Rs[((size_t)b * NJ + j) * 9 + e];
+      G[e] = g;
+    }
+    const float *th = theta + (size_t)b * 72 + 3 * j;
+    float dth[3];
+    rodrigues_bwd(th[0], th[1], th[2], G, dth);
+    d_theta[(size_t)b * 72 + 3 * j + 0] = dth[0];
+    d_theta[(size_t)b * 72 + 3 * j + 1] = dth[1];
+    d_theta[(size_t)b * 72 + 3 * j + 2] = dth[2];
+  }
+  if (lane < NB) {
+    // d beta = Jdirs^T dJ + (dp . shapedirs^T), the latter from the blend backward GEMM
+    float acc = 0.0f;
+    for (int ks = 0; ks < ksplit; ++ks) acc += dx_part[((size_t)ks * B + b) * KX + NPF + lane];
+    for (int jc = 0; jc < NJ * 3; ++jc) acc = fmaf(Jdirs[(size_t)jc * NB + lane], S.dJ[jc / 3][jc % 3], acc);
+    d_beta[(size_t)b * NB + lane] = acc;
+  }
+}
+
+// batch_rodrigues stand-alone (batch_lbs.py:42): one thread per rotation.
+__global__ void k_rodrigues(int N, const float *__restrict__ theta, float *__restrict__ R) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float r[9];
+  rodrigues_fwd(theta[3 * (size_t)i], theta[3 * (size_t)i + 1], theta[3 * (size_t)i + 2], r);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) R[(size_t)i * 9 + e] = r[e];
+}
+
+// batch_global_rigid_transformation stand-alone (batch_lbs.py:91): caller-supplied Rs, Js;
+// A is the reference's [B,24,4,4] with bottom rows [0,0,0,1].
+__global__ void __launch_bounds__(128) k_global_rigid(int B, Tree tree, const float *__restrict__ Rs,
+                                                      const float *__restrict__ Js, float *__restrict__ newJ,
+                                                      float *__restrict__ A44) {
+  int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  int j = lane < NJ ? lane : NJ - 1;
+  float R[9], J[3], G[12];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) R[e] = Rs[((size_t)b * NJ + j) * 9 + e];
+#pragma unroll
+  for (int cc = 0; cc < 3; ++cc) J[cc] = Js[((size_t)b * NJ + j) * 3 + cc];
+  chain_fwd(tree, lane, R, J, G);
+  if (lane < NJ) {
+    float *a = A44 + ((size_t)b * NJ + j) * 16;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      a[4 * r + 0] = G[3 * r + 0];
+      a[4 * r + 1] = G[3 * r + 1];
+      a[4 * r + 2] = G[3 * r + 2];
+      a[4 * r + 3] = G[9 + r] - (G[3 * r + 0] * J[0] + G[3 * r + 1] * J[1] + G[3 * r + 2] * J[2]);
+      newJ[((size_t)b * NJ + j) * 3 + r] = G[9 + r];
+    }
+    a[12] = 0.0f;
+    a[13] = 0.0f;
+    a[14] = 0.0f;
+    a[15] = 1.0f;
+  }
+}
+
+// batch_skew stand-alone (batch_lbs.py:15-39): [[0,-z,y],[z,0,-x],[-y,x,0]].
+__global__ void k_skew(int N, const float *__restrict__ vec, float *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float x = vec[3 * (size_t)i], y = vec[3 * (size_t)i + 1], z = vec[3 * (size_t)i + 2];
+  float *o = out + (size_t)i * 9;
+  o[0] = 0.f; o[1] = -z; o[2] = y;
+  o[3] = z; o[4] = 0.f; o[5] = -x;
+  o[6] = -y; o[7] = x; o[8] = 0.f;
+}
+
+// batch_lrotmin stand-alone (batch_lbs.py:67-88): (Rodrigues(theta[:, 3:]) - I) -> [B,207].
+__global__ void k_lrotmin(int B, const float *__restrict__ theta, float *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 23) return;
+  int b = i / 23, j = i % 23 + 1;
+  float r[9];
+  const float *th = theta + (size_t)b * 72 + 3 * j;
+  rodrigues_fwd(th[0], th[1], th[2], r);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) out[(size_t)b * NPF + (j - 1) * 9 + e] = r[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+}
+
+int launch_skew(smplb_ctx *c, int N, const float *vec, float *out) {
+  LAUNCH(c, "skew", cdiv(N, 128), 128, 0, k_skew, N, vec, out);
+  return 0;
+}
+
+int launch_lrotmin(smplb_ctx *c, int B, const float *theta, float *out) {
+  LAUNCH(c, "lrotmin", cdiv(B * 23, 128), 128, 0, k_lrotmin, B, theta, out);
+  return 0;
+}
+
+int launch_pose_fwd(smplb_ctx *c, int B, const float *beta, const float *theta, float *Rs, float *J, float *A,
+                    float *Jtr, float *x) {
+  LAUNCH(c, "pose_fwd", cdiv(B, 4), 128, 0, k_pose_fwd, B, c->NB, c->tree, beta, theta, c->d_J0, c->d_Jdirs, Rs, J, A,
+         Jtr, x);
+  return 0;
+}
+
+int launch_pose_bwd(smplb_ctx *c, int B, const float *theta, const float *Rs, const float *J, const float *A,
+                    const float *dA_part, const float *dx_part, int ksplit, const float *d_Rs, float *d_beta,
+                    float *d_theta) {
+  LAUNCH(c, "pose_bwd", cdiv(B, PB_WARPS), 32 * PB_WARPS, 0, k_pose_bwd, B, c->NB, c->tree, theta, Rs, J, A, dA_part,
+         dx_part, ksplit, d_Rs, c->d_Jdirs, d_beta, d_theta);
+  return 0;
+}
+
+int launch_rodrigues(smplb_ctx *c, int N, const float *theta, float *R) {
+  LAUNCH(c, "rodrigues", cdiv(N, 128), 128, 0, k_rodrigues, N, theta, R);
+  return 0;
+}
+
+int launch_global_rigid(smplb_ctx *c, int B, const float *Rs, const float *Js, float *new_J, float *A44) {
+  LAUNCH(c, "global_rigid", cdiv(B, 4), 128, 0, k_global_rigid, B, c->tree, Rs, Js, new_J, A44);
+  return 0;
+}

@@ -1,0 +1,860 @@
+// C ABI of libsmplb.so (see include/smplb.h): context, memory, orchestration of the kernels.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+
+#include "smplb_internal.h"
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+
+void smplb_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *smplb_last_error(void) { return g_err; }
+extern "C" int smplb_version(void) { return SMPLB_VERSION; }
+
+// ---------------------------------------------------------------------------------- profiling
+ProfScope::ProfScope(smplb_ctx *ctx, const char *name) : c(ctx) {
+  r.name = name;
+  r.e0 = r.e1 = nullptr;
+  if (!c->profile) return;
+  for (cudaEvent_t *e : {&r.e0, &r.e1}) {
+    if (!c->event_pool.empty()) {
+      *e = c->event_pool.back();
+      c->event_pool.pop_back();
+    } else {
+      cudaEventCreate(e);
+    }
+  }
+  cudaEventRecord(r.e0, c->stream);
+}
+ProfScope::~ProfScope() {
+  if (!r.e0) return;
+  cudaEventRecord(r.e1, c->stream);
+  c->prof.push_back(r);
+}
+
+// ------------------------------------------------------------------------- host-mode staging
+// In SMPLB_HOST mode every pointer is host memory: inputs are copied to temporary device
+// buffers (stream-ordered allocations), outputs are copied back at finish().
+struct Stager {
+  smplb_ctx *c;
+  int mem;
+  struct Out {
+    void *host, *dev;
+    size_t bytes;
+  };
+  std::vector<void *> temps;
+  std::vector<Out> outs;
+  bool failed = false;
+  Stager(smplb_ctx *ctx, int m) : c(ctx), mem(m) {}
+  void *alloc(size_t bytes) {
+    void *d = nullptr;
+    if (cudaMallocAsync(&d, bytes ? bytes : 4, c->stream) != cudaSuccess) {
+      failed = true;
+      return nullptr;
+    }
+    temps.push_back(d);
+    return d;
+  }
+  template <typename T>
+  const T *in(const T *p, size_t n) {
+    if (!p || mem == SMPLB_DEVICE) return p;
+    void *d = alloc(n * sizeof(T));
+    if (!d) return nullptr;
+    if (cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) failed = true;
+    return (const T *)d;
+  }
+  template <typename T>
+  T *out(T *p, size_t n) {
+    if (!p || mem == SMPLB_DEVICE) return p;
+    void *d = alloc(n * sizeof(T));
+    if (!d) return nullptr;
+    outs.push_back({(void *)p, d, n * sizeof(T)});
+    return (T *)d;
+  }
+  int finish() {
+    int rc = 0;
+    if (mem == SMPLB_HOST) {
+      for (auto &o : outs)
+        if (cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) failed = true;
+      for (void *t : temps) cudaFreeAsync(t, c->stream);
+      temps.clear();
+      cudaError_t e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess || failed) {
+        smplb_set_error("host-mode staging failed: %s", cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
+        rc = SMPLB_ECUDA;
+      }
+    }
+    return rc;
+  }
+  ~Stager() {
+    for (void *t : temps) cudaFreeAsync(t, c->stream);
+  }
+};
+
+#define CHECK_CTX(c)                                                    \
+  do {                                                                  \
+    RET_IF(!(c), SMPLB_EINVAL, "null context");                         \
+    CUDA_TRY(cudaSetDevice((c)->device));                               \
+  } while (0)
+#define CHECK_MEM(mem) RET_IF((mem) != SMPLB_HOST && (mem) != SMPLB_DEVICE, SMPLB_EINVAL, "mem must be SMPLB_HOST or SMPLB_DEVICE")
+
+// ------------------------------------------------------------------------------- create-time
+// J0 = J_regressor^T v_template and Jdirs = J_regressor^T shapedirs in fp64 (one-off constant
+// folding of batch_smpl.py:115-118 through :110-112; exact algebra).
+__global__ void __launch_bounds__(256) k_fold_joints(int V, int NB, const float *__restrict__ Jreg,
+                                                     const float *__restrict__ shapedirs, const float *__restrict__ vt,
+                                                     float *__restrict__ J0, float *__restrict__ Jdirs) {
+  __shared__ double red[256];
+  int jc = blockIdx.x;           // 3j + c
+  int k = blockIdx.y;            // 0..NB-1: Jdirs column, NB: J0
+  int j = jc / 3, cc = jc % 3;
+  double s = 0.0;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    double src = (k < NB) ? (double)shapedirs[(size_t)k * V * 3 + 3 * v + cc] : (double)vt[3 * v + cc];
+    s += (double)Jreg[(size_t)v * NJ + j] * src;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (k < NB) Jdirs[(size_t)jc * NB + k] = (float)red[0];
+    else J0[jc] = (float)red[0];
+  }
+}
+
+template <typename T>
+static int dev_upload(T **dst, const T *src, size_t n) {
+  CUDA_TRY(cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) CUDA_TRY(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static void free_ws(smplb_ctx *c) {
+  void **ptrs[] = {(void **)&c->ws_x, (void **)&c->ws_Rs, (void **)&c->ws_J, (void **)&c->ws_A, (void **)&c->ws_Jtr,
+                   (void **)&c->ws_vposed, (void **)&c->ws_verts, (void **)&c->ws_joints, (void **)&c->ws_kp,
+                   (void **)&c->ws_dkp, (void **)&c->ws_djoints, (void **)&c->ws_dverts, (void **)&c->ws_dp, (void **)&c->ws_dA,
+                   (void **)&c->ws_dx, (void **)&c->ws_part, (void **)&c->ws_cnt, (void **)&c->ws_theta,
+                   (void **)&c->ws_beta, (void **)&c->ws_gp};
+  for (void **p : ptrs) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  c->ws_batch = 0;
+  c->saved_B = 0;
+  c->ws_gp_cap = 0;
+}
+
+#define WS_ALLOC(field, count)                                                        \
+  do {                                                                                \
+    size_t _n = (size_t)(count);                                                      \
+    CUDA_TRY(cudaMalloc((void **)&c->field, std::max<size_t>(_n, 1) * 4));            \
+  } while (0)
+
+// Big buffers that only some calls need are allocated lazily by ensure_* below.
+static int ensure_ws(smplb_ctx *c, int B) {
+  if (B <= c->ws_batch) return 0;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  free_ws(c);
+  int n = std::max(B, c->max_batch);
+  size_t nb = (size_t)n;
+  WS_ALLOC(ws_x, nb * KX);
+  WS_ALLOC(ws_Rs, nb * NJ * 9);
+  WS_ALLOC(ws_J, nb * NJ * 3);
+  WS_ALLOC(ws_A, nb * NJ * 12);
+  WS_ALLOC(ws_Jtr, nb * NJ * 3);
+  WS_ALLOC(ws_vposed, nb * c->pitch);
+  WS_ALLOC(ws_joints, nb * c->K * 3);
+  WS_ALLOC(ws_kp, nb * c->K * 2);
+  WS_ALLOC(ws_dkp, nb * c->K * 2);
+  WS_ALLOC(ws_djoints, nb * c->K * 3);
+  WS_ALLOC(ws_dA, (size_t)VSPLIT * nb * NJ * 12);
+  WS_ALLOC(ws_dx, (size_t)c->ksplit * nb * KX);
+  WS_ALLOC(ws_part, nb);
+  WS_ALLOC(ws_cnt, nb);
+  WS_ALLOC(ws_theta, nb * 72);
+  WS_ALLOC(ws_beta, nb * c->NB);
+  c->ws_batch = n;
+  return 0;
+}
+
+static int ensure_buf(smplb_ctx *c, float **field, size_t count, bool zero) {
+  if (*field) return 0;
+  CUDA_TRY(cudaMalloc((void **)field, std::max<size_t>(count, 1) * 4));
+  if (zero) CUDA_TRY(cudaMemsetAsync(*field, 0, count * 4, c->stream));
+  return 0;
+}
+
+extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, int max_batch) {
+  RET_IF(!out || !m, SMPLB_EINVAL, "null argument");
+  *out = nullptr;
+  RET_IF(m->num_verts < 1 || m->num_betas < 1 || m->num_betas > KX - NPF - 1, SMPLB_EINVAL,
+         "num_verts >= 1 and 1 <= num_betas <= %d required", KX - NPF - 1);
+  RET_IF(m->num_keypoints < 1 || m->num_keypoints > MAXK, SMPLB_EINVAL, "1 <= num_keypoints <= %d required", MAXK);
+  RET_IF(!m->v_template || !m->shapedirs || !m->posedirs || !m->J_regressor || !m->weights || !m->joint_regressor ||
+             !m->parents,
+         SMPLB_EINVAL, "model has a null array");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  RET_IF(e != cudaSuccess || ndev == 0, SMPLB_EDEVICE, "no CUDA device available (%s); libsmplb has no CPU fallback",
+         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  RET_IF(device < 0 || device >= ndev, SMPLB_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  RET_IF(prop.major != 10, SMPLB_EDEVICE, "device %d is sm_%d%d; libsmplb is built for sm_100a only", device, prop.major,
+         prop.minor);
+  CUDA_TRY(cudaSetDevice(device));
+
+  smplb_ctx *c = new smplb_ctx();
+  c->device = device;
+  c->V = m->num_verts;
+  c->NB = m->num_betas;
+  c->K = m->num_keypoints;
+  c->V3 = 3 * c->V;
+  c->pitch = cdiv(c->V3, 128) * 128;
+  c->ksplit = 16;
+  c->max_batch = std::max(max_batch, 1);
+  // kinematic tree: parent index < child index (batch_lbs.py:130 walks joints in index order)
+  c->tree.max_depth = 0;
+  for (int j = 0; j < NJ; ++j) {
+    int p = m->parents[j];
+    if (p < 0 || p >= NJ) p = -1;    // uint32(-1) cast to int32 (batch_smpl.py:65)
+    if (j == 0) p = -1;
+    if (p >= j) {
+      delete c;
+      smplb_set_error("parents[%d] = %d: parents must precede children", j, p);
+      return SMPLB_EINVAL;
+    }
+    c->tree.parent[j] = (signed char)p;
+    c->tree.depth[j] = p < 0 ? 0 : (signed char)(c->tree.depth[p] + 1);
+    c->tree.max_depth = std::max(c->tree.max_depth, (int)c->tree.depth[j]);
+  }
+  int rc = 0;
+  auto fail = [&](int code) {
+    smplb_destroy(c);
+    return code;
+  };
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(SMPLB_ECUDA);
+  size_t V = c->V;
+  if ((rc = dev_upload(&c->d_vt, m->v_template, V * 3))) return fail(rc);
+  if ((rc = dev_upload(&c->d_shapedirs, m->shapedirs, (size_t)c->NB * V * 3))) return fail(rc);
+  if ((rc = dev_upload(&c->d_posedirs, m->posedirs, (size_t)NPF * V * 3))) return fail(rc);
+  if ((rc = dev_upload(&c->d_W, m->weights, V * NJ))) return fail(rc);
+  if ((rc = dev_upload(&c->d_JR, m->joint_regressor, V * c->K))) return fail(rc);
+  float *d_Jreg = nullptr;
+  if ((rc = dev_upload(&d_Jreg, m->J_regressor, V * NJ))) return fail(rc);
+  // Dext = [posedirs ; shapedirs ; v_template ; 0] with row pitch c->pitch (zero padded)
+  size_t dext_bytes = (size_t)KX * c->pitch * sizeof(float);
+  if (cudaMalloc((void **)&c->d_Dext, dext_bytes) != cudaSuccess || cudaMemset(c->d_Dext, 0, dext_bytes) != cudaSuccess)
+    return fail(SMPLB_ECUDA);
+  size_t rowb = V * 3 * sizeof(float), pitchb = (size_t)c->pitch * sizeof(float);
+  if (cudaMemcpy2D(c->d_Dext, pitchb, c->d_posedirs, rowb, rowb, NPF, cudaMemcpyDeviceToDevice) != cudaSuccess ||
+      cudaMemcpy2D(c->d_Dext + (size_t)NPF * c->pitch, pitchb, c->d_shapedirs, rowb, rowb, c->NB,
+                   cudaMemcpyDeviceToDevice) != cudaSuccess ||
+      cudaMemcpy(c->d_Dext + (size_t)(NPF + c->NB) * c->pitch, c->d_vt, rowb, cudaMemcpyDeviceToDevice) != cudaSuccess)
+    return fail(SMPLB_ECUDA);
+  if (cudaMalloc((void **)&c->d_J0, NJ * 3 * 4) != cudaSuccess ||
+      cudaMalloc((void **)&c->d_Jdirs, (size_t)NJ * 3 * c->NB * 4) != cudaSuccess)
+    return fail(SMPLB_ECUDA);
+  k_fold_joints<<<dim3(NJ * 3, c->NB + 1), 256, 0, c->stream>>>(c->V, c->NB, d_Jreg, c->d_shapedirs, c->d_vt, c->d_J0,
+                                                               c->d_Jdirs);
+  c->launches++;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    smplb_set_error("k_fold_joints failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_Jreg);
+    return fail(SMPLB_ECUDA);
+  }
+  cudaFree(d_Jreg);
+  // CSR views of joint_regressor [V,K] (index construction only, any sparsity pattern)
+  {
+    int K = c->K;
+    std::vector<int> koff(K + 1, 0), kidx, voff(V + 1, 0), vk;
+    std::vector<float> kval, vval;
+    for (int k = 0; k < K; ++k) {
+      for (size_t v = 0; v < V; ++v) {
+        float w = m->joint_regressor[v * K + k];
+        if (w != 0.0f) {
+          kidx.push_back((int)v);
+          kval.push_back(w);
+        }
+      }
+      koff[k + 1] = (int)kidx.size();
+    }
+    for (size_t v = 0; v < V; ++v) {
+      for (int k = 0; k < K; ++k) {
+        float w = m->joint_regressor[v * K + k];
+        if (w != 0.0f) {
+          vk.push_back(k);
+          vval.push_back(w);
+        }
+      }
+      voff[v + 1] = (int)vk.size();
+    }
+    if ((rc = dev_upload(&c->d_kcsr_off, koff.data(), koff.size()))) return fail(rc);
+    if ((rc = dev_upload(&c->d_kcsr_idx, kidx.data(), kidx.size()))) return fail(rc);
+    if ((rc = dev_upload(&c->d_kcsr_val, kval.data(), kval.size()))) return fail(rc);
+    if ((rc = dev_upload(&c->d_vcsr_off, voff.data(), voff.size()))) return fail(rc);
+    if ((rc = dev_upload(&c->d_vcsr_k, vk.data(), vk.size()))) return fail(rc);
+    if ((rc = dev_upload(&c->d_vcsr_val, vval.data(), vval.size()))) return fail(rc);
+  }
+  if (cudaMalloc((void **)&c->ws_scal, 64 * 4) != cudaSuccess ||
+      cudaMalloc((void **)&c->ws_cnt64, 8 * sizeof(long long)) != cudaSuccess)
+    return fail(SMPLB_ECUDA);
+  cudaMemset(c->ws_scal, 0, 64 * 4);
+  cudaMemset(c->ws_cnt64, 0, 8 * sizeof(long long));
+  if ((rc = ensure_ws(c, c->max_batch))) return fail(rc);
+  *out = c;
+  return 0;
+}
+
+extern "C" int smplb_destroy(smplb_ctx *c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  smplb_comm_destroy(c);
+  free_ws(c);
+  void *ptrs[] = {c->d_vt,       c->d_shapedirs, c->d_posedirs, c->d_W,        c->d_JR,       c->d_Dext,   c->d_J0,
+                  c->d_Jdirs,    c->d_kcsr_off,  c->d_kcsr_idx, c->d_kcsr_val, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val,
+                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  for (int i = 0; i < 16; ++i) {
+    if (c->timer0[i]) cudaEventDestroy(c->timer0[i]);
+    if (c->timer1[i]) cudaEventDestroy(c->timer1[i]);
+  }
+  for (auto &r : c->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (auto e : c->event_pool) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------- memory
+extern "C" int smplb_malloc(smplb_ctx *c, void **dptr, size_t bytes) {
+  CHECK_CTX(c);
+  RET_IF(!dptr, SMPLB_EINVAL, "null dptr");
+  CUDA_TRY(cudaMalloc(dptr, bytes ? bytes : 1));
+  return 0;
+}
+extern "C" int smplb_free(smplb_ctx *c, void *dptr) {
+  CHECK_CTX(c);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaFree(dptr));
+  return 0;
+}
+extern "C" int smplb_host_alloc(void **hptr, size_t bytes) {
+  RET_IF(!hptr, SMPLB_EINVAL, "null hptr");
+  CUDA_TRY(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+extern "C" int smplb_host_free(void *hptr) {
+  CUDA_TRY(cudaFreeHost(hptr));
+  return 0;
+}
+extern "C" int smplb_memcpy_h2d(smplb_ctx *c, void *dst, const void *src, size_t bytes) {
+  CHECK_CTX(c);
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+extern "C" int smplb_memcpy_d2h(smplb_ctx *c, void *dst, const void *src, size_t bytes) {
+  CHECK_CTX(c);
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+extern "C" int smplb_memset(smplb_ctx *c, void *dst, int value, size_t bytes) {
+  CHECK_CTX(c);
+  CUDA_TRY(cudaMemsetAsync(dst, value, bytes, c->stream));
+  return 0;
+}
+extern "C" int smplb_sync(smplb_ctx *c) {
+  CHECK_CTX(c);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int smplb_flush_l2(smplb_ctx *c, size_t bytes) {
+  CHECK_CTX(c);
+  if (bytes > c->flush_bytes) {
+    if (c->flush_buf) CUDA_TRY(cudaFree(c->flush_buf));
+    c->flush_buf = nullptr;
+    CUDA_TRY(cudaMalloc(&c->flush_buf, bytes));
+    c->flush_bytes = bytes;
+  }
+  CUDA_TRY(cudaMemsetAsync(c->flush_buf, 0x5a, bytes, c->stream));
+  return 0;
+}
+extern "C" int smplb_timer_start(smplb_ctx *c, int slot) {
+  CHECK_CTX(c);
+  RET_IF(slot < 0 || slot >= 16, SMPLB_EINVAL, "timer slot out of range");
+  if (!c->timer0[slot]) {
+    CUDA_TRY(cudaEventCreate(&c->timer0[slot]));
+    CUDA_TRY(cudaEventCreate(&c->timer1[slot]));
+  }
+  CUDA_TRY(cudaEventRecord(c->timer0[slot], c->stream));
+  return 0;
+}
+extern "C" int smplb_timer_stop(smplb_ctx *c, int slot) {
+  CHECK_CTX(c);
+  RET_IF(slot < 0 || slot >= 16 || !c->timer1[slot], SMPLB_EINVAL, "timer slot not started");
+  CUDA_TRY(cudaEventRecord(c->timer1[slot], c->stream));
+  return 0;
+}
+extern "C" int smplb_timer_elapsed_ms(smplb_ctx *c, int slot, float *ms) {
+  CHECK_CTX(c);
+  RET_IF(slot < 0 || slot >= 16 || !c->timer1[slot] || !ms, SMPLB_EINVAL, "timer slot not started");
+  CUDA_TRY(cudaEventSynchronize(c->timer1[slot]));
+  CUDA_TRY(cudaEventElapsedTime(ms, c->timer0[slot], c->timer1[slot]));
+  return 0;
+}
+extern "C" int smplb_launch_count(smplb_ctx *c, int64_t *count) {
+  RET_IF(!c || !count, SMPLB_EINVAL, "null argument");
+  *count = c->launches;
+  return 0;
+}
+extern "C" int smplb_profile_enable(smplb_ctx *c, int on) {
+  RET_IF(!c, SMPLB_EINVAL, "null context");
+  c->profile = on != 0;
+  return 0;
+}
+extern "C" int smplb_profile_read(smplb_ctx *c, char *buf, size_t buflen) {
+  CHECK_CTX(c);
+  RET_IF(!buf || buflen == 0, SMPLB_EINVAL, "null buffer");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  std::map<std::string, std::pair<double, int>> acc;
+  std::vector<std::string> order;
+  for (auto &r : c->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (!acc.count(r.name)) order.push_back(r.name);
+    acc[r.name].first += ms;
+    acc[r.name].second += 1;
+    c->event_pool.push_back(r.e0);
+    c->event_pool.push_back(r.e1);
+  }
+  c->prof.clear();
+  std::string s;
+  char line[256];
+  for (auto &n : order) {
+    snprintf(line, sizeof(line), "%s %.6f %d\n", n.c_str(), acc[n].first, acc[n].second);
+    s += line;
+  }
+  snprintf(buf, buflen, "%s", s.c_str());
+  return 0;
+}
+
+// --------------------------------------------------------------------------------- SMPL fwd/bwd
+static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float *theta, float *verts, float *joints,
+                            float *Rs, float *Jtr, const float *cam, const float *kp_gt, float *kp_pred,
+                            bool need_verts) {
+  TRY(ensure_ws(c, B));
+  CUDA_TRY(cudaMemcpyAsync(c->ws_beta, beta, (size_t)B * c->NB * 4, cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->ws_theta, theta, (size_t)B * 72 * 4, cudaMemcpyDeviceToDevice, c->stream));
+  TRY(launch_pose_fwd(c, B, c->ws_beta, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, Jtr ? Jtr : c->ws_Jtr, c->ws_x));
+  if (Rs) CUDA_TRY(cudaMemcpyAsync(Rs, c->ws_Rs, (size_t)B * NJ * 9 * 4, cudaMemcpyDeviceToDevice, c->stream));
+  TRY(launch_blend_fwd(c, B, c->ws_x, c->ws_vposed));
+  float *vout = verts;
+  if (!vout) {
+    (void)need_verts;
+    TRY(ensure_buf(c, &c->ws_verts, (size_t)c->ws_batch * c->V3, false));
+    vout = c->ws_verts;
+  }
+  TRY(launch_skin_fwd(c, B, c->ws_A, c->ws_vposed, vout));
+  TRY(launch_joints(c, B, vout, cam, kp_gt, joints ? joints : c->ws_joints, kp_pred, kp_gt ? c->ws_dkp : nullptr,
+                    kp_gt ? c->ws_part : nullptr, kp_gt ? c->ws_cnt : nullptr));
+  c->saved_B = B;
+  return 0;
+}
+
+static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const float *d_joints, const float *d_Rs,
+                             float *d_beta, float *d_theta) {
+  RET_IF(c->saved_B != B, SMPLB_ESTATE, "smplb_smpl_backward(B=%d) without a matching forward (saved B=%d)", B,
+         c->saved_B);
+  TRY(ensure_buf(c, &c->ws_dp, (size_t)c->ws_batch * c->pitch, true));
+  TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed, d_verts, d_joints, c->ws_dp, c->ws_dA));
+  TRY(launch_blend_bwd(c, B, c->ws_dp, c->ws_dx));
+  TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, c->ws_dx, c->ksplit, d_Rs, d_beta,
+                      d_theta));
+  return 0;
+}
+
+extern "C" int smplb_smpl_forward(smplb_ctx *c, int B, const float *beta, const float *theta, float *verts,
+                                  float *joints, float *Rs, float *J_transformed, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(B < 1 || !beta || !theta || !joints, SMPLB_EINVAL, "B >= 1 and non-null beta, theta, joints required");
+  Stager st(c, mem);
+  const float *dbeta = st.in(beta, (size_t)B * c->NB), *dtheta = st.in(theta, (size_t)B * 72);
+  float *dverts = st.out(verts, (size_t)B * c->V3), *djoints = st.out(joints, (size_t)B * c->K * 3);
+  float *dRs = st.out(Rs, (size_t)B * NJ * 9), *dJtr = st.out(J_transformed, (size_t)B * NJ * 3);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(smpl_forward_dev(c, B, dbeta, dtheta, dverts, djoints, dRs, dJtr, nullptr, nullptr, nullptr, verts != nullptr));
+  return st.finish();
+}
+
+extern "C" int smplb_smpl_backward(smplb_ctx *c, int B, const float *d_verts, const float *d_joints,
+                                   const float *d_Rs, float *d_beta, float *d_theta, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(B < 1 || !d_beta || !d_theta, SMPLB_EINVAL, "B >= 1 and non-null d_beta, d_theta required");
+  Stager st(c, mem);
+  const float *dv = st.in(d_verts, (size_t)B * c->V3), *dj = st.in(d_joints, (size_t)B * c->K * 3);
+  const float *dr = st.in(d_Rs, (size_t)B * NJ * 9);
+  float *db = st.out(d_beta, (size_t)B * c->NB), *dt = st.out(d_theta, (size_t)B * 72);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(smpl_backward_dev(c, B, dv, dj, dr, db, dt));
+  return st.finish();
+}
+
+extern "C" int smplb_rodrigues(smplb_ctx *c, int N, const float *theta, float *R, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(N < 1 || !theta || !R, SMPLB_EINVAL, "N >= 1 and non-null pointers required");
+  Stager st(c, mem);
+  const float *dt = st.in(theta, (size_t)N * 3);
+  float *dR = st.out(R, (size_t)N * 9);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_rodrigues(c, N, dt, dR));
+  return st.finish();
+}
+
+extern "C" int smplb_global_rigid(smplb_ctx *c, int B, const float *Rs, const float *Js, float *new_J, float *A,
+                                  int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(B < 1 || !Rs || !Js || !new_J || !A, SMPLB_EINVAL, "B >= 1 and non-null pointers required");
+  Stager st(c, mem);
+  const float *dR = st.in(Rs, (size_t)B * NJ * 9), *dJ = st.in(Js, (size_t)B * NJ * 3);
+  float *dn = st.out(new_J, (size_t)B * NJ * 3), *dA = st.out(A, (size_t)B * NJ * 16);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_global_rigid(c, B, dR, dJ, dn, dA));
+  return st.finish();
+}
+
+// --------------------------------------------------------------------------------- projection
+extern "C" int smplb_orth_proj(smplb_ctx *c, int B, int N, const float *X, const float *cam, float *out, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(B < 1 || N < 1 || !X || !cam || !out, SMPLB_EINVAL, "B, N >= 1 and non-null pointers required");
+  Stager st(c, mem);
+  const float *dX = st.in(X, (size_t)B * N * 3), *dc = st.in(cam, (size_t)B * 3);
+  float *dout = st.out(out, (size_t)B * N * 2);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_proj(c, B, N, dX, dc, 0, 0.f, 0.f, dout));
+  return st.finish();
+}
+
+extern "C" int smplb_reproject_vertices(smplb_ctx *c, int B, int N, const float *verts, const float *cam, float im_w,
+                                        float im_h, float *out, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(B < 1 || N < 1 || !verts || !cam || !out, SMPLB_EINVAL, "B, N >= 1 and non-null pointers required");
+  Stager st(c, mem);
+  const float *dX = st.in(verts, (size_t)B * N * 3), *dc = st.in(cam, (size_t)B * 3);
+  float *dout = st.out(out, (size_t)B * N * 2);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_proj(c, B, N, dX, dc, 1, im_w, im_h, dout));
+  return st.finish();
+}
+
+extern "C" int smplb_proj_backward(smplb_ctx *c, int B, int N, const float *X, const float *cam, const float *d_out,
+                                   int pixel, float im_w, float im_h, float *d_X, float *d_cam, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(B < 1 || N < 1 || !X || !cam || !d_out, SMPLB_EINVAL, "B, N >= 1 and non-null X, cam, d_out required");
+  Stager st(c, mem);
+  const float *dX = st.in(X, (size_t)B * N * 3), *dc = st.in(cam, (size_t)B * 3), *dd = st.in(d_out, (size_t)B * N * 2);
+  float *oX = st.out(d_X, (size_t)B * N * 3), *oc = st.out(d_cam, (size_t)B * 3);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_proj_bwd(c, B, N, dX, dc, dd, pixel, im_w, im_h, 1.0f, nullptr, 0, oX, oc));
+  return st.finish();
+}
+
+// -------------------------------------------------------------------------------------- losses
+extern "C" int smplb_kp_loss(smplb_ctx *c, int B, int K, const float *kp_gt, const float *kp_pred, float *abs_sum,
+                             int64_t *num_present, float *d_kp_pred, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(B < 1 || K < 1 || !kp_gt || !kp_pred || !abs_sum || !num_present, SMPLB_EINVAL,
+         "B, K >= 1 and non-null kp_gt, kp_pred, abs_sum, num_present required");
+  TRY(ensure_ws(c, B));
+  Stager st(c, mem);
+  const float *dg = st.in(kp_gt, (size_t)B * K * 3), *dp = st.in(kp_pred, (size_t)B * K * 2);
+  float *ds = st.out(abs_sum, 1);
+  long long *dn = (long long *)st.out(num_present, 1);
+  float *dd = st.out(d_kp_pred, (size_t)B * K * 2);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_kp_loss(c, B, K, dg, dp, dd, c->ws_part, c->ws_cnt));
+  TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, ds, dn));
+  return st.finish();
+}
+
+static int ensure_mesh_ws(smplb_ctx *c, int B, int V) {
+  size_t n = (size_t)std::max(B, c->ws_batch) * std::max(V, c->V) * 2;
+  if (n > c->ws_mesh_cap) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (void **p : {(void **)&c->ws_silpred, (void **)&c->ws_dsil, (void **)&c->ws_silcnt}) {
+      if (*p) CUDA_TRY(cudaFree(*p));
+      *p = nullptr;
+      CUDA_TRY(cudaMalloc(p, n * 4));
+    }
+    c->ws_mesh_cap = n;
+  }
+  size_t np = (size_t)B * (32 + cdiv(V, 256) + 1);
+  if (np > c->ws_mesh_part_cap) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->ws_mesh_part) CUDA_TRY(cudaFree(c->ws_mesh_part));
+    c->ws_mesh_part = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&c->ws_mesh_part, np * 4));
+    c->ws_mesh_part_cap = np;
+  }
+  return 0;
+}
+
+extern "C" int smplb_mesh_reproj_loss(smplb_ctx *c, int B, int V, const float *points_xy, const int32_t *offsets, int P,
+                                      const float *sil_pred, float *loss, float *d_sil_pred, int32_t *ind_ab,
+                                      int32_t *ind_ba, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(B < 1 || V < 1 || P < 0 || !offsets || !sil_pred || !loss || (P > 0 && !points_xy), SMPLB_EINVAL,
+         "B, V >= 1, P >= 0 and non-null offsets, sil_pred, loss required");
+  TRY(ensure_mesh_ws(c, B, V));
+  Stager st(c, mem);
+  const float *dp = st.in(points_xy, (size_t)P * 2);
+  const int32_t *dof = st.in(offsets, (size_t)B + 1);
+  const float *ds = st.in(sil_pred, (size_t)B * V * 2);
+  float *dl = st.out(loss, 1), *dg = st.out(d_sil_pred, (size_t)B * V * 2);
+  int32_t *dia = st.out(ind_ab, (size_t)P), *dib = st.out(ind_ba, (size_t)B * V);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  if (!dp) dp = c->ws_scal;  // P == 0: never dereferenced
+  TRY(launch_mesh_loss(c, B, V, dp, dof, P, ds, dl, dg, c->ws_silcnt, c->ws_mesh_part, dia, dib));
+  return st.finish();
+}
+
+extern "C" int smplb_skew(smplb_ctx *c, int N, const float *vec, float *out, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(N < 1 || !vec || !out, SMPLB_EINVAL, "N >= 1 and non-null pointers required");
+  Stager st(c, mem);
+  const float *dv = st.in(vec, (size_t)N * 3);
+  float *d_o = st.out(out, (size_t)N * 9);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_skew(c, N, dv, d_o));
+  return st.finish();
+}
+
+extern "C" int smplb_lrotmin(smplb_ctx *c, int B, const float *theta, float *out, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(B < 1 || !theta || !out, SMPLB_EINVAL, "B >= 1 and non-null pointers required");
+  Stager st(c, mem);
+  const float *dt = st.in(theta, (size_t)B * 72);
+  float *d_o = st.out(out, (size_t)B * NPF);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_lrotmin(c, B, dt, d_o));
+  return st.finish();
+}
+
+static int ensure_gp_ws(smplb_ctx *c, int M) {
+  size_t need = ((size_t)cdiv(M, 64) + 2) * SMPLB_GP_FLOATS;
+  if (need <= c->ws_gp_cap) return 0;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (c->ws_gp) CUDA_TRY(cudaFree(c->ws_gp));
+  c->ws_gp = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&c->ws_gp, need * 4));
+  c->ws_gp_cap = need;
+  return 0;
+}
+
+extern "C" int smplb_gradient_penalty(smplb_ctx *c, int M, const float *g0, const float *g1, const float *g2,
+                                      const float *g3, float *penalty, float *col_sums, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(M < 1 || !g0 || !g1 || !g2 || !g3 || !penalty, SMPLB_EINVAL, "M >= 1 and non-null g0..g3, penalty required");
+  TRY(ensure_gp_ws(c, M));
+  Stager st(c, mem);
+  const float *d0 = st.in(g0, (size_t)M * 169), *d1 = st.in(g1, (size_t)M * 42), *d2 = st.in(g2, (size_t)M * 10),
+              *d3 = st.in(g3, (size_t)M * 207);
+  float *dp = st.out(penalty, 1), *dc = st.out(col_sums, SMPLB_GP_FLOATS);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  float *sums = dc ? dc : c->ws_gp + (size_t)cdiv(M, 64) * SMPLB_GP_FLOATS;
+  TRY(launch_gp_colsum(c, M, d0, d1, d2, d3, sums));
+  TRY(launch_gp_final(c, (long long)M, sums, dp));
+  return st.finish();
+}
+
+extern "C" int smplb_gradient_penalty_from_sums(smplb_ctx *c, int64_t M_total, const float *col_sums, float *penalty,
+                                                int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(M_total < 1 || !col_sums || !penalty, SMPLB_EINVAL, "M_total >= 1 and non-null pointers required");
+  Stager st(c, mem);
+  const float *dc = st.in(col_sums, SMPLB_GP_FLOATS);
+  float *dp = st.out(penalty, 1);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_gp_final(c, (long long)M_total, dc, dp));
+  return st.finish();
+}
+
+extern "C" int smplb_gradient_penalty_backward(smplb_ctx *c, int M, int64_t M_total, const float *col_sums, float *d_g0,
+                                               float *d_g1, float *d_g2, float *d_g3, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(M < 1 || M_total < 1 || !col_sums, SMPLB_EINVAL, "M, M_total >= 1 and non-null col_sums required");
+  Stager st(c, mem);
+  const float *dc = st.in(col_sums, SMPLB_GP_FLOATS);
+  float *o0 = st.out(d_g0, (size_t)M * 169), *o1 = st.out(d_g1, (size_t)M * 42), *o2 = st.out(d_g2, (size_t)M * 10),
+        *o3 = st.out(d_g3, (size_t)M * 207);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_gp_bwd(c, M, (long long)M_total, dc, o0, o1, o2, o3));
+  return st.finish();
+}
+
+// ---------------------------------------------------------------------------------- fused step
+extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *theta, const float *cam,
+                          const float *kp_gt, const float *points_xy, const int32_t *offsets, int P, float w_kp,
+                          float w_mesh, float img_size, int64_t kp_count_override, float *verts, float *joints, float *Rs,
+                          float *kp_pred, float *loss_parts, float *d_beta, float *d_theta, float *d_cam, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(B < 1 || !beta || !theta || !cam || !kp_gt || !loss_parts, SMPLB_EINVAL,
+         "B >= 1 and non-null beta, theta, cam, kp_gt, loss_parts required");
+  bool have_mesh = offsets != nullptr;
+  bool bwd = d_beta || d_theta || d_cam;
+  RET_IF(bwd && !(d_beta && d_theta && d_cam), SMPLB_EINVAL, "d_beta, d_theta, d_cam must be all set or all NULL");
+  RET_IF(have_mesh && P > 0 && !points_xy, SMPLB_EINVAL, "points_xy is NULL but P > 0");
+  TRY(ensure_ws(c, B));
+  if (have_mesh) TRY(ensure_mesh_ws(c, B, c->V));
+  int K = c->K;
+  Stager st(c, mem);
+  const float *dbeta = st.in(beta, (size_t)B * c->NB), *dtheta = st.in(theta, (size_t)B * 72);
+  const float *dcam = st.in(cam, (size_t)B * 3), *dkpgt = st.in(kp_gt, (size_t)B * K * 3);
+  const float *dpts = have_mesh ? st.in(points_xy, (size_t)P * 2) : nullptr;
+  const int32_t *doff = have_mesh ? st.in(offsets, (size_t)B + 1) : nullptr;
+  float *overts = st.out(verts, (size_t)B * c->V3), *ojoints = st.out(joints, (size_t)B * K * 3);
+  float *oRs = st.out(Rs, (size_t)B * NJ * 9), *okp = st.out(kp_pred, (size_t)B * K * 2);
+  float *oloss = st.out(loss_parts, 4);
+  float *odb = st.out(d_beta, (size_t)B * c->NB), *odt = st.out(d_theta, (size_t)B * 72), *odc = st.out(d_cam, (size_t)B * 3);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  if (have_mesh && !dpts) dpts = c->ws_scal;
+
+  float *jbuf = ojoints ? ojoints : c->ws_joints;
+  TRY(smpl_forward_dev(c, B, dbeta, dtheta, overts, jbuf, oRs, nullptr, dcam, dkpgt, okp ? okp : c->ws_kp, true));
+  const float *vbuf = overts ? overts : c->ws_verts;
+  TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, c->ws_scal + 0, c->ws_cnt64));
+  if (have_mesh) {
+    TRY(launch_proj(c, B, c->V, vbuf, dcam, 1, img_size, img_size, c->ws_silpred));
+    TRY(launch_mesh_loss(c, B, c->V, dpts, doff, P, c->ws_silpred, c->ws_scal + 2, bwd ? c->ws_dsil : nullptr,
+                         c->ws_silcnt, c->ws_mesh_part, nullptr, nullptr));
+  }
+  TRY(launch_finalize_loss(c, w_kp, w_mesh, (long long)kp_count_override, have_mesh ? 1 : 0, oloss));
+  if (bwd) {
+    // d kp loss -> d joints, d cam; scale w_kp / num_present (global count if overridden)
+    TRY(launch_proj_bwd(c, B, K, jbuf, dcam, c->ws_dkp, 0, 0.f, 0.f, w_kp, c->ws_cnt64, 0, c->ws_djoints, odc));
+    const float *dverts = nullptr;
+    if (have_mesh) {
+      TRY(ensure_buf(c, &c->ws_dverts, (size_t)c->ws_batch * c->V3, false));
+      TRY(launch_proj_bwd(c, B, c->V, vbuf, dcam, c->ws_dsil, 1, img_size, img_size, w_mesh, nullptr, 1, c->ws_dverts, odc));
+      dverts = c->ws_dverts;
+    }
+    TRY(smpl_backward_dev(c, B, dverts, c->ws_djoints, nullptr, odb, odt));
+  }
+  return st.finish();
+}
+
+// ------------------------------------------------------------------------------ NCCL (dlopen)
+// The only exchange on this path is a <=512-float sum (loss numerators, counts, the 428
+// gradient-penalty column sums), so NCCL is loaded lazily and is not a link-time dependency.
+typedef struct {
+  char internal[128];
+} nccl_uid_t;
+typedef int (*fn_getuid)(nccl_uid_t *);
+typedef int (*fn_initrank)(void **, int, nccl_uid_t, int);
+typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_destroy)(void *);
+typedef const char *(*fn_errstr)(int);
+static struct {
+  void *lib;
+  fn_getuid getuid;
+  fn_initrank initrank;
+  fn_allreduce allreduce;
+  fn_destroy destroy;
+  fn_errstr errstr;
+} g_nccl = {};
+
+static int nccl_load() {
+  if (g_nccl.lib) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  RET_IF(!g_nccl.lib, SMPLB_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.getuid = (fn_getuid)dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.initrank = (fn_initrank)dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.destroy = (fn_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
+  RET_IF(!g_nccl.getuid || !g_nccl.initrank || !g_nccl.allreduce || !g_nccl.destroy, SMPLB_ENCCL,
+         "libnccl is missing a required symbol");
+  return 0;
+}
+#define NCCL_TRY(expr)                                                                              \
+  do {                                                                                              \
+    int _r = (expr);                                                                                \
+    if (_r != 0) {                                                                                  \
+      smplb_set_error("%s -> NCCL error %d (%s)", #expr, _r, g_nccl.errstr ? g_nccl.errstr(_r) : "?"); \
+      return SMPLB_ENCCL;                                                                           \
+    }                                                                                               \
+  } while (0)
+
+extern "C" int smplb_comm_unique_id(void *id128) {
+  RET_IF(!id128, SMPLB_EINVAL, "null id buffer");
+  TRY(nccl_load());
+  NCCL_TRY(g_nccl.getuid((nccl_uid_t *)id128));
+  return 0;
+}
+
+extern "C" int smplb_comm_init(smplb_ctx *c, int nranks, int rank, const void *id128) {
+  CHECK_CTX(c);
+  RET_IF(nranks < 1 || rank < 0 || rank >= nranks || !id128, SMPLB_EINVAL, "bad nranks/rank/id");
+  TRY(nccl_load());
+  nccl_uid_t id;
+  memcpy(&id, id128, sizeof(id));
+  NCCL_TRY(g_nccl.initrank(&c->nccl_comm, nranks, id, rank));
+  c->nranks = nranks;
+  c->rank = rank;
+  return 0;
+}
+
+extern "C" int smplb_comm_allreduce_sum(smplb_ctx *c, float *dev_buf, int count) {
+  CHECK_CTX(c);
+  RET_IF(!dev_buf || count < 1, SMPLB_EINVAL, "null buffer or count < 1");
+  if (c->nranks == 1 && !c->nccl_comm) return 0;
+  RET_IF(!c->nccl_comm, SMPLB_ENCCL, "smplb_comm_init has not been called");
+  NCCL_TRY(g_nccl.allreduce(dev_buf, dev_buf, (size_t)count, /*ncclFloat*/ 7, /*ncclSum*/ 0, c->nccl_comm, c->stream));
+  return 0;
+}
+
+extern "C" int smplb_comm_destroy(smplb_ctx *c) {
+  if (!c || !c->nccl_comm) return 0;
+  if (g_nccl.destroy) g_nccl.destroy(c->nccl_comm);
+  c->nccl_comm = nullptr;
+  c->nranks = 1;
+  c->rank = 0;
+  return 0;
+}

@@ -1,0 +1,180 @@
+// Internal declarations shared by the kernel translation units of libsmplb.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "smplb.h"
+
+#define NJ 24          // SMPL joints
+#define NPF 207        // pose-feature length, 23 * 9
+#define KX 224         // padded length of x_ext = [pose_feature(207) | beta(NB) | 1 | 0...]
+#define VSPLIT 4       // vertex-range splits of the skinning backward (fixed-order partial sums)
+#define MAXK SMPLB_MAX_KEYPOINTS
+
+struct Tree {
+  signed char parent[NJ];
+  signed char depth[NJ];
+  int max_depth;
+};
+
+struct ProfRec {
+  const char *name;
+  cudaEvent_t e0, e1;
+};
+
+struct smplb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int V = 0, NB = 0, K = 0, max_batch = 0;
+  int V3 = 0;       // 3V
+  int pitch = 0;    // row pitch (floats) of v_posed / dp / Dext: 3V rounded up to 128
+  int ksplit = 1;   // split-K factor of the blend backward GEMM
+  Tree tree;
+  // ---- constants on the device
+  float *d_vt = nullptr, *d_shapedirs = nullptr, *d_posedirs = nullptr;
+  float *d_W = nullptr, *d_JR = nullptr;
+  float *d_Dext = nullptr;   // [KX][pitch]: rows 0..206 posedirs, 207..207+NB-1 shapedirs, 207+NB v_template
+  float *d_J0 = nullptr;     // [24*3]      J_regressor^T v_template
+  float *d_Jdirs = nullptr;  // [24*3][NB]  J_regressor^T shapedirs
+  int *d_kcsr_off = nullptr, *d_kcsr_idx = nullptr;  // joint_regressor by keypoint (forward gather)
+  float *d_kcsr_val = nullptr;
+  int *d_vcsr_off = nullptr, *d_vcsr_k = nullptr;    // joint_regressor by vertex (backward)
+  float *d_vcsr_val = nullptr;
+  // ---- workspace, sized for max_batch (grown on demand)
+  int ws_batch = 0;
+  float *ws_x = nullptr;       // [B][KX]
+  float *ws_Rs = nullptr;      // [B][24][9]
+  float *ws_J = nullptr;       // [B][24][3]
+  float *ws_A = nullptr;       // [B][24][12]  rows (R r0 r1 r2 | t)
+  float *ws_Jtr = nullptr;     // [B][24][3]
+  float *ws_vposed = nullptr;  // [B][pitch]
+  float *ws_verts = nullptr;   // [B][3V]   used when the caller does not ask for verts
+  float *ws_joints = nullptr;  // [B][K][3]
+  float *ws_kp = nullptr;      // [B][K][2]
+  float *ws_dkp = nullptr;     // [B][K][2]  unscaled d loss / d kp_pred
+  float *ws_djoints = nullptr; // [B][K][3]
+  float *ws_dverts = nullptr;  // [B][3V]
+  float *ws_silpred = nullptr; // [B][V][2]
+  float *ws_dsil = nullptr;    // [B][V][2]
+  int *ws_silcnt = nullptr;    // [B][V][2] integer sign sums of the pixel->vertex term
+  float *ws_dp = nullptr;      // [B][pitch]
+  float *ws_dA = nullptr;      // [VSPLIT][B][288]
+  float *ws_dx = nullptr;      // [ksplit][B][KX]
+  float *ws_part = nullptr;    // per-body / per-block float partials
+  int *ws_cnt = nullptr;       // per-body int partials
+  float *ws_scal = nullptr;    // small device scalars: [0]=kp abs_sum [2]=mesh [3]=total
+  long long *ws_cnt64 = nullptr;  // [0] = kp num_present
+  float *ws_theta = nullptr, *ws_beta = nullptr;   // copies kept for backward
+  float *ws_gp = nullptr;      // gradient-penalty partials
+  size_t ws_gp_cap = 0;        // floats
+  float *ws_mesh_part = nullptr;   // mesh-loss per-CTA partials
+  size_t ws_mesh_part_cap = 0;
+  size_t ws_mesh_cap = 0;      // elements of ws_silpred / ws_dsil / ws_silcnt
+  int saved_B = 0;
+  unsigned attr_done = 0;   // bit i: cudaFuncSetAttribute done for kernel i on this device
+  // ---- misc
+  void *flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  cudaEvent_t timer0[16] = {}, timer1[16] = {};
+  int64_t launches = 0;
+  bool profile = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
+  // NCCL (dlopen'ed)
+  void *nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+void smplb_set_error(const char *fmt, ...);
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      smplb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));     \
+      return SMPLB_ECUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+#define RET_IF(cond, code, ...)   \
+  do {                            \
+    if (cond) {                   \
+      smplb_set_error(__VA_ARGS__); \
+      return (code);              \
+    }                             \
+  } while (0)
+
+#define TRY(expr)          \
+  do {                     \
+    int _r = (expr);       \
+    if (_r != 0) return _r; \
+  } while (0)
+
+struct ProfScope {
+  smplb_ctx *c;
+  ProfRec r;
+  ProfScope(smplb_ctx *ctx, const char *name);
+  ~ProfScope();
+};
+
+// Launch helper: counts launches, optional per-kernel event timing, checks the launch.
+#define LAUNCH(ctx, name, grid, block, smem, kernel, ...)                                   \
+  do {                                                                                      \
+    {                                                                                       \
+      ProfScope _ps((ctx), (name));                                                         \
+      kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                      \
+    }                                                                                       \
+    (ctx)->launches++;                                                                      \
+    cudaError_t _le = cudaGetLastError();                                                   \
+    if (_le != cudaSuccess) {                                                               \
+      smplb_set_error("launch %s failed: %s", (name), cudaGetErrorString(_le));             \
+      return SMPLB_ECUDA;                                                                   \
+    }                                                                                       \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+#ifdef __CUDACC__
+__device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; }
+#endif
+
+// ---- kernel launchers (device pointers only), one per stage -------------------------------
+// k_pose.cu
+int launch_pose_fwd(smplb_ctx *c, int B, const float *beta, const float *theta, float *Rs, float *J, float *A,
+                    float *Jtr, float *x);
+int launch_pose_bwd(smplb_ctx *c, int B, const float *theta, const float *Rs, const float *J, const float *A,
+                    const float *dA_part, const float *dx_part, int ksplit, const float *d_Rs, float *d_beta,
+                    float *d_theta);
+int launch_rodrigues(smplb_ctx *c, int N, const float *theta, float *R);
+int launch_global_rigid(smplb_ctx *c, int B, const float *Rs, const float *Js, float *new_J, float *A44);
+int launch_skew(smplb_ctx *c, int N, const float *vec, float *out);
+int launch_lrotmin(smplb_ctx *c, int B, const float *theta, float *out);
+// k_blend.cu
+int launch_blend_fwd(smplb_ctx *c, int B, const float *x, float *v_posed);
+int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part);
+// k_skin.cu
+int launch_skin_fwd(smplb_ctx *c, int B, const float *A, const float *v_posed, float *verts);
+int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, const float *kp_gt, float *joints,
+                  float *kp_pred, float *dkp, float *part, int *cnt);
+int launch_skin_bwd(smplb_ctx *c, int B, const float *A, const float *v_posed, const float *d_verts,
+                    const float *d_joints, float *dp, float *dA_part);
+int launch_proj(smplb_ctx *c, int B, int N, const float *X, const float *cam, int pixel, float im_w, float im_h,
+                float *out);
+int launch_proj_bwd(smplb_ctx *c, int B, int N, const float *X, const float *cam, const float *d_out, int pixel,
+                    float im_w, float im_h, float gscale, const long long *den, int accumulate_cam, float *d_X,
+                    float *d_cam);
+// k_loss.cu
+int launch_kp_loss(smplb_ctx *c, int B, int K, const float *kp_gt, const float *kp_pred, float *dkp, float *part,
+                   int *cnt);
+int launch_reduce_kp(smplb_ctx *c, int B, const float *part, const int *cnt, float *abs_sum, long long *num_present);
+int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *offsets, int P, const float *sil_pred,
+                     float *loss, float *d_sil_pred, int *cnt_scratch, float *part_scratch, int *ind_ab, int *ind_ba);
+int launch_finalize_loss(smplb_ctx *c, float w_kp, float w_mesh, long long count_override, int have_mesh,
+                         float *loss_parts);
+int launch_gp_colsum(smplb_ctx *c, int M, const float *g0, const float *g1, const float *g2, const float *g3,
+                     float *col_sums);
+int launch_gp_final(smplb_ctx *c, long long M_total, const float *col_sums, float *penalty);
+int launch_gp_bwd(smplb_ctx *c, int M, long long M_total, const float *col_sums, float *d0, float *d1, float *d2,
+                  float *d3);

@@ -65,3 +65,13 @@ def rel_err(a, ref):
     a = np.asarray(a, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     return float(np.max(np.abs(a - ref)) / max(float(np.max(np.abs(ref))), 1e-30))
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """libsmplb.so is built in-tree (nvcc cross-compiles without a GPU)."""
+    from hpe_b200._lib import LIB_PATH
+    if not os.path.isfile(LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return LIB_PATH

@@ -1,0 +1,316 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (ctypes facade),
+against (a) the committed golden vectors produced by the reference's own code
+and (b) the fp64 numpy oracle on fresh seeded inputs.
+
+Tolerance: fp32 kernels must satisfy
+max|x - ref| <= 1e-4 * max|ref| per tensor against the fp64 oracle; masking
+and counts are bit-exact.  Nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from hpe_b200 import ops, runtime, synthetic
+from hpe_b200.tf_smpl import batch_lbs, projection
+from hpe_b200.tf_smpl.batch_smpl import SMPL
+from oracle import smpl_numpy as onp
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def smpl_small(small_model):
+    return SMPL(small_model, max_batch=8)
+
+
+@pytest.fixture(scope="module")
+def smpl_full(full_model):
+    return SMPL(full_model, max_batch=64)
+
+
+def f64(d, *keys):
+    return [d[k].astype(np.float64) for k in keys]
+
+
+# ------------------------------------------------------------------ golden vectors
+def test_forward_golden_small(smpl_small, golden_small):
+    g = golden_small
+    verts, joints, Rs = smpl_small(g["beta"], g["theta"], get_skin=True)
+    assert verts.dtype == np.float32 and verts.shape == g["verts"].shape
+    assert rel_err(verts, g["verts"]) < TOL
+    assert rel_err(joints, g["joints"]) < TOL
+    assert rel_err(Rs, g["Rs"]) < TOL
+    assert rel_err(smpl_small.J_transformed, g["J_transformed"]) < TOL
+    # get_skin=False returns joints only (batch_smpl.py:157-160)
+    j2 = smpl_small(g["beta"], g["theta"])
+    assert np.array_equal(j2, joints)
+    # theta == 0 (sample 0): Rs is exactly the identity
+    assert np.array_equal(Rs[0], np.broadcast_to(np.eye(3, dtype=np.float32), (24, 3, 3)))
+
+
+def test_forward_golden_full(smpl_full, golden_full):
+    g = golden_full
+    st = int(g["vert_stride"])
+    verts, joints, Rs = smpl_full(g["beta"], g["theta"], get_skin=True)
+    assert rel_err(verts[:, ::st], g["verts_sub"]) < TOL
+    assert rel_err(joints, g["joints"]) < TOL
+    assert rel_err(Rs, g["Rs"]) < TOL
+    assert rel_err(smpl_full.J_transformed, g["J_transformed"]) < TOL
+
+
+def test_forward_lsp(small_model, golden_small_lsp):
+    g = golden_small_lsp
+    s = SMPL(small_model, joint_type="lsp", max_batch=4)
+    joints = s(g["beta"], g["theta"])
+    assert joints.shape == (3, 14, 3)
+    assert rel_err(joints, g["joints"]) < TOL
+    out = s.step(g["beta"], g["theta"], g["cam"], g["kp_gt"], w_kp=1.0)
+    assert abs(out["loss_parts"][3] - float(g["kp_loss"])) < TOL * abs(float(g["kp_loss"]))
+    assert rel_err(out["d_beta"], g["kp_d_beta"]) < TOL
+    assert rel_err(out["d_theta"], g["kp_d_theta"]) < TOL
+    assert rel_err(out["d_cam"], g["kp_d_cam"]) < TOL
+
+
+@pytest.mark.parametrize("which", ["small", "full"])
+def test_backward_upstream_golden(which, smpl_small, smpl_full, golden_small, golden_full):
+    s, g = (smpl_small, golden_small) if which == "small" else (smpl_full, golden_full)
+    s(g["beta"], g["theta"], get_skin=True)
+    d_beta, d_theta = s.backward(g["up_verts"], g["up_joints"], g["up_Rs"])
+    assert rel_err(d_beta, g["up_d_beta"]) < TOL
+    assert rel_err(d_theta, g["up_d_theta"]) < TOL
+
+
+@pytest.mark.parametrize("which", ["small", "full"])
+def test_step_kp_golden(which, smpl_small, smpl_full, golden_small, golden_full):
+    s, g = (smpl_small, golden_small) if which == "small" else (smpl_full, golden_full)
+    out = s.step(g["beta"], g["theta"], g["cam"], g["kp_gt"], w_kp=1.0)
+    assert rel_err(out["kp_pred"], g["kp_pred"]) < TOL
+    lp = out["loss_parts"]
+    # visibility count is bit-exact (integer) and the loss is numerator / count
+    vis = g["kp_gt"][:, :, 2]
+    assert int(lp[1]) == 2 * int(np.count_nonzero(vis))
+    assert abs(lp[3] - float(g["kp_loss"])) < TOL * abs(float(g["kp_loss"]))
+    assert rel_err(out["d_beta"], g["kp_d_beta"]) < TOL
+    assert rel_err(out["d_theta"], g["kp_d_theta"]) < TOL
+    assert rel_err(out["d_cam"], g["kp_d_cam"]) < TOL
+    # sample 1 is all-invisible: its gradients are EXACTLY zero
+    assert not out["d_beta"][1].any() and not out["d_theta"][1].any() and not out["d_cam"][1].any()
+
+
+@pytest.mark.parametrize("which", ["small", "full"])
+def test_step_kp_plus_mesh_golden(which, smpl_small, smpl_full, golden_small, golden_full):
+    """60 * kp + 0.001 * mesh, the trainer's weighting (config.py:67-68)."""
+    s, g = (smpl_small, golden_small) if which == "small" else (smpl_full, golden_full)
+    B = g["beta"].shape[0]
+    sil = ops.silhouette_csr(g["seg_points"], B)
+    out = s.step(g["beta"], g["theta"], g["cam"], g["kp_gt"], silhouette=sil, w_kp=60.0, w_mesh=0.001)
+    lp = out["loss_parts"]
+    assert abs(lp[2] - float(g["mesh_loss"])) < TOL * abs(float(g["mesh_loss"]))
+    want = 60.0 * float(g["kp_loss"]) + 0.001 * float(g["mesh_loss"])
+    assert abs(lp[3] - want) < TOL * abs(want)
+    assert rel_err(out["d_beta"], g["step_d_beta"]) < 5 * TOL      # NN index near-ties
+    assert rel_err(out["d_theta"], g["step_d_theta"]) < 5 * TOL
+    assert rel_err(out["d_cam"], g["step_d_cam"]) < 5 * TOL
+
+
+# ------------------------------------------------------------------ stand-alone ops vs oracle
+def test_batch_lbs_functions(small_model):
+    rng = np.random.default_rng(11)
+    th = (rng.normal(size=(50, 3)) * 0.8).astype(np.float32)
+    th[0] = 0
+    th[1] = [1e-9, -1e-9, 0]
+    th[2] = [3.0, -2.5, 4.0]
+    R = batch_lbs.batch_rodrigues(th)
+    assert rel_err(R, onp.batch_rodrigues(th.astype(np.float64))) < 1e-5
+    assert np.array_equal(R[0], np.eye(3, dtype=np.float32))
+    assert np.array_equal(batch_lbs.batch_skew(th), onp.batch_skew(th))       # pure data movement: bit-exact
+    theta = (rng.normal(size=(7, 72)) * 0.4).astype(np.float32)
+    assert rel_err(batch_lbs.batch_lrotmin(theta), onp.batch_lrotmin(theta.astype(np.float64))) < 1e-5
+    Rs = onp.batch_rodrigues(theta.reshape(-1, 3).astype(np.float64)).reshape(7, 24, 3, 3)
+    Js = rng.normal(size=(7, 24, 3)) * 0.3
+    parents = small_model["kintree_table"][0].astype(np.int32)
+    newJ, A = batch_lbs.batch_global_rigid_transformation(Rs.astype(np.float32), Js.astype(np.float32), parents)
+    newJ_o, A_o = onp.batch_global_rigid_transformation(Rs.astype(np.float32).astype(np.float64),
+                                                       Js.astype(np.float32).astype(np.float64), parents)
+    assert A.shape == (7, 24, 4, 4)
+    assert rel_err(newJ, newJ_o) < 1e-5 and rel_err(A, A_o) < 1e-5
+    assert np.array_equal(A[:, :, 3, :], np.broadcast_to(np.float32([0, 0, 0, 1]), (7, 24, 4)))
+
+
+def test_projection_functions():
+    rng = np.random.default_rng(12)
+    X = rng.normal(size=(5, 37, 3)).astype(np.float32)
+    cam = np.stack([rng.uniform(0.5, 1.2, 5), rng.normal(size=5) * 0.1, rng.normal(size=5) * 0.1], 1).astype(np.float32)
+    p = projection.batch_orth_proj_idrot(X, cam)
+    assert rel_err(p, onp.batch_orth_proj_idrot(X.astype(np.float64), cam.astype(np.float64))) < 1e-6
+    q = projection.reproject_vertices(X, cam, [224.0, 224.0])
+    assert rel_err(q, onp.reproject_vertices(X.astype(np.float64), cam.astype(np.float64), [224.0, 224.0])) < 1e-6
+    # linear in the scale s (SURVEY §4 invariant)
+    cam2 = cam.copy()
+    cam2[:, 0] *= 2
+    assert rel_err(projection.batch_orth_proj_idrot(X, cam2), 2 * p.astype(np.float64)) < 1e-6
+    d = rng.normal(size=(5, 37, 2)).astype(np.float32)
+    for im in (None, [224.0, 224.0]):
+        dX, dc = projection.projection_backward(X, cam, d, im)
+        if im is None:
+            dX_o, dc_o = onp.orth_proj_backward(X.astype(np.float64), cam.astype(np.float64), d.astype(np.float64))
+        else:
+            dX_o, dc_o = onp.reproject_vertices_backward(X.astype(np.float64), cam.astype(np.float64), im, d.astype(np.float64))
+        assert rel_err(dX, dX_o) < 1e-5 and rel_err(dc, dc_o) < 1e-5
+
+
+def test_kp_loss_masking_bit_exact():
+    inp = synthetic.make_inputs(33, seed=5)
+    rng = np.random.default_rng(6)
+    pred = rng.uniform(-1, 1, size=(33, 19, 2)).astype(np.float32)
+    s, n, d = ops.kp_reprojection_loss_parts(inp["kp_gt"], pred, want_grad=True)
+    vis = inp["kp_gt"][:, :, 2]
+    assert n == 2 * int(np.count_nonzero(vis))                     # integer count: exact
+    assert not d[vis == 0].any()                                   # masked terms contribute exactly 0
+    assert np.array_equal(d[vis != 0], np.sign(pred - inp["kp_gt"][:, :, :2])[vis != 0])
+    num, cnt = onp.kp_loss_parts(inp["kp_gt"].astype(np.float64), pred.astype(np.float64))
+    assert cnt == n and abs(s - num) < 1e-5 * num
+    assert abs(ops.kp_reprojection_loss(inp["kp_gt"], pred) - num / cnt) < 1e-5 * num / cnt
+    # nothing visible -> exactly 0 (div_no_nan)
+    gt0 = inp["kp_gt"].copy()
+    gt0[:, :, 2] = 0
+    assert ops.kp_reprojection_loss(gt0, pred) == 0.0
+    # the weight is the visibility VALUE, the count is vis != 0 (appendix A.7)
+    gt2 = np.zeros((1, 19, 3), np.float32)
+    gt2[0, 0] = [0.5, 0.5, 2.0]
+    assert ops.kp_reprojection_loss(gt2, np.zeros((1, 19, 2), np.float32)) == pytest.approx(1.0, rel=1e-6)
+
+
+def test_mesh_loss_vs_oracle():
+    rng = np.random.default_rng(21)
+    B, V = 4, 700
+    seg = synthetic.make_silhouettes(B, seed=9, a_range=(6, 12), b_range=(10, 20))
+    pts3 = synthetic.silhouette_points(seg)
+    sp = (rng.normal(size=(B, V, 2)) * np.array([12.0, 22.0]) + 112.0).astype(np.float32)
+    loss, g = ops.mesh_reprojection_loss(pts3, sp, B, want_grad=True)
+    lo = onp.mesh_reprojection_loss(pts3.astype(np.float64), sp.astype(np.float64), B)
+    assert abs(loss - lo) < TOL * lo
+    go = onp.mesh_loss_backward(pts3.astype(np.float64), sp.astype(np.float64), B)
+    # per-vertex gradient parity, excluding vertices whose NN choice is a near-tie
+    bad = np.abs(g - go).max(axis=2) > 1e-4 * np.abs(go).max()
+    assert bad.mean() < 0.01
+    assert not g[2].any()                                           # empty image: exactly 0
+    # single-image helpers (ops.py:60-102)
+    A = np.stack([pts3[pts3[:, 0] == 0][:, 2], pts3[pts3[:, 0] == 0][:, 1]], 1)
+    iab, iba = ops.find_nearest_neighbors(A, sp[0])
+    oab, oba = onp.find_nearest_neighbors(A.astype(np.float32), sp[0])
+    assert (iab == oab).mean() > 0.99 and (iba == oba).mean() > 0.99
+    bd = ops.bidirectional_dist(A, sp[0])
+    assert abs(bd - onp.bidirectional_dist(A.astype(np.float64), sp[0].astype(np.float64))) < TOL * bd
+    # exact-tie rule: duplicated vertices -> the FIRST index wins (tf.argmin)
+    spd = np.concatenate([sp[0, :5], sp[0, :5]], 0)
+    iab, _ = ops.find_nearest_neighbors(A, spd)
+    assert iab.max() < 5
+
+
+def test_gradient_penalty(golden_small):
+    g = golden_small
+    gin = [g["gp_in%d" % i] for i in range(4)]
+    pen, sums = ops.compute_gradient_penalty(gin, want_sums=True)
+    assert abs(pen - float(g["gp_penalty"])) < TOL * float(g["gp_penalty"])
+    M = gin[0].shape[0]
+    want = np.concatenate([x.reshape(M, -1).astype(np.float64).sum(0) for x in gin])
+    assert rel_err(sums, want) < 1e-5
+    assert abs(ops.gradient_penalty_from_sums(sums, M) - pen) < 1e-6 * pen
+    for i, d in enumerate(ops.gradient_penalty_backward(sums, M)):
+        assert d.shape == gin[i].shape
+        assert rel_err(d, g["gp_grad%d" % i]) < TOL
+    # sharded == whole: the sums of two halves add up (what the NCCL all-reduce does)
+    h = M // 2
+    _, s1 = ops.compute_gradient_penalty([x[:h] for x in gin], want_sums=True)
+    _, s2 = ops.compute_gradient_penalty([x[h:] for x in gin], want_sums=True)
+    assert abs(ops.gradient_penalty_from_sums(s1 + s2, M) - pen) < 1e-5 * pen
+
+
+# ------------------------------------------------------------------ fresh inputs vs oracle, edge sizes
+@pytest.mark.parametrize("B", [1, 5, 33, 129])
+def test_step_fresh_inputs_vs_oracle(B, smpl_full, full_model):
+    inp = synthetic.make_inputs(B, seed=500 + B)
+    out = smpl_full.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"], w_kp=1.0)
+    o = onp.SMPL(full_model, dtype=np.float64)
+    b = {k: v.astype(np.float64) for k, v in inp.items()}
+    verts, joints, Rs = o(b["beta"], b["theta"], get_skin=True)
+    kp = onp.batch_orth_proj_idrot(joints, b["cam"])
+    assert rel_err(out["verts"], verts) < TOL and rel_err(out["joints"], joints) < TOL and rel_err(out["Rs"], Rs) < TOL
+    num, cnt = onp.kp_loss_parts(b["kp_gt"], kp)
+    assert int(out["loss_parts"][1]) == cnt
+    if cnt == 0:
+        assert out["loss_parts"][3] == 0.0 and not out["d_theta"].any()
+        return
+    assert abs(out["loss_parts"][3] - num / cnt) < TOL * num / cnt
+    dj, dcam = onp.orth_proj_backward(joints, b["cam"], onp.kp_loss_backward(b["kp_gt"], kp))
+    db, dth = onp.smpl_backward(o, b["beta"], b["theta"], None, dj, None)
+    assert rel_err(out["d_beta"], db) < TOL and rel_err(out["d_theta"], dth) < TOL and rel_err(out["d_cam"], dcam) < TOL
+
+
+def test_rank1_theta_and_batch1(smpl_full, full_model):
+    """data_loader.py:141 calls SMPL with beta [1,10] and theta [72]."""
+    inp = synthetic.make_inputs(3, seed=77)
+    verts, joints, Rs = smpl_full(inp["beta"][2:3], inp["theta"][2], get_skin=True)
+    o = onp.SMPL(full_model, dtype=np.float64)
+    v, j, R = o(inp["beta"][2:3].astype(np.float64), inp["theta"][2:3].astype(np.float64), get_skin=True)
+    assert verts.shape == (1, 6890, 3) and rel_err(verts, v) < TOL and rel_err(joints, j) < TOL
+
+
+def test_device_arrays_match_host_path_bit_exact(smpl_full):
+    inp = synthetic.make_inputs(16, seed=88)
+    ctx = smpl_full.ctx
+    host = smpl_full.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"])
+    dev = smpl_full.step(ctx.to_device(inp["beta"]), ctx.to_device(inp["theta"]), ctx.to_device(inp["cam"]),
+                         ctx.to_device(inp["kp_gt"]))
+    for k in ("verts", "joints", "Rs", "kp_pred", "loss_parts", "d_beta", "d_theta", "d_cam"):
+        assert isinstance(dev[k], runtime.DeviceArray)
+        assert np.array_equal(dev[k].numpy(), host[k]), k
+    with pytest.raises(TypeError):
+        smpl_full(ctx.to_device(inp["beta"]), inp["theta"])          # mixing kinds is an error
+
+
+def test_backward_requires_matching_forward(smpl_small, golden_small):
+    from hpe_b200 import SmplbError
+    smpl_small(golden_small["beta"], golden_small["theta"])
+    with pytest.raises(SmplbError) as ei:
+        smpl_small.backward(d_joints=np.zeros((2, 19, 3), np.float32))
+    assert ei.value.code == -4
+
+
+# ------------------------------------------------------------------ BASELINE sizes: properties
+def test_full_size_properties(full_model):
+    """B = 4096 (BASELINE config 2): determinism, shard-equivalence and
+    identity-pose invariants, which need no oracle run at that size."""
+    B = 4096
+    s = SMPL(full_model, max_batch=B)
+    inp = synthetic.make_inputs(B, seed=1000)
+    inp["theta"][7] = 0.0
+    a = s.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"])
+    a = {k: np.array(v) for k, v in a.items()}
+    b = s.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"])
+    for k in a:
+        assert np.array_equal(a[k], b[k]), "run-to-run nondeterminism in %s" % k
+    assert np.isfinite(a["verts"]).all() and np.isfinite(a["d_theta"]).all()
+    # per-sample outputs do not depend on the batch they are computed in; the loss numerators
+    # and counts of two shards add up to the whole (the multi-GPU reduction)
+    h = B // 2
+    tot = int(a["loss_parts"][1])
+    lo = {k: np.array(v) for k, v in s.step(inp["beta"][:h], inp["theta"][:h], inp["cam"][:h], inp["kp_gt"][:h],
+                                            kp_count_override=tot).items()}
+    hi = {k: np.array(v) for k, v in s.step(inp["beta"][h:], inp["theta"][h:], inp["cam"][h:], inp["kp_gt"][h:],
+                                            kp_count_override=tot).items()}
+    for k in ("verts", "joints", "Rs", "kp_pred", "d_beta", "d_theta", "d_cam"):
+        assert np.array_equal(np.concatenate([lo[k], hi[k]]), a[k]), k
+    assert int(lo["loss_parts"][1]) + int(hi["loss_parts"][1]) == tot
+    assert abs(lo["loss_parts"][0] + hi["loss_parts"][0] - a["loss_parts"][0]) < 1e-5 * a["loss_parts"][0]
+    # identity pose: Rs == I exactly and verts == (sum_j W_vj) * v_shaped up to fp32 rounding
+    assert np.array_equal(a["Rs"][7], np.broadcast_to(np.eye(3, dtype=np.float32), (24, 3, 3)))
+    o = onp.SMPL(full_model, dtype=np.float64)
+    v_shaped = (inp["beta"][7].astype(np.float64) @ o.shapedirs).reshape(-1, 3) + o.v_template
+    assert rel_err(a["verts"][7], v_shaped) < 1e-5
+    # spot-check 3 samples of the big batch against the oracle
+    idx = [0, 1234, 4095]
+    v, j, R = o(inp["beta"][idx].astype(np.float64), inp["theta"][idx].astype(np.float64), get_skin=True)
+    assert rel_err(a["verts"][idx], v) < TOL and rel_err(a["joints"][idx], j) < TOL
