@@ -47,7 +47,8 @@ __global__ void k_kp_loss(int B, int K, const float *__restrict__ kp_gt, const f
 
 // Sum of the per-body partials: one block, fixed order.
 __global__ void __launch_bounds__(1024) k_reduce_kp(int B, const float *__restrict__ part, const int *__restrict__ cnt,
-                                                    float *__restrict__ abs_sum, long long *__restrict__ num_present) {
+                                                    float *__restrict__ abs_sum, long long *__restrict__ num_present,
+                                                    float *__restrict__ cnt_as_float) {
   __shared__ float red[1024];
   __shared__ long long redc[1024];
   int t = threadIdx.x;
@@ -70,22 +71,25 @@ __global__ void __launch_bounds__(1024) k_reduce_kp(int B, const float *__restri
   if (t == 0) {
     *abs_sum = red[0];
     *num_present = redc[0];
+    if (cnt_as_float) *cnt_as_float = (float)redc[0];   // exact below 2^24; the all-reduced form
   }
 }
 
-// loss_parts = {kp abs_sum, kp num_present (as float), mesh sum, w_kp * kp/num + w_mesh * mesh}
+// scal = {kp abs_sum, kp num_present as float, mesh sum} -- already all-reduced over the ranks
+// when a communicator is attached.  loss_parts = {abs_sum, num_present, mesh sum,
+// w_kp * abs_sum / num_present + w_mesh * mesh}; kp_cnt receives the count the backward
+// divides by (count_override > 0 wins: single-process emulation of shards).
 __global__ void k_finalize_loss(float w_kp, float w_mesh, long long count_override, int have_mesh,
-                                const float *__restrict__ kp_sum, long long *__restrict__ kp_cnt,
-                                const float *__restrict__ mesh, float *__restrict__ out) {
-  long long local = *kp_cnt;
-  long long den = count_override > 0 ? count_override : local;
-  float kp = den > 0 ? *kp_sum / (float)den : 0.0f;
-  float ml = have_mesh ? *mesh : 0.0f;
-  out[0] = *kp_sum;
-  out[1] = (float)local;
+                                const float *__restrict__ scal, long long *__restrict__ kp_cnt,
+                                float *__restrict__ out) {
+  long long den = count_override > 0 ? count_override : (long long)scal[1];
+  float kp = den > 0 ? scal[0] / (float)den : 0.0f;
+  float ml = have_mesh ? scal[2] : 0.0f;
+  out[0] = scal[0];
+  out[1] = scal[1];
   out[2] = ml;
   out[3] = w_kp * kp + w_mesh * ml;
-  *kp_cnt = den;   // the backward divides by the (possibly global) count
+  *kp_cnt = den;
 }
 
 // ------------------------------------------------------------------------------- mesh loss
@@ -322,15 +326,16 @@ int launch_kp_loss(smplb_ctx *c, int B, int K, const float *kp_gt, const float *
   return 0;
 }
 
-int launch_reduce_kp(smplb_ctx *c, int B, const float *part, const int *cnt, float *abs_sum, long long *num_present) {
-  LAUNCH(c, "reduce_kp", 1, 1024, 0, k_reduce_kp, B, part, cnt, abs_sum, num_present);
+int launch_reduce_kp(smplb_ctx *c, int B, const float *part, const int *cnt, float *abs_sum, long long *num_present,
+                     float *cnt_as_float) {
+  LAUNCH(c, "reduce_kp", 1, 1024, 0, k_reduce_kp, B, part, cnt, abs_sum, num_present, cnt_as_float);
   return 0;
 }
 
 int launch_finalize_loss(smplb_ctx *c, float w_kp, float w_mesh, long long count_override, int have_mesh,
                          float *loss_parts) {
-  LAUNCH(c, "finalize_loss", 1, 1, 0, k_finalize_loss, w_kp, w_mesh, count_override, have_mesh, c->ws_scal + 0,
-         c->ws_cnt64, c->ws_scal + 2, loss_parts);
+  LAUNCH(c, "finalize_loss", 1, 1, 0, k_finalize_loss, w_kp, w_mesh, count_override, have_mesh, c->ws_scal,
+         c->ws_cnt64, loss_parts);
   return 0;
 }
 

@@ -599,7 +599,7 @@ extern "C" int smplb_kp_loss(smplb_ctx *c, int B, int K, const float *kp_gt, con
   float *dd = st.out(d_kp_pred, (size_t)B * K * 2);
   RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
   TRY(launch_kp_loss(c, B, K, dg, dp, dd, c->ws_part, c->ws_cnt));
-  TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, ds, dn));
+  TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, ds, dn, nullptr));
   return st.finish();
 }
 
@@ -755,11 +755,16 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
   float *jbuf = ojoints ? ojoints : c->ws_joints;
   TRY(smpl_forward_dev(c, B, dbeta, dtheta, overts, jbuf, oRs, nullptr, dcam, dkpgt, okp ? okp : c->ws_kp, true));
   const float *vbuf = overts ? overts : c->ws_verts;
-  TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, c->ws_scal + 0, c->ws_cnt64));
+  TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, c->ws_scal + 0, c->ws_cnt64, c->ws_scal + 1));
   if (have_mesh) {
     TRY(launch_proj(c, B, c->V, vbuf, dcam, 1, img_size, img_size, c->ws_silpred));
     TRY(launch_mesh_loss(c, B, c->V, dpts, doff, P, c->ws_silpred, c->ws_scal + 2, bwd ? c->ws_dsil : nullptr,
                          c->ws_silcnt, c->ws_mesh_part, nullptr, nullptr));
+  }
+  if (c->nccl_comm && c->nranks > 1) {
+    // the path's one exchange: {kp numerator, kp count, mesh sum} summed over the batch shards
+    if (!have_mesh) CUDA_TRY(cudaMemsetAsync(c->ws_scal + 2, 0, 4, c->stream));
+    TRY(smplb_comm_allreduce_sum(c, c->ws_scal, 3));
   }
   TRY(launch_finalize_loss(c, w_kp, w_mesh, (long long)kp_count_override, have_mesh ? 1 : 0, oloss));
   if (bwd) {

@@ -182,7 +182,9 @@ int smplb_gradient_penalty_backward(smplb_ctx *ctx, int M, int64_t M_total, cons
  *        all-reduced count, which depends only on kp_gt) else the local count.
  *   out: verts [B,V,3] (may be NULL only if no mesh loss), joints [B,K,3], Rs [B,24,3,3]
  *        (may be NULL), kp_pred [B,K,2] (may be NULL),
- *        loss_parts [4] = {kp abs_sum, kp num_present, mesh loss sum, total weighted loss}
+ *        loss_parts [4] = {kp abs_sum, kp num_present, mesh loss sum, total weighted loss};
+ *        with a communicator attached (smplb_comm_init, nranks > 1) the first three are
+ *        all-reduced over the ranks inside the call and the gradients use the global count
  *        d_beta [B,10], d_theta [B,72], d_cam [B,3] (all three may be NULL == forward only) */
 int smplb_step(smplb_ctx *ctx, int B, const float *beta, const float *theta, const float *cam,
                const float *kp_gt, const float *points_xy, const int32_t *offsets, int P, float w_kp,

@@ -268,13 +268,16 @@ def smpl_backward(smpl, beta, theta, d_verts=None, d_joints=None, d_Rs=None):
     if d_verts is not None:
         g = g + np.asarray(d_verts, dtype=dt)
     if d_joints is not None:
-        g = g + np.einsum("vk,bkc->bvc", smpl.joint_regressor, np.asarray(d_joints, dtype=dt))
+        g = g + np.matmul(smpl.joint_regressor, np.asarray(d_joints, dtype=dt))       # [V,K] @ [B,K,3]
     W = smpl.weights
     AR, At = A[:, :, :3, :3], A[:, :, :3, 3]
-    dAR = np.einsum("vj,bvr,bvc->bjrc", W, g, v_posed)
-    dAt = np.einsum("vj,bvr->bjr", W, g)
-    TR = np.einsum("vj,bjrc->bvrc", W, AR)
-    dp = np.einsum("bvrc,bvr->bvc", TR, g)
+    # T = W A, verts = T [p;1]  =>  dT = g (x) [p;1],  dA = W^T dT,  dp = T_R^T g
+    ph = np.concatenate([v_posed, np.ones((B, V, 1), dtype=dt)], axis=2)
+    dT = (g[:, :, :, None] * ph[:, :, None, :]).reshape(B, V, 12)
+    dA = np.matmul(W.T, dT).reshape(B, 24, 3, 4)
+    dAR, dAt = dA[:, :, :, :3], dA[:, :, :, 3]
+    TR = np.matmul(W, np.ascontiguousarray(AR).reshape(B, 24, 9)).reshape(B, V, 3, 3)
+    dp = np.sum(TR * g[:, :, :, None], axis=2)
     # global transforms Rg, tg from A: A_R = Rg, A_t = tg - Rg J
     Rg = AR
     dRg = dAR - np.einsum("bjr,bjc->bjrc", dAt, J)
@@ -299,7 +302,7 @@ def smpl_backward(smpl, beta, theta, d_verts=None, d_joints=None, d_Rs=None):
     if d_Rs is not None:
         dR = dR + np.asarray(d_Rs, dtype=dt).reshape(B, 24, 3, 3)
     # v_shaped receives dp (through v_posed) and J_regressor^T dJ
-    dvs = dp + np.einsum("vj,bjc->bvc", smpl.J_regressor, dJ)
+    dvs = dp + np.matmul(smpl.J_regressor, dJ)                                        # [V,24] @ [B,24,3]
     d_beta = np.matmul(dvs.reshape(B, V * 3), smpl.shapedirs.T)
     d_theta = rodrigues_backward(theta.reshape(-1, 3), dR.reshape(-1, 3, 3)).reshape(B, 72)
     return d_beta, d_theta
