@@ -45,6 +45,7 @@ SIGNATURES = {
     "smplb_launch_count": [_P, C.POINTER(_L)],
     "smplb_profile_enable": [_P, _I],
     "smplb_profile_read": [_P, C.c_char_p, _SZ],
+    "smplb_debug_set": [_P, C.c_char_p, _I],
     "smplb_smpl_forward": [_P, _I, _P, _P, _P, _P, _P, _P, _I],
     "smplb_smpl_backward": [_P, _I, _P, _P, _P, _P, _P, _I],
     "smplb_rodrigues": [_P, _I, _P, _P, _I],

@@ -1,0 +1,411 @@
+// Blend-shape contraction on the 5th-generation tensor cores (tcgen05 + TMEM, TMA-fed).
+//
+//   v_posed[b, n] = 2^-s * sum_k x16[b,k] * Dt16[n,k]          (batch_smpl.py:110-112, :126-132)
+//
+// Operands are fp16 (same 11-bit significand as tf32, at twice the rate) with fp32
+// accumulation in TMEM.  The K axis (256 = 4 swizzle atoms of 64) carries
+//   k   0..206  pose_feature            x posedirs * 2^s
+//   k 207..216  beta_hi                 x shapedirs_hi * 2^s     } split-precision terms: the
+//   k 217..226  beta_hi                 x shapedirs_lo * 2^s     } shape blend and the template
+//   k 227..236  beta_lo                 x shapedirs_hi * 2^s     } are ~1 m and must keep fp32
+//   k 237..239  1, 1, 1                 x v_template hi/mid/lo   } accuracy
+//   k 240..255  0
+// 2^s is a power of two chosen at create time so the constants sit in fp16's normal range;
+// the epilogue multiplies by 2^-s (exact).
+//
+// Kernel shape: persistent, one CTA per SM, warp-specialised:
+//   warp 0   TMA producer (x16 tile per output tile, Dt16 tile per N block)
+//   warp 1   tcgen05.mma issuer (one lane), TMEM allocator
+//   warps 2-5  epilogue: tcgen05.ld -> scale -> swizzled smem staging -> TMA store
+// Tile 128 (samples) x 128 (vertex coordinates); two TMEM accumulator stages so the MMAs of
+// tile i+1 overlap the epilogue of tile i.  The kernel is bound by its fp32 output stream.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "smplb_internal.h"
+
+#define TC_BM 128
+#define TC_BN 128
+#define TC_KP 256          // padded K
+#define TC_KB 64           // K elements per 128-byte swizzle atom
+#define TC_NKB (TC_KP / TC_KB)
+#define TC_ASTAGES 2
+#define TC_THREADS 192
+
+#define SM_B_OFF 0
+#define SM_A_OFF (64 * 1024)
+#define SM_C_OFF (192 * 1024)
+#define SM_BAR_OFF (224 * 1024)
+#define SM_TOTAL (SM_BAR_OFF + 128)
+#define TILE_KB_BYTES (128 * 128)   // one k-block of an operand tile: 128 rows x 128 B
+
+// ------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate; one thread issues for the CTA.
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i gets row (lane base + i).
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: start address >> 4, LBO (ignored for
+// swizzled K-major) = 1, SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (Blackwell), layout 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor: D fp32 (bits 4-5 = 1), A/B fp16 (0), both K-major, N >> 3 at bit 17,
+// M >> 4 at bit 24.
+#define TC_IDESC ((1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24))
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_blend_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_d,
+               const __grid_constant__ CUtensorMap map_c, int n_mblk, int n_nblk, float inv_scale) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + SM_BAR_OFF;
+  // barrier slots (8 bytes each)
+  const uint32_t full_a = bar0 + 0, empty_a = bar0 + 16, full_b = bar0 + 32, empty_b = bar0 + 40;
+  const uint32_t tmem_full = bar0 + 48, tmem_empty = bar0 + 64;
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + SM_BAR_OFF + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = n_mblk * n_nblk;
+  const int t0 = (int)(((long long)blockIdx.x * total) / gridDim.x);
+  const int t1 = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_ASTAGES; ++i) {
+      mbar_init(full_a + 8 * i, 1);
+      mbar_init(empty_a + 8 * i, 1);
+      mbar_init(tmem_full + 8 * i, 1);
+      mbar_init(tmem_empty + 8 * i, 4);   // one arrival per epilogue warp
+    }
+    mbar_init(full_b, 1);
+    mbar_init(empty_b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_BAR_OFF + 96),
+                 "n"(2 * TC_BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int cur_n = -1, b_loads = 0, stage = 0, phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        int n = t / n_mblk, m = t % n_mblk;
+        if (n != cur_n) {
+          if (b_loads > 0) mbar_wait(empty_b, (b_loads - 1) & 1);   // MMAs of the previous N block retired
+          mbar_expect_tx(full_b, TC_NKB * TILE_KB_BYTES);
+          for (int kb = 0; kb < TC_NKB; ++kb)
+            tma_load_2d(sbase + SM_B_OFF + kb * TILE_KB_BYTES, &map_d, kb * TC_KB, n * TC_BN, full_b);
+          ++b_loads;
+          cur_n = n;
+        }
+        mbar_wait(empty_a + 8 * stage, phase ^ 1);
+        mbar_expect_tx(full_a + 8 * stage, TC_NKB * TILE_KB_BYTES);
+        for (int kb = 0; kb < TC_NKB; ++kb)
+          tma_load_2d(sbase + SM_A_OFF + stage * (TC_NKB * TILE_KB_BYTES) + kb * TILE_KB_BYTES, &map_x, kb * TC_KB,
+                      m * TC_BM, full_a + 8 * stage);
+        if (++stage == TC_ASTAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      int cur_n = -1, b_loads = 0, stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        int n = t / n_mblk;
+        if (n != cur_n) {
+          mbar_wait(full_b, b_loads & 1);
+          ++b_loads;
+          cur_n = n;
+        }
+        mbar_wait(tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
+        mbar_wait(full_a + 8 * stage, phase);             // x16 tile landed
+        tc_fence_after();
+        uint32_t d_tmem = tmem_base + acc * TC_BN;
+#pragma unroll
+        for (int kb = 0; kb < TC_NKB; ++kb) {
+          uint32_t a_addr = sbase + SM_A_OFF + stage * (TC_NKB * TILE_KB_BYTES) + kb * TILE_KB_BYTES;
+          uint32_t b_addr = sbase + SM_B_OFF + kb * TILE_KB_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_KB / 16; ++k) {
+            // advance 16 fp16 = 32 B inside the 128 B swizzle atom
+            uint64_t ad = umma_desc_sw128(a_addr + k * 32);
+            uint64_t bd = umma_desc_sw128(b_addr + k * 32);
+            tc_mma_f16(d_tmem, ad, bd, TC_IDESC, (kb | k) != 0);
+          }
+        }
+        tc_commit(empty_a + 8 * stage);      // smem stage reusable once these MMAs retire
+        tc_commit(tmem_full + 8 * acc);      // accumulator ready for the epilogue
+        bool last_of_n = (t + 1 == t1) || ((t + 1) / n_mblk != n);
+        if (last_of_n) tc_commit(empty_b);
+        if (++stage == TC_ASTAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const uint32_t stage_base = sbase + SM_C_OFF + (warp - 2) * 8192;
+    int acc = 0, acc_phase = 0, buf = 0;
+    for (int t = t0; t < t1; ++t) {
+      int n = t / n_mblk, m = t % n_mblk;
+      mbar_wait(tmem_full + 8 * acc, acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cch = 0; cch < TC_BN / 32; ++cch) {
+        uint32_t r[32];
+        tc_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * TC_BN + cch * 32, r);
+        tc_wait_ld();
+        if (cch == TC_BN / 32 - 1) {
+          // all of this accumulator has been read into registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
+        }
+        // the staging buffer we are about to overwrite was read by the TMA store issued 2 chunks ago
+        if (lane == 0) tma_wait_read<1>();
+        __syncwarp();
+        uint32_t row_addr = stage_base + buf * 4096 + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v;
+          v.x = __uint_as_float(r[4 * j + 0]) * inv_scale;
+          v.y = __uint_as_float(r[4 * j + 1]) * inv_scale;
+          v.z = __uint_as_float(r[4 * j + 2]) * inv_scale;
+          v.w = __uint_as_float(r[4 * j + 3]) * inv_scale;
+          uint32_t addr = row_addr + ((j ^ (lane & 7)) << 4);   // SWIZZLE_128B: 16B chunk ^= row % 8
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                       : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_c, stage_base + buf * 4096, n * TC_BN + cch * 32, m * TC_BM + 32 * q);
+          tma_commit();
+        }
+        buf ^= 1;
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (lane == 0) tma_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------- operand construction
+__global__ void k_absmax(size_t n, const float *__restrict__ x, unsigned int *__restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order as uints
+}
+
+// Dt16[n][k] (row pitch 256 halves) from Dext fp32 [KX][pitch]; see the K map at the top.
+__global__ void k_build_dt16(int pitch, int V3, int NB, float scale, const float *__restrict__ Dext,
+                             __half *__restrict__ Dt) {
+  int n = blockIdx.x * 4 + (threadIdx.x >> 6);
+  int k0 = (threadIdx.x & 63) * 4;
+  if (n >= pitch) return;
+  for (int k = k0; k < k0 + 4; ++k) {
+    float v = 0.f;
+    if (n < V3) {
+      if (k < NPF) {
+        v = Dext[(size_t)k * pitch + n] * scale;
+      } else if (k < NPF + 3 * 10) {
+        int slot = (k - NPF) / 10, bi = (k - NPF) % 10;
+        if (bi < NB) {
+          float s = Dext[(size_t)(NPF + bi) * pitch + n] * scale;
+          float hi = __half2float(__float2half_rn(s));
+          v = (slot == 1) ? (s - hi) : hi;    // slots: hi, lo, hi
+        }
+      } else if (k < NPF + 33) {
+        float t = Dext[(size_t)(NPF + NB) * pitch + n] * scale;
+        float hi = __half2float(__float2half_rn(t));
+        float mid = __half2float(__float2half_rn(t - hi));
+        int w = k - (NPF + 30);
+        v = w == 0 ? hi : (w == 1 ? mid : (t - hi - mid));
+      }
+    }
+    Dt[(size_t)n * TC_KP + k] = __float2half_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_fn_t g_encode = nullptr;
+
+static int get_encode() {
+  if (g_encode) return 0;
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  RET_IF(!fn || qres != cudaDriverEntryPointSuccess, SMPLB_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  g_encode = (encode_fn_t)fn;
+  return 0;
+}
+
+static int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, int elem_bytes, void *ptr, uint64_t inner,
+                       uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  (void)elem_bytes;
+  CUresult r = g_encode(map, dt, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RET_IF(r != CUDA_SUCCESS, SMPLB_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return 0;
+}
+
+// Called from smplb_create: builds Dt16 and picks the power-of-two scale.
+int blend_tc_init(smplb_ctx *c) {
+  c->tc_ok = false;
+  if (c->NB > 10) return 0;   // the K map above reserves 10 slots per shape term
+  TRY(get_encode());
+  unsigned int *d_max = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d_max, 4));
+  CUDA_TRY(cudaMemsetAsync(d_max, 0, 4, c->stream));
+  size_t n = (size_t)(NPF + c->NB + 1) * c->pitch;
+  k_absmax<<<296, 256, 0, c->stream>>>(n, c->d_Dext, d_max);
+  unsigned int bits = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bits, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  cudaFree(d_max);
+  float mx;
+  memcpy(&mx, &bits, 4);
+  int s = 0;
+  if (mx > 0.f && isfinite(mx)) s = (int)floorf(log2f(16384.0f / mx));
+  s = s < -8 ? -8 : (s > 24 ? 24 : s);
+  c->tc_scale = ldexpf(1.0f, s);
+  c->tc_inv_scale = ldexpf(1.0f, -s);
+  CUDA_TRY(cudaMalloc((void **)&c->d_Dt16, (size_t)c->pitch * TC_KP * sizeof(__half)));
+  k_build_dt16<<<cdiv(c->pitch, 4), 256, 0, c->stream>>>(c->pitch, c->V3, c->NB, c->tc_scale, c->d_Dext,
+                                                         (__half *)c->d_Dt16);
+  c->launches += 2;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaFuncSetAttribute(k_blend_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  c->num_sms = sms;
+  TRY(make_map_2d((CUtensorMap *)c->map_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c->d_Dt16, TC_KP, (uint64_t)c->pitch,
+                  TC_KP * 2, TC_KB, TC_BN));
+  c->tc_ok = true;
+  return 0;
+}
+
+int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed) {
+  RET_IF(!c->tc_ok, SMPLB_ESTATE, "tcgen05 blend path is not initialised");
+  alignas(64) CUtensorMap map_x, map_c;
+  TRY(make_map_2d(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)x16, TC_KP, (uint64_t)B, TC_KP * 2, TC_KB, TC_BM));
+  TRY(make_map_2d(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)v_posed, (uint64_t)c->pitch, (uint64_t)B,
+                  (uint64_t)c->pitch * 4, 32, 32));
+  int n_mblk = cdiv(B, TC_BM), n_nblk = c->pitch / TC_BN;
+  int total = n_mblk * n_nblk;
+  int grid = total < c->num_sms ? total : c->num_sms;
+  LAUNCH(c, "blend_fwd_tc", grid, TC_THREADS, SM_TOTAL, k_blend_tc, map_x, *(const CUtensorMap *)c->map_d, map_c, n_mblk,
+         n_nblk, c->tc_inv_scale);
+  return 0;
+}

@@ -6,6 +6,8 @@
 //   batch_skew                         src/tf_smpl/batch_lbs.py:15-39
 //   batch_global_rigid_transformation  src/tf_smpl/batch_lbs.py:91-152
 //   joint regression + pose feature    src/tf_smpl/batch_smpl.py:115-127
+#include <cuda_fp16.h>
+
 #include "smplb_internal.h"
 
 #define FULL 0xffffffffu
@@ -107,7 +109,8 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
                                                   const float *__restrict__ theta, const float *__restrict__ J0,
                                                   const float *__restrict__ Jdirs, float *__restrict__ Rs,
                                                   float *__restrict__ Jout, float *__restrict__ A,
-                                                  float *__restrict__ Jtr, float *__restrict__ x) {
+                                                  float *__restrict__ Jtr, float *__restrict__ x,
+                                                  __half *__restrict__ x16) {
   int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -137,6 +140,30 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
       // pose_feature index (j-1)*9 + 3r + c (batch_smpl.py:126-127)
 #pragma unroll
       for (int e = 0; e < 9; ++e) x[(size_t)b * KX + (j - 1) * 9 + e] = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+    }
+  }
+  if (x16) {
+    // fp16 operand row of the tcgen05 blend GEMM (K map in k_blend_tc.cu): pose_feature,
+    // beta_hi, beta_hi, beta_lo, three 1s (v_template hi/mid/lo), zero padding to 256.
+    __half *xr = x16 + (size_t)b * 256;
+    if (act && j >= 1) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e)
+        xr[(j - 1) * 9 + e] = __float2half_rn(R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f));
+    }
+    for (int k = NPF + lane; k < 256; k += 32) {
+      float v = 0.0f;
+      if (k < NPF + 30) {
+        int slot = (k - NPF) / 10, bi = (k - NPF) % 10;
+        if (bi < NB) {
+          float bv = beta[(size_t)b * NB + bi];
+          float hi = __half2float(__float2half_rn(bv));
+          v = (slot == 2) ? (bv - hi) : hi;
+        }
+      } else if (k < NPF + 33) {
+        v = 1.0f;
+      }
+      xr[k] = __float2half_rn(v);
     }
   }
   if (x) {
@@ -358,9 +385,9 @@ int launch_lrotmin(smplb_ctx *c, int B, const float *theta, float *out) {
 }
 
 int launch_pose_fwd(smplb_ctx *c, int B, const float *beta, const float *theta, float *Rs, float *J, float *A,
-                    float *Jtr, float *x) {
+                    float *Jtr, float *x, void *x16) {
   LAUNCH(c, "pose_fwd", cdiv(B, 4), 128, 0, k_pose_fwd, B, c->NB, c->tree, beta, theta, c->d_J0, c->d_Jdirs, Rs, J, A,
-         Jtr, x);
+         Jtr, x, (__half *)x16);
   return 0;
 }
 

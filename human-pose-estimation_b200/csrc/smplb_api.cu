@@ -148,7 +148,7 @@ static void free_ws(smplb_ctx *c) {
                    (void **)&c->ws_vposed, (void **)&c->ws_verts, (void **)&c->ws_joints, (void **)&c->ws_kp,
                    (void **)&c->ws_dkp, (void **)&c->ws_djoints, (void **)&c->ws_dverts, (void **)&c->ws_dp, (void **)&c->ws_dA,
                    (void **)&c->ws_dx, (void **)&c->ws_part, (void **)&c->ws_cnt, (void **)&c->ws_theta,
-                   (void **)&c->ws_beta, (void **)&c->ws_gp};
+                   (void **)&c->ws_beta, (void **)&c->ws_gp, (void **)&c->ws_x16};
   for (void **p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -172,6 +172,7 @@ static int ensure_ws(smplb_ctx *c, int B) {
   int n = std::max(B, c->max_batch);
   size_t nb = (size_t)n;
   WS_ALLOC(ws_x, nb * KX);
+  WS_ALLOC(ws_x16, nb * 128);   // 256 halves per row
   WS_ALLOC(ws_Rs, nb * NJ * 9);
   WS_ALLOC(ws_J, nb * NJ * 3);
   WS_ALLOC(ws_A, nb * NJ * 12);
@@ -316,6 +317,7 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
   cudaMemset(c->ws_scal, 0, 64 * 4);
   cudaMemset(c->ws_cnt64, 0, 8 * sizeof(long long));
   if ((rc = ensure_ws(c, c->max_batch))) return fail(rc);
+  if ((rc = blend_tc_init(c))) return fail(rc);
   *out = c;
   return 0;
 }
@@ -328,7 +330,7 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
   free_ws(c);
   void *ptrs[] = {c->d_vt,       c->d_shapedirs, c->d_posedirs, c->d_W,        c->d_JR,       c->d_Dext,   c->d_J0,
                   c->d_Jdirs,    c->d_kcsr_off,  c->d_kcsr_idx, c->d_kcsr_val, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val,
-                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part};
+                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 16; ++i) {
@@ -426,6 +428,15 @@ extern "C" int smplb_launch_count(smplb_ctx *c, int64_t *count) {
   *count = c->launches;
   return 0;
 }
+extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
+  RET_IF(!c || !key, SMPLB_EINVAL, "null argument");
+  if (!strcmp(key, "blend_tc")) {
+    c->use_tc = value;
+    return 0;
+  }
+  smplb_set_error("unknown debug key %s", key);
+  return SMPLB_EINVAL;
+}
 extern "C" int smplb_profile_enable(smplb_ctx *c, int on) {
   RET_IF(!c, SMPLB_EINVAL, "null context");
   c->profile = on != 0;
@@ -464,9 +475,12 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   TRY(ensure_ws(c, B));
   CUDA_TRY(cudaMemcpyAsync(c->ws_beta, beta, (size_t)B * c->NB * 4, cudaMemcpyDeviceToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->ws_theta, theta, (size_t)B * 72 * 4, cudaMemcpyDeviceToDevice, c->stream));
-  TRY(launch_pose_fwd(c, B, c->ws_beta, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, Jtr ? Jtr : c->ws_Jtr, c->ws_x));
+  bool tc = c->tc_ok && c->use_tc;
+  TRY(launch_pose_fwd(c, B, c->ws_beta, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, Jtr ? Jtr : c->ws_Jtr,
+                      tc ? nullptr : c->ws_x, tc ? c->ws_x16 : nullptr));
   if (Rs) CUDA_TRY(cudaMemcpyAsync(Rs, c->ws_Rs, (size_t)B * NJ * 9 * 4, cudaMemcpyDeviceToDevice, c->stream));
-  TRY(launch_blend_fwd(c, B, c->ws_x, c->ws_vposed));
+  if (tc) TRY(launch_blend_fwd_tc(c, B, c->ws_x16, c->ws_vposed));
+  else TRY(launch_blend_fwd(c, B, c->ws_x, c->ws_vposed));
   float *vout = verts;
   if (!vout) {
     (void)need_verts;

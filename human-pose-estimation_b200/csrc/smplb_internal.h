@@ -43,6 +43,14 @@ struct smplb_ctx {
   float *d_kcsr_val = nullptr;
   int *d_vcsr_off = nullptr, *d_vcsr_k = nullptr;    // joint_regressor by vertex (backward)
   float *d_vcsr_val = nullptr;
+  // ---- tcgen05 blend path (k_blend_tc.cu)
+  bool tc_ok = false;          // operands built, tensor map encoded
+  int use_tc = 1;              // smplb_debug_set("blend_tc", 0) selects the FP32 CUDA-core GEMM (validation)
+  float tc_scale = 1.f, tc_inv_scale = 1.f;
+  void *d_Dt16 = nullptr;      // [pitch][256] fp16, K-major
+  alignas(64) unsigned char map_d[128];   // CUtensorMap of Dt16
+  int num_sms = 148;
+  void *ws_x16 = nullptr;      // [B][256] fp16 operand rows
   // ---- workspace, sized for max_batch (grown on demand)
   int ws_batch = 0;
   float *ws_x = nullptr;       // [B][KX]
@@ -143,7 +151,7 @@ __device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; 
 // ---- kernel launchers (device pointers only), one per stage -------------------------------
 // k_pose.cu
 int launch_pose_fwd(smplb_ctx *c, int B, const float *beta, const float *theta, float *Rs, float *J, float *A,
-                    float *Jtr, float *x);
+                    float *Jtr, float *x, void *x16);
 int launch_pose_bwd(smplb_ctx *c, int B, const float *theta, const float *Rs, const float *J, const float *A,
                     const float *dA_part, const float *dx_part, int ksplit, const float *d_Rs, float *d_beta,
                     float *d_theta);
@@ -154,6 +162,9 @@ int launch_lrotmin(smplb_ctx *c, int B, const float *theta, float *out);
 // k_blend.cu
 int launch_blend_fwd(smplb_ctx *c, int B, const float *x, float *v_posed);
 int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part);
+// k_blend_tc.cu
+int blend_tc_init(smplb_ctx *c);
+int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed);
 // k_skin.cu
 int launch_skin_fwd(smplb_ctx *c, int B, const float *A, const float *v_posed, float *verts);
 int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, const float *kp_gt, float *joints,

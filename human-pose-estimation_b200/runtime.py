@@ -124,6 +124,9 @@ class Context(object):
         check(lib().smplb_launch_count(self.handle, C.byref(n)))
         return n.value
 
+    def debug_set(self, key, value):
+        check(lib().smplb_debug_set(self.handle, key.encode(), int(value)))
+
     def profile(self, on):
         check(lib().smplb_profile_enable(self.handle, 1 if on else 0))
 

@@ -97,6 +97,9 @@ int smplb_launch_count(smplb_ctx *ctx, int64_t *count);
  * enabled (debug/bench breakdown only; serialises nothing but adds event overhead). */
 int smplb_profile_enable(smplb_ctx *ctx, int on);
 int smplb_profile_read(smplb_ctx *ctx, char *buf, size_t buflen); /* "name ms count\n" lines; resets */
+/* Test hook: key "blend_tc" = 0 routes the blend contraction through the FP32 CUDA-core GEMM
+ * that cross-checks the tcgen05 kernel (default 1). */
+int smplb_debug_set(smplb_ctx *ctx, const char *key, int value);
 
 /* ---- SMPL.__call__(beta, theta, get_skin) (batch_smpl.py:88-160) ------------------ *
  * beta [B,10], theta [B,72] -> verts [B,V,3] (may be NULL == get_skin False),
