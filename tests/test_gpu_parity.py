@@ -314,3 +314,25 @@ def test_full_size_properties(full_model):
     idx = [0, 1234, 4095]
     v, j, R = o(inp["beta"][idx].astype(np.float64), inp["theta"][idx].astype(np.float64), get_skin=True)
     assert rel_err(a["verts"][idx], v) < TOL and rel_err(a["joints"][idx], j) < TOL
+
+
+def test_tcgen05_blend_matches_fp32_gemm(smpl_full, full_model):
+    """The tcgen05 fp16-split blend GEMM against the FP32 CUDA-core GEMM of the same
+    contraction, and its a-priori error bound: |dv| <= u (2+eps) sum_k |pf_k||P_k|
+    with u = 2^-11 for the pose term; the shape/template terms are split to fp32 accuracy."""
+    inp = synthetic.make_inputs(200, seed=4242)
+    ctx = smpl_full.ctx
+    try:
+        ctx.debug_set("blend_tc", 0)
+        v0, _, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
+    finally:
+        ctx.debug_set("blend_tc", 1)
+    v1, _, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
+    assert np.isfinite(v1).all()
+    o = onp.SMPL(full_model, dtype=np.float64)
+    inter = {}
+    o(inp["beta"][:8].astype(np.float64), inp["theta"][:8].astype(np.float64), get_skin=True, intermediates=inter)
+    bound = 2.0 ** -11 * 2.01 * (np.abs(inter["pose_feature"]) @ np.abs(o.posedirs)).reshape(8, -1, 3)
+    # skinning is a convex combination of rigid transforms: it does not amplify |dv_posed|
+    assert np.abs(v1[:8].astype(np.float64) - v0[:8]).max() <= bound.max() * 1.8 + 2e-6
+    assert rel_err(v1, v0) < 3e-5
