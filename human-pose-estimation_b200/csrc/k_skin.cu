@@ -156,10 +156,15 @@ struct SkinBwdSmem {
 };
 
 __global__ void __launch_bounds__(SB_THREADS)
-    k_skin_bwd(int B, int V, int K, int pitch, const float *__restrict__ W, const float *__restrict__ A,
-               const float *__restrict__ v_posed, const float *__restrict__ d_verts,
-               const float *__restrict__ d_joints, const int *__restrict__ voff, const int *__restrict__ vk,
-               const float *__restrict__ vval, float *__restrict__ dp, float *__restrict__ dA_part) {
+    k_skin_bwd(int B, int V, int Vreal, int K, int pitch_vp, int pitch_dp, const int *__restrict__ vmap,
+               const float *__restrict__ W, const float *__restrict__ A, const float *__restrict__ v_posed,
+               const float *__restrict__ d_verts, const float *__restrict__ d_joints, const int *__restrict__ voff,
+               const int *__restrict__ vk, const float *__restrict__ vval, float *__restrict__ dp,
+               float *__restrict__ dA_part) {
+  // V counts the vertices this launch walks: all of them, or (vmap != NULL) only the rows of
+  // joint_regressor with a non-zero entry -- when no d_verts is given every other vertex has
+  // g == 0 and contributes nothing.  W, voff are indexed by the walked index, v_posed /
+  // d_verts by the real vertex vmap[v], dp by the walked index (compact when vmap != NULL).
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SkinBwdSmem &S = *reinterpret_cast<SkinBwdSmem *>(smem_raw);
   int tid = threadIdx.x;
@@ -204,8 +209,9 @@ __global__ void __launch_bounds__(SB_THREADS)
       float g0 = 0.f, g1 = 0.f, g2 = 0.f, p0 = 0.f, p1 = 0.f, p2 = 0.f, one = 0.f;
       if (v < V && sl < ns) {
         size_t b = (size_t)(s0 + sl);
+        int vr = vmap ? vmap[v] : v;
         if (d_verts) {
-          const float *dv = d_verts + (b * V + v) * 3;
+          const float *dv = d_verts + (b * Vreal + vr) * 3;
           g0 = dv[0];
           g1 = dv[1];
           g2 = dv[2];
@@ -226,12 +232,12 @@ __global__ void __launch_bounds__(SB_THREADS)
 #pragma unroll
           for (int e = 0; e < 9; ++e) TR[e] = fmaf(wj, S.AR[sl][j][e], TR[e]);
         }
-        const float *pp = v_posed + b * pitch + 3 * (size_t)v;
+        const float *pp = v_posed + b * pitch_vp + 3 * (size_t)vr;
         p0 = pp[0];
         p1 = pp[1];
         p2 = pp[2];
         one = 1.0f;
-        float *o = dp + b * pitch + 3 * (size_t)v;
+        float *o = dp + b * pitch_dp + 3 * (size_t)v;
         o[0] = TR[0] * g0 + TR[3] * g1 + TR[6] * g2;   // dp = T_R^T g
         o[1] = TR[1] * g0 + TR[4] * g1 + TR[7] * g2;
         o[2] = TR[2] * g0 + TR[5] * g1 + TR[8] * g2;
@@ -354,14 +360,21 @@ int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, con
 }
 
 int launch_skin_bwd(smplb_ctx *c, int B, const float *A, const float *v_posed, const float *d_verts,
-                    const float *d_joints, float *dp, float *dA_part) {
+                    const float *d_joints, float *dp, float *dA_part, bool compact) {
   if (!(c->attr_done & 1u)) {
     CUDA_TRY(cudaFuncSetAttribute(k_skin_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SkinBwdSmem)));
     c->attr_done |= 1u;
   }
   dim3 grid(cdiv(B, SB_ST), VSPLIT);
-  LAUNCH(c, "skin_bwd", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->V, c->K, c->pitch, c->d_W, A, v_posed,
-         d_verts, d_joints, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val, dp, dA_part);
+  if (compact) {
+    LAUNCH(c, "skin_bwd_active", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->n_act, c->V, c->K, c->pitch,
+           c->pitch_act, c->d_act_idx, c->d_act_W, A, v_posed, (const float *)nullptr, d_joints, c->d_acsr_off,
+           c->d_acsr_k, c->d_acsr_val, dp, dA_part);
+  } else {
+    LAUNCH(c, "skin_bwd", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->V, c->V, c->K, c->pitch, c->pitch,
+           (const int *)nullptr, c->d_W, A, v_posed, d_verts, d_joints, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val, dp,
+           dA_part);
+  }
   return 0;
 }
 

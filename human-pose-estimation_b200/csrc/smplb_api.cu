@@ -148,7 +148,7 @@ static void free_ws(smplb_ctx *c) {
                    (void **)&c->ws_vposed, (void **)&c->ws_verts, (void **)&c->ws_joints, (void **)&c->ws_kp,
                    (void **)&c->ws_dkp, (void **)&c->ws_djoints, (void **)&c->ws_dverts, (void **)&c->ws_dp, (void **)&c->ws_dA,
                    (void **)&c->ws_dx, (void **)&c->ws_part, (void **)&c->ws_cnt, (void **)&c->ws_theta,
-                   (void **)&c->ws_beta, (void **)&c->ws_gp, (void **)&c->ws_x16};
+                   (void **)&c->ws_beta, (void **)&c->ws_gp, (void **)&c->ws_x16, (void **)&c->ws_dp_act};
   for (void **p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -310,6 +310,36 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
     if ((rc = dev_upload(&c->d_vcsr_off, voff.data(), voff.size()))) return fail(rc);
     if ((rc = dev_upload(&c->d_vcsr_k, vk.data(), vk.size()))) return fail(rc);
     if ((rc = dev_upload(&c->d_vcsr_val, vval.data(), vval.size()))) return fail(rc);
+    // active vertices (non-empty rows) and everything the compact backward needs, gathered
+    std::vector<int> act, aoff(1, 0), ak;
+    std::vector<float> aval, aW;
+    for (size_t v = 0; v < V; ++v) {
+      if (voff[v + 1] == voff[v]) continue;
+      act.push_back((int)v);
+      for (int e = voff[v]; e < voff[v + 1]; ++e) {
+        ak.push_back(vk[e]);
+        aval.push_back(vval[e]);
+      }
+      aoff.push_back((int)ak.size());
+      for (int j = 0; j < NJ; ++j) aW.push_back(m->weights[v * NJ + j]);
+    }
+    c->n_act = (int)act.size();
+    c->pitch_act = std::max(128, cdiv(3 * c->n_act, 128) * 128);
+    if ((rc = dev_upload(&c->d_act_idx, act.data(), act.size()))) return fail(rc);
+    if ((rc = dev_upload(&c->d_act_W, aW.data(), aW.size()))) return fail(rc);
+    if ((rc = dev_upload(&c->d_acsr_off, aoff.data(), aoff.size()))) return fail(rc);
+    if ((rc = dev_upload(&c->d_acsr_k, ak.data(), ak.size()))) return fail(rc);
+    if ((rc = dev_upload(&c->d_acsr_val, aval.data(), aval.size()))) return fail(rc);
+    size_t ab = (size_t)KX * c->pitch_act * sizeof(float);
+    if (cudaMalloc((void **)&c->d_Dext_act, ab) != cudaSuccess || cudaMemset(c->d_Dext_act, 0, ab) != cudaSuccess)
+      return fail(SMPLB_ECUDA);
+    // gather the three columns of every active vertex from Dext (device-to-device strided copies)
+    for (int a = 0; a < c->n_act; ++a) {
+      if (cudaMemcpy2DAsync(c->d_Dext_act + 3 * a, (size_t)c->pitch_act * 4, c->d_Dext + 3 * (size_t)act[a],
+                            (size_t)c->pitch * 4, 12, KX, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess)
+        return fail(SMPLB_ECUDA);
+    }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(SMPLB_ECUDA);
   }
   if (cudaMalloc((void **)&c->ws_scal, 64 * 4) != cudaSuccess ||
       cudaMalloc((void **)&c->ws_cnt64, 8 * sizeof(long long)) != cudaSuccess)
@@ -330,7 +360,8 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
   free_ws(c);
   void *ptrs[] = {c->d_vt,       c->d_shapedirs, c->d_posedirs, c->d_W,        c->d_JR,       c->d_Dext,   c->d_J0,
                   c->d_Jdirs,    c->d_kcsr_off,  c->d_kcsr_idx, c->d_kcsr_val, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val,
-                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part};
+                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
+                  c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 16; ++i) {
@@ -434,6 +465,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->use_tc = value;
     return 0;
   }
+  if (!strcmp(key, "compact_bwd")) {
+    c->use_compact = value;
+    return 0;
+  }
   smplb_set_error("unknown debug key %s", key);
   return SMPLB_EINVAL;
 }
@@ -498,9 +533,19 @@ static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const fl
                              float *d_beta, float *d_theta) {
   RET_IF(c->saved_B != B, SMPLB_ESTATE, "smplb_smpl_backward(B=%d) without a matching forward (saved B=%d)", B,
          c->saved_B);
-  TRY(ensure_buf(c, &c->ws_dp, (size_t)c->ws_batch * c->pitch, true));
-  TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed, d_verts, d_joints, c->ws_dp, c->ws_dA));
-  TRY(launch_blend_bwd(c, B, c->ws_dp, c->ws_dx));
+  // No upstream gradient on verts: only vertices the keypoint regressor touches carry a
+  // gradient, so walk just those (exact: the skipped terms are zeros).
+  bool compact = (d_verts == nullptr) && c->use_compact && c->n_act < c->V;
+  float *dp;
+  if (compact) {
+    TRY(ensure_buf(c, &c->ws_dp_act, (size_t)c->ws_batch * c->pitch_act, true));
+    dp = c->ws_dp_act;
+  } else {
+    TRY(ensure_buf(c, &c->ws_dp, (size_t)c->ws_batch * c->pitch, true));
+    dp = c->ws_dp;
+  }
+  TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed, d_verts, d_joints, dp, c->ws_dA, compact));
+  TRY(launch_blend_bwd(c, B, dp, c->ws_dx, compact));
   TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, c->ws_dx, c->ksplit, d_Rs, d_beta,
                       d_theta));
   return 0;

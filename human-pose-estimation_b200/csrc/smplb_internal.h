@@ -43,6 +43,16 @@ struct smplb_ctx {
   float *d_kcsr_val = nullptr;
   int *d_vcsr_off = nullptr, *d_vcsr_k = nullptr;    // joint_regressor by vertex (backward)
   float *d_vcsr_val = nullptr;
+  // ---- active vertices: rows of joint_regressor with a non-zero.  With no upstream d_verts
+  //      the backward only has to walk these (every other vertex has a zero gradient).
+  int n_act = 0, pitch_act = 0;
+  int use_compact = 1;             // smplb_debug_set("compact_bwd", 0) forces the dense walk (validation)
+  int *d_act_idx = nullptr;
+  float *d_act_W = nullptr;        // [n_act][24]
+  int *d_acsr_off = nullptr, *d_acsr_k = nullptr;
+  float *d_acsr_val = nullptr;
+  float *d_Dext_act = nullptr;     // [KX][pitch_act]
+  float *ws_dp_act = nullptr;      // [B][pitch_act]
   // ---- tcgen05 blend path (k_blend_tc.cu)
   bool tc_ok = false;          // operands built, tensor map encoded
   int use_tc = 1;              // smplb_debug_set("blend_tc", 0) selects the FP32 CUDA-core GEMM (validation)
@@ -161,7 +171,7 @@ int launch_skew(smplb_ctx *c, int N, const float *vec, float *out);
 int launch_lrotmin(smplb_ctx *c, int B, const float *theta, float *out);
 // k_blend.cu
 int launch_blend_fwd(smplb_ctx *c, int B, const float *x, float *v_posed);
-int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part);
+int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part, bool compact);
 // k_blend_tc.cu
 int blend_tc_init(smplb_ctx *c);
 int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed);
@@ -170,7 +180,7 @@ int launch_skin_fwd(smplb_ctx *c, int B, const float *A, const float *v_posed, f
 int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, const float *kp_gt, float *joints,
                   float *kp_pred, float *dkp, float *part, int *cnt);
 int launch_skin_bwd(smplb_ctx *c, int B, const float *A, const float *v_posed, const float *d_verts,
-                    const float *d_joints, float *dp, float *dA_part);
+                    const float *d_joints, float *dp, float *dA_part, bool compact);
 int launch_proj(smplb_ctx *c, int B, int N, const float *X, const float *cam, int pixel, float im_w, float im_h,
                 float *out);
 int launch_proj_bwd(smplb_ctx *c, int B, int N, const float *X, const float *cam, const float *d_out, int pixel,

@@ -336,3 +336,19 @@ def test_tcgen05_blend_matches_fp32_gemm(smpl_full, full_model):
     # skinning is a convex combination of rigid transforms: it does not amplify |dv_posed|
     assert np.abs(v1[:8].astype(np.float64) - v0[:8]).max() <= bound.max() * 1.8 + 2e-6
     assert rel_err(v1, v0) < 3e-5
+
+
+def test_compact_backward_equals_dense_walk(smpl_full):
+    """With no upstream d_verts the backward walks only the vertices the keypoint
+    regressor touches; the skipped terms are exact zeros, so the result must match the
+    dense walk to fp32 summation-order noise."""
+    inp = synthetic.make_inputs(40, seed=99)
+    ctx = smpl_full.ctx
+    a = smpl_full.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"])
+    try:
+        ctx.debug_set("compact_bwd", 0)
+        b = smpl_full.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"])
+    finally:
+        ctx.debug_set("compact_bwd", 1)
+    for k in ("d_beta", "d_theta", "d_cam"):
+        assert rel_err(a[k], b[k]) < 2e-6, k
