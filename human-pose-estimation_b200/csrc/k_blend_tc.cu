@@ -40,94 +40,9 @@
 #define SM_TOTAL (SM_BAR_OFF + 128)
 #define TILE_KB_BYTES (128 * 128)   // one k-block of an operand tile: 128 rows x 128 B
 
-// ------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#include "tc_ptx.cuh"
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
-               "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate; one thread issues for the CTA.
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread i gets row (lane base + i).
-__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t *r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: start address >> 4, LBO (ignored for
-// swizzled K-major) = 1, SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (Blackwell), layout 2.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// Instruction descriptor: D fp32 (bits 4-5 = 1), A/B fp16 (0), both K-major, N >> 3 at bit 17,
-// M >> 4 at bit 24.
-#define TC_IDESC ((1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24))
+#define TC_IDESC umma_idesc_f16(TC_BM, TC_BN)
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_blend_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_d,
@@ -300,15 +215,16 @@ __global__ void k_absmax(size_t n, const float *__restrict__ x, unsigned int *__
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order as uints
 }
 
-// Dt16[n][k] (row pitch 256 halves) from Dext fp32 [KX][pitch]; see the K map at the top.
-__global__ void k_build_dt16(int pitch, int V3, int NB, float scale, const float *__restrict__ Dext,
+// Dt16[n][k] (row pitch 256 halves) from Dext fp32 [KX][pitch] (same planar column order n,
+// zero in the padding columns); see the K map at the top.
+__global__ void k_build_dt16(int pitch, int NB, float scale, const float *__restrict__ Dext,
                              __half *__restrict__ Dt) {
   int n = blockIdx.x * 4 + (threadIdx.x >> 6);
   int k0 = (threadIdx.x & 63) * 4;
   if (n >= pitch) return;
   for (int k = k0; k < k0 + 4; ++k) {
     float v = 0.f;
-    if (n < V3) {
+    {
       if (k < NPF) {
         v = Dext[(size_t)k * pitch + n] * scale;
       } else if (k < NPF + 3 * 10) {
@@ -382,7 +298,7 @@ int blend_tc_init(smplb_ctx *c) {
   c->tc_scale = ldexpf(1.0f, s);
   c->tc_inv_scale = ldexpf(1.0f, -s);
   CUDA_TRY(cudaMalloc((void **)&c->d_Dt16, (size_t)c->pitch * TC_KP * sizeof(__half)));
-  k_build_dt16<<<cdiv(c->pitch, 4), 256, 0, c->stream>>>(c->pitch, c->V3, c->NB, c->tc_scale, c->d_Dext,
+  k_build_dt16<<<cdiv(c->pitch, 4), 256, 0, c->stream>>>(c->pitch, c->NB, c->tc_scale, c->d_Dext,
                                                          (__half *)c->d_Dt16);
   c->launches += 2;
   CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
                                                   const float *__restrict__ Jdirs, float *__restrict__ Rs,
                                                   float *__restrict__ Jout, float *__restrict__ A,
                                                   float *__restrict__ Jtr, float *__restrict__ x,
-                                                  __half *__restrict__ x16) {
+                                                  __half *__restrict__ x16, __half *__restrict__ A16) {
   int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -190,6 +190,20 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
     if (Jtr) {
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) Jtr[((size_t)b * NJ + j) * 3 + cc] = G[9 + cc];
+    }
+    if (A16) {
+      // fp16 split operand of the tcgen05 skinning GEMM (k_skin_tc.cu): row (b, e = 4r + d),
+      // columns j | 24 + j | 48 + j = A_hi | A_lo | A_hi  (pairs with W_hi | W_hi | W_lo)
+      __half *rowbase = A16 + (size_t)b * 12 * 128;
+#pragma unroll
+      for (int e = 0; e < 12; ++e) {
+        float val = a[e];
+        __half hi = __float2half_rn(val);
+        __half lo = __float2half_rn(val - __half2float(hi));
+        rowbase[e * 128 + j] = hi;
+        rowbase[e * 128 + 24 + j] = lo;
+        rowbase[e * 128 + 48 + j] = hi;
+      }
     }
   }
 }
@@ -385,9 +399,9 @@ int launch_lrotmin(smplb_ctx *c, int B, const float *theta, float *out) {
 }
 
 int launch_pose_fwd(smplb_ctx *c, int B, const float *beta, const float *theta, float *Rs, float *J, float *A,
-                    float *Jtr, float *x, void *x16) {
+                    float *Jtr, float *x, void *x16, void *A16) {
   LAUNCH(c, "pose_fwd", cdiv(B, 4), 128, 0, k_pose_fwd, B, c->NB, c->tree, beta, theta, c->d_J0, c->d_Jdirs, Rs, J, A,
-         Jtr, x, (__half *)x16);
+         Jtr, x, (__half *)x16, (__half *)A16);
   return 0;
 }
 

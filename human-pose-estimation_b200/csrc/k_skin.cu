@@ -19,7 +19,7 @@
 #define SK_VT 128
 #define SK_SPB 32
 #define SK_CH 8
-__global__ void __launch_bounds__(SK_VT) k_skin_fwd(int B, int V, int pitch, const float *__restrict__ W,
+__global__ void __launch_bounds__(SK_VT) k_skin_fwd(int B, int V, int Vp, const float *__restrict__ W,
                                                     const float *__restrict__ A, const float *__restrict__ v_posed,
                                                     float *__restrict__ verts) {
   __shared__ __align__(16) float sA[SK_CH][NJ * 12];
@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(SK_VT) k_skin_fwd(int B, int V, int pitch, con
         T[8] = fmaf(wj, r2.x, T[8]); T[9] = fmaf(wj, r2.y, T[9]); T[10] = fmaf(wj, r2.z, T[10]); T[11] = fmaf(wj, r2.w, T[11]);
       }
       size_t b = (size_t)(s0 + s);
-      const float *p = v_posed + b * pitch + 3 * (size_t)vc;
-      float p0 = p[0], p1 = p[1], p2 = p[2];
+      const float *p = v_posed + b * (3 * (size_t)Vp) + vc;   // planar: coordinate c at c * Vp + v
+      float p0 = p[0], p1 = p[Vp], p2 = p[2 * (size_t)Vp];
       if (vok) {
         float *o = verts + (b * V + v) * 3;
         o[0] = fmaf(T[0], p0, fmaf(T[1], p1, fmaf(T[2], p2, T[3])));
@@ -156,7 +156,7 @@ struct SkinBwdSmem {
 };
 
 __global__ void __launch_bounds__(SB_THREADS)
-    k_skin_bwd(int B, int V, int Vreal, int K, int pitch_vp, int pitch_dp, const int *__restrict__ vmap,
+    k_skin_bwd(int B, int V, int Vreal, int K, int Vp_vp, int Vp_dp, const int *__restrict__ vmap,
                const float *__restrict__ W, const float *__restrict__ A, const float *__restrict__ v_posed,
                const float *__restrict__ d_verts, const float *__restrict__ d_joints, const int *__restrict__ voff,
                const int *__restrict__ vk, const float *__restrict__ vval, float *__restrict__ dp,
@@ -232,15 +232,15 @@ __global__ void __launch_bounds__(SB_THREADS)
 #pragma unroll
           for (int e = 0; e < 9; ++e) TR[e] = fmaf(wj, S.AR[sl][j][e], TR[e]);
         }
-        const float *pp = v_posed + b * pitch_vp + 3 * (size_t)vr;
+        const float *pp = v_posed + b * (3 * (size_t)Vp_vp) + vr;   // planar layouts
         p0 = pp[0];
-        p1 = pp[1];
-        p2 = pp[2];
+        p1 = pp[Vp_vp];
+        p2 = pp[2 * (size_t)Vp_vp];
         one = 1.0f;
-        float *o = dp + b * pitch_dp + 3 * (size_t)v;
+        float *o = dp + b * (3 * (size_t)Vp_dp) + v;
         o[0] = TR[0] * g0 + TR[3] * g1 + TR[6] * g2;   // dp = T_R^T g
-        o[1] = TR[1] * g0 + TR[4] * g1 + TR[7] * g2;
-        o[2] = TR[2] * g0 + TR[5] * g1 + TR[8] * g2;
+        o[Vp_dp] = TR[1] * g0 + TR[4] * g1 + TR[7] * g2;
+        o[2 * (size_t)Vp_dp] = TR[2] * g0 + TR[5] * g1 + TR[8] * g2;
       }
       float4 *dst = reinterpret_cast<float4 *>(S.GP[vl][sl]);
       dst[0] = make_float4(g0, g1, g2, 0.f);
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256) k_proj_bwd(int N, const float *__restrict
 
 int launch_skin_fwd(smplb_ctx *c, int B, const float *A, const float *v_posed, float *verts) {
   dim3 grid(cdiv(c->V, SK_VT), cdiv(B, SK_SPB));
-  LAUNCH(c, "skin_fwd", grid, SK_VT, 0, k_skin_fwd, B, c->V, c->pitch, c->d_W, A, v_posed, verts);
+  LAUNCH(c, "skin_fwd", grid, SK_VT, 0, k_skin_fwd, B, c->V, c->Vp, c->d_W, A, v_posed, verts);
   return 0;
 }
 
@@ -367,11 +367,11 @@ int launch_skin_bwd(smplb_ctx *c, int B, const float *A, const float *v_posed, c
   }
   dim3 grid(cdiv(B, SB_ST), VSPLIT);
   if (compact) {
-    LAUNCH(c, "skin_bwd_active", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->n_act, c->V, c->K, c->pitch,
-           c->pitch_act, c->d_act_idx, c->d_act_W, A, v_posed, (const float *)nullptr, d_joints, c->d_acsr_off,
+    LAUNCH(c, "skin_bwd_active", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->n_act, c->V, c->K, c->Vp,
+           c->Vpa, c->d_act_idx, c->d_act_W, A, v_posed, (const float *)nullptr, d_joints, c->d_acsr_off,
            c->d_acsr_k, c->d_acsr_val, dp, dA_part);
   } else {
-    LAUNCH(c, "skin_bwd", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->V, c->V, c->K, c->pitch, c->pitch,
+    LAUNCH(c, "skin_bwd", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->V, c->V, c->K, c->Vp, c->Vp,
            (const int *)nullptr, c->d_W, A, v_posed, d_verts, d_joints, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val, dp,
            dA_part);
   }

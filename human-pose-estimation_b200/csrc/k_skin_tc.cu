@@ -1,0 +1,262 @@
+// Linear blend skinning with the per-vertex transforms formed on the tensor cores.
+//
+//   T[v, (s, e)] = sum_j W[v, j] * A[s, j, e]        e = 4r + d indexes the 3x4 transform
+//   verts[s, v, r] = T[v,s,4r+0..2] . v_posed[s, v, :] + T[v,s,4r+3]     (batch_smpl.py:139-149)
+//
+// Dense 24-wide blending costs 288 FMA per (vertex, sample) on the FP32 pipes -- 2-4x more time
+// than moving the kernel's bytes -- so T runs as a tcgen05 GEMM: M = 128 vertices (TMEM lanes),
+// N = 12 * 16 samples, K = 72 -> 80.  fp16 operands are split so the product keeps fp32-grade
+// accuracy (a single fp16/tf32 rounding of W would move vertices by ~0.5 mm, 5x the tolerance):
+//   columns   0..23   W_hi   x   A_hi
+//   columns  24..47   W_hi   x   A_lo
+//   columns  48..71   W_lo   x   A_hi          (72..127 zero; 5 MMAs of K = 16 are issued)
+// T never leaves the SM: the epilogue threads (one per vertex = TMEM lane) read it with
+// tcgen05.ld, apply it to v_posed and write verts through a shared-memory transpose so both
+// global streams are fully coalesced.  The kernel is bound by those two streams.
+//
+// Persistent, warp-specialised: warp 0 TMA producer (W16 tile per vertex tile, A16 chunk per
+// tile), warp 1 MMA issuer + TMEM allocator, warps 2-5 epilogue; two TMEM accumulator stages.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "smplb_internal.h"
+#include "tc_ptx.cuh"
+
+#define ST_VT 128                 // vertices per tile (MMA M)
+#define ST_S 16                   // samples per tile
+#define ST_N (12 * ST_S)          // MMA N = 192
+#define ST_KP 128                 // padded K in shared memory (two 64-wide swizzle atoms)
+#define ST_ASTAGES 2
+#define ST_THREADS 192
+#define ST_W_BYTES (2 * ST_VT * 128)      // 32 KB: two k-blocks of 128 rows x 128 B
+#define ST_A_KB_BYTES (ST_N * 128)        // 24 KB: one k-block of the A16 chunk
+#define ST_A_BYTES (2 * ST_A_KB_BYTES)    // 48 KB
+#define ST_SM_W 0
+#define ST_SM_A (ST_W_BYTES)
+#define ST_SM_T (ST_SM_A + ST_ASTAGES * ST_A_BYTES)          // epilogue transpose staging: 4 warps x 96 floats
+#define ST_SM_BAR (ST_SM_T + 4 * 96 * 4)
+#define ST_SM_TOTAL (ST_SM_BAR + 128)
+
+__global__ void __launch_bounds__(ST_THREADS, 1)
+    k_skin_tc(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_a, int B, int V, int Vp,
+              int n_vt, int n_ch, const float *__restrict__ v_posed, float *__restrict__ verts) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + ST_SM_BAR;
+  const uint32_t full_a = bar0 + 0, empty_a = bar0 + 16, full_w = bar0 + 32, empty_w = bar0 + 40;
+  const uint32_t tmem_full = bar0 + 48, tmem_empty = bar0 + 64;
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + ST_SM_BAR + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = n_vt * n_ch;
+  const int t0 = (int)(((long long)blockIdx.x * total) / gridDim.x);
+  const int t1 = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST_ASTAGES; ++i) {
+      mbar_init(full_a + 8 * i, 1);
+      mbar_init(empty_a + 8 * i, 1);
+      mbar_init(tmem_full + 8 * i, 1);
+      mbar_init(tmem_empty + 8 * i, 4);
+    }
+    mbar_init(full_w, 1);
+    mbar_init(empty_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + ST_SM_BAR + 96), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int cur_vt = -1, w_loads = 0, stage = 0, phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        int vt = t / n_ch, ch = t % n_ch;
+        if (vt != cur_vt) {
+          if (w_loads > 0) mbar_wait(empty_w, (w_loads - 1) & 1);
+          mbar_expect_tx(full_w, ST_W_BYTES);
+          for (int kb = 0; kb < 2; ++kb)
+            tma_load_2d(sbase + ST_SM_W + kb * (ST_VT * 128), &map_w, kb * 64, vt * ST_VT, full_w);
+          ++w_loads;
+          cur_vt = vt;
+        }
+        mbar_wait(empty_a + 8 * stage, phase ^ 1);
+        mbar_expect_tx(full_a + 8 * stage, ST_A_BYTES);
+        for (int kb = 0; kb < 2; ++kb)
+          tma_load_2d(sbase + ST_SM_A + stage * ST_A_BYTES + kb * ST_A_KB_BYTES, &map_a, kb * 64, ch * ST_N,
+                      full_a + 8 * stage);
+        if (++stage == ST_ASTAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(ST_VT, ST_N);
+      int cur_vt = -1, w_loads = 0, stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        int vt = t / n_ch;
+        if (vt != cur_vt) {
+          mbar_wait(full_w, w_loads & 1);
+          ++w_loads;
+          cur_vt = vt;
+        }
+        mbar_wait(tmem_empty + 8 * acc, acc_phase ^ 1);
+        mbar_wait(full_a + 8 * stage, phase);
+        tc_fence_after();
+        uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t w_addr = sbase + ST_SM_W, a_addr = sbase + ST_SM_A + stage * ST_A_BYTES;
+        // K = 80: four 16-wide steps in the first swizzle atom, one in the second
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + k * 32), umma_desc_sw128(a_addr + k * 32), idesc, k != 0);
+        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + ST_VT * 128), umma_desc_sw128(a_addr + ST_A_KB_BYTES), idesc, 1);
+        tc_commit(empty_a + 8 * stage);
+        tc_commit(tmem_full + 8 * acc);
+        bool last_of_vt = (t + 1 == t1) || ((t + 1) / n_ch != vt);
+        if (last_of_vt) tc_commit(empty_w);
+        if (++stage == ST_ASTAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int q = warp & 3;                       // TMEM lane quarter: vertices 32q .. 32q+31 of the tile
+    float *stg = reinterpret_cast<float *>(smem + ST_SM_T) + (warp - 2) * 96;
+    const size_t vp_row = 3 * (size_t)Vp;
+    int acc = 0, acc_phase = 0;
+    for (int t = t0; t < t1; ++t) {
+      int vt = t / n_ch, ch = t % n_ch;
+      int v0 = vt * ST_VT + 32 * q;               // first vertex of this warp
+      int v = v0 + lane;
+      int nv = min(32, V - v0);                   // valid vertices of this warp (<= 0: none)
+      mbar_wait(tmem_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256;
+#pragma unroll 1
+      for (int sg = 0; sg < ST_S / 4; ++sg) {
+        // T of 4 samples: 48 fp32 columns
+        uint32_t r[48];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) tc_ld_32x4(trow + sg * 48 + i * 4, r + 4 * i);
+        tc_wait_ld();
+        if (sg == ST_S / 4 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);   // accumulator fully read
+        }
+#pragma unroll
+        for (int si = 0; si < 4; ++si) {
+          int b = ch * ST_S + sg * 4 + si;
+          if (b >= B || nv <= 0) continue;          // warp-uniform
+          const float *pr = v_posed + (size_t)b * vp_row + v;       // planar: three coalesced 128 B reads
+          float p0 = pr[0], p1 = pr[Vp], p2 = pr[2 * (size_t)Vp];
+          const uint32_t *T = r + 12 * si;
+          float o0 = fmaf(__uint_as_float(T[0]), p0, fmaf(__uint_as_float(T[1]), p1, fmaf(__uint_as_float(T[2]), p2, __uint_as_float(T[3]))));
+          float o1 = fmaf(__uint_as_float(T[4]), p0, fmaf(__uint_as_float(T[5]), p1, fmaf(__uint_as_float(T[6]), p2, __uint_as_float(T[7]))));
+          float o2 = fmaf(__uint_as_float(T[8]), p0, fmaf(__uint_as_float(T[9]), p1, fmaf(__uint_as_float(T[10]), p2, __uint_as_float(T[11]))));
+          // transpose through shared memory: [vertex][xyz] is contiguous in verts
+          __syncwarp();
+          stg[3 * lane + 0] = o0;
+          stg[3 * lane + 1] = o1;
+          stg[3 * lane + 2] = o2;
+          __syncwarp();
+          float *dst = verts + ((size_t)b * V + v0) * 3;
+          int nflt = 3 * nv;
+          if (lane < nflt) dst[lane] = stg[lane];
+          if (lane + 32 < nflt) dst[lane + 32] = stg[lane + 32];
+          if (lane + 64 < nflt) dst[lane + 64] = stg[lane + 64];
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// W16[v][k]: W_hi | W_hi | W_lo | 0 (row pitch 128 halves); rows >= V are zero.
+__global__ void k_build_w16(int V, int Vp, const float *__restrict__ W, __half *__restrict__ W16) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Vp * 128) return;
+  int v = i / 128, k = i % 128;
+  float out = 0.f;
+  if (v < V && k < 72) {
+    float w = W[(size_t)v * NJ + (k % 24)];
+    float hi = __half2float(__float2half_rn(w));
+    out = (k < 48) ? hi : (w - hi);
+  }
+  W16[i] = __float2half_rn(out);
+}
+
+typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_fn_t g_encode2 = nullptr;
+
+static int make_map_f16(CUtensorMap *map, void *ptr, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                        uint32_t box_outer) {
+  if (!g_encode2) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    RET_IF(!fn || qres != cudaDriverEntryPointSuccess, SMPLB_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+    g_encode2 = (encode_fn_t)fn;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode2(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RET_IF(r != CUDA_SUCCESS, SMPLB_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return 0;
+}
+
+int skin_tc_init(smplb_ctx *c) {
+  c->skin_tc_ok = false;
+  CUDA_TRY(cudaMalloc((void **)&c->d_W16, (size_t)c->Vp * 128 * sizeof(__half)));
+  k_build_w16<<<cdiv(c->Vp * 128, 256), 256, 0, c->stream>>>(c->V, c->Vp, c->d_W, (__half *)c->d_W16);
+  c->launches++;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaFuncSetAttribute(k_skin_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SM_TOTAL));
+  TRY(make_map_f16((CUtensorMap *)c->map_w, c->d_W16, ST_KP, (uint64_t)c->Vp, 64, ST_VT));
+  if (!c->num_sms) CUDA_TRY(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
+  c->skin_tc_ok = true;
+  return 0;
+}
+
+int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts) {
+  RET_IF(!c->skin_tc_ok, SMPLB_ESTATE, "tcgen05 skinning path is not initialised");
+  alignas(64) CUtensorMap map_a;
+  TRY(make_map_f16(&map_a, (void *)A16, ST_KP, (uint64_t)B * 12, 64, ST_N));
+  int n_vt = c->Vp / ST_VT, n_ch = cdiv(B, ST_S);
+  int total = n_vt * n_ch;
+  int grid = total < c->num_sms ? total : c->num_sms;
+  LAUNCH(c, "skin_fwd_tc", grid, ST_THREADS, ST_SM_TOTAL, k_skin_tc, *(const CUtensorMap *)c->map_w, map_a, B, c->V,
+         c->Vp, n_vt, n_ch, v_posed, verts);
+  return 0;
+}

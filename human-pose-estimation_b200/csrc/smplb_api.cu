@@ -136,6 +136,34 @@ __global__ void __launch_bounds__(256) k_fold_joints(int V, int NB, const float 
   }
 }
 
+// Dext[k][c * Vp + v] (planar, zero padded): rows 0..206 posedirs, 207..207+NB-1 shapedirs,
+// 207+NB v_template -- a pure re-layout of the reference's [*, 3v+c] matrices.
+__global__ void k_build_dext(int V, int Vp, int NB, const float *__restrict__ posedirs,
+                             const float *__restrict__ shapedirs, const float *__restrict__ vt, float *__restrict__ Dext) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int k = blockIdx.y;
+  if (n >= 3 * Vp) return;
+  int cc = n / Vp, v = n % Vp;
+  float val = 0.f;
+  if (v < V) {
+    size_t src = 3 * (size_t)v + cc;
+    if (k < NPF) val = posedirs[(size_t)k * 3 * V + src];
+    else if (k < NPF + NB) val = shapedirs[(size_t)(k - NPF) * 3 * V + src];
+    else if (k == NPF + NB) val = vt[src];
+  }
+  Dext[(size_t)k * 3 * Vp + n] = val;
+}
+
+// Dext_act[k][c * Vpa + a] = Dext[k][c * Vp + act[a]]
+__global__ void k_gather_dext(int n_act, int Vpa, int Vp, const int *__restrict__ act, const float *__restrict__ Dext,
+                              float *__restrict__ out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int k = blockIdx.y;
+  if (n >= 3 * Vpa) return;
+  int cc = n / Vpa, a = n % Vpa;
+  out[(size_t)k * 3 * Vpa + n] = a < n_act ? Dext[(size_t)k * 3 * Vp + (size_t)cc * Vp + act[a]] : 0.f;
+}
+
 template <typename T>
 static int dev_upload(T **dst, const T *src, size_t n) {
   CUDA_TRY(cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T)));
@@ -148,7 +176,7 @@ static void free_ws(smplb_ctx *c) {
                    (void **)&c->ws_vposed, (void **)&c->ws_verts, (void **)&c->ws_joints, (void **)&c->ws_kp,
                    (void **)&c->ws_dkp, (void **)&c->ws_djoints, (void **)&c->ws_dverts, (void **)&c->ws_dp, (void **)&c->ws_dA,
                    (void **)&c->ws_dx, (void **)&c->ws_part, (void **)&c->ws_cnt, (void **)&c->ws_theta,
-                   (void **)&c->ws_beta, (void **)&c->ws_gp, (void **)&c->ws_x16, (void **)&c->ws_dp_act};
+                   (void **)&c->ws_beta, (void **)&c->ws_gp, (void **)&c->ws_x16, (void **)&c->ws_dp_act, (void **)&c->ws_A16};
   for (void **p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -173,6 +201,8 @@ static int ensure_ws(smplb_ctx *c, int B) {
   size_t nb = (size_t)n;
   WS_ALLOC(ws_x, nb * KX);
   WS_ALLOC(ws_x16, nb * 128);   // 256 halves per row
+  WS_ALLOC(ws_A16, nb * 12 * 64);   // 12 rows x 128 halves per sample; columns 72..127 stay zero
+  CUDA_TRY(cudaMemsetAsync(c->ws_A16, 0, nb * 12 * 64 * 4, c->stream));
   WS_ALLOC(ws_Rs, nb * NJ * 9);
   WS_ALLOC(ws_J, nb * NJ * 3);
   WS_ALLOC(ws_A, nb * NJ * 12);
@@ -225,7 +255,8 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
   c->NB = m->num_betas;
   c->K = m->num_keypoints;
   c->V3 = 3 * c->V;
-  c->pitch = cdiv(c->V3, 128) * 128;
+  c->Vp = cdiv(c->V, 128) * 128;
+  c->pitch = 3 * c->Vp;
   c->ksplit = 16;
   c->max_batch = std::max(max_batch, 1);
   // kinematic tree: parent index < child index (batch_lbs.py:130 walks joints in index order)
@@ -257,16 +288,12 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
   if ((rc = dev_upload(&c->d_JR, m->joint_regressor, V * c->K))) return fail(rc);
   float *d_Jreg = nullptr;
   if ((rc = dev_upload(&d_Jreg, m->J_regressor, V * NJ))) return fail(rc);
-  // Dext = [posedirs ; shapedirs ; v_template ; 0] with row pitch c->pitch (zero padded)
+  // Dext = [posedirs ; shapedirs ; v_template ; 0], planar columns, row pitch c->pitch
   size_t dext_bytes = (size_t)KX * c->pitch * sizeof(float);
-  if (cudaMalloc((void **)&c->d_Dext, dext_bytes) != cudaSuccess || cudaMemset(c->d_Dext, 0, dext_bytes) != cudaSuccess)
-    return fail(SMPLB_ECUDA);
-  size_t rowb = V * 3 * sizeof(float), pitchb = (size_t)c->pitch * sizeof(float);
-  if (cudaMemcpy2D(c->d_Dext, pitchb, c->d_posedirs, rowb, rowb, NPF, cudaMemcpyDeviceToDevice) != cudaSuccess ||
-      cudaMemcpy2D(c->d_Dext + (size_t)NPF * c->pitch, pitchb, c->d_shapedirs, rowb, rowb, c->NB,
-                   cudaMemcpyDeviceToDevice) != cudaSuccess ||
-      cudaMemcpy(c->d_Dext + (size_t)(NPF + c->NB) * c->pitch, c->d_vt, rowb, cudaMemcpyDeviceToDevice) != cudaSuccess)
-    return fail(SMPLB_ECUDA);
+  if (cudaMalloc((void **)&c->d_Dext, dext_bytes) != cudaSuccess) return fail(SMPLB_ECUDA);
+  k_build_dext<<<dim3(cdiv(c->pitch, 256), KX), 256, 0, c->stream>>>(c->V, c->Vp, c->NB, c->d_posedirs, c->d_shapedirs,
+                                                                     c->d_vt, c->d_Dext);
+  c->launches++;
   if (cudaMalloc((void **)&c->d_J0, NJ * 3 * 4) != cudaSuccess ||
       cudaMalloc((void **)&c->d_Jdirs, (size_t)NJ * 3 * c->NB * 4) != cudaSuccess)
     return fail(SMPLB_ECUDA);
@@ -324,21 +351,18 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
       for (int j = 0; j < NJ; ++j) aW.push_back(m->weights[v * NJ + j]);
     }
     c->n_act = (int)act.size();
-    c->pitch_act = std::max(128, cdiv(3 * c->n_act, 128) * 128);
+    c->Vpa = std::max(128, cdiv(c->n_act, 128) * 128);
+    c->pitch_act = 3 * c->Vpa;
     if ((rc = dev_upload(&c->d_act_idx, act.data(), act.size()))) return fail(rc);
     if ((rc = dev_upload(&c->d_act_W, aW.data(), aW.size()))) return fail(rc);
     if ((rc = dev_upload(&c->d_acsr_off, aoff.data(), aoff.size()))) return fail(rc);
     if ((rc = dev_upload(&c->d_acsr_k, ak.data(), ak.size()))) return fail(rc);
     if ((rc = dev_upload(&c->d_acsr_val, aval.data(), aval.size()))) return fail(rc);
     size_t ab = (size_t)KX * c->pitch_act * sizeof(float);
-    if (cudaMalloc((void **)&c->d_Dext_act, ab) != cudaSuccess || cudaMemset(c->d_Dext_act, 0, ab) != cudaSuccess)
-      return fail(SMPLB_ECUDA);
-    // gather the three columns of every active vertex from Dext (device-to-device strided copies)
-    for (int a = 0; a < c->n_act; ++a) {
-      if (cudaMemcpy2DAsync(c->d_Dext_act + 3 * a, (size_t)c->pitch_act * 4, c->d_Dext + 3 * (size_t)act[a],
-                            (size_t)c->pitch * 4, 12, KX, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess)
-        return fail(SMPLB_ECUDA);
-    }
+    if (cudaMalloc((void **)&c->d_Dext_act, ab) != cudaSuccess) return fail(SMPLB_ECUDA);
+    k_gather_dext<<<dim3(cdiv(c->pitch_act, 256), KX), 256, 0, c->stream>>>(c->n_act, c->Vpa, c->Vp, c->d_act_idx,
+                                                                           c->d_Dext, c->d_Dext_act);
+    c->launches++;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(SMPLB_ECUDA);
   }
   if (cudaMalloc((void **)&c->ws_scal, 64 * 4) != cudaSuccess ||
@@ -348,6 +372,7 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
   cudaMemset(c->ws_cnt64, 0, 8 * sizeof(long long));
   if ((rc = ensure_ws(c, c->max_batch))) return fail(rc);
   if ((rc = blend_tc_init(c))) return fail(rc);
+  if ((rc = skin_tc_init(c))) return fail(rc);
   *out = c;
   return 0;
 }
@@ -360,7 +385,7 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
   free_ws(c);
   void *ptrs[] = {c->d_vt,       c->d_shapedirs, c->d_posedirs, c->d_W,        c->d_JR,       c->d_Dext,   c->d_J0,
                   c->d_Jdirs,    c->d_kcsr_off,  c->d_kcsr_idx, c->d_kcsr_val, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val,
-                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
+                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_W16,      c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
                   c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -465,6 +490,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->use_tc = value;
     return 0;
   }
+  if (!strcmp(key, "skin_tc")) {
+    c->use_skin_tc = value;
+    return 0;
+  }
   if (!strcmp(key, "compact_bwd")) {
     c->use_compact = value;
     return 0;
@@ -511,8 +540,9 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   CUDA_TRY(cudaMemcpyAsync(c->ws_beta, beta, (size_t)B * c->NB * 4, cudaMemcpyDeviceToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->ws_theta, theta, (size_t)B * 72 * 4, cudaMemcpyDeviceToDevice, c->stream));
   bool tc = c->tc_ok && c->use_tc;
+  bool stc = c->skin_tc_ok && c->use_skin_tc;
   TRY(launch_pose_fwd(c, B, c->ws_beta, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, Jtr ? Jtr : c->ws_Jtr,
-                      tc ? nullptr : c->ws_x, tc ? c->ws_x16 : nullptr));
+                      tc ? nullptr : c->ws_x, tc ? c->ws_x16 : nullptr, stc ? c->ws_A16 : nullptr));
   if (Rs) CUDA_TRY(cudaMemcpyAsync(Rs, c->ws_Rs, (size_t)B * NJ * 9 * 4, cudaMemcpyDeviceToDevice, c->stream));
   if (tc) TRY(launch_blend_fwd_tc(c, B, c->ws_x16, c->ws_vposed));
   else TRY(launch_blend_fwd(c, B, c->ws_x, c->ws_vposed));
@@ -522,7 +552,8 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
     TRY(ensure_buf(c, &c->ws_verts, (size_t)c->ws_batch * c->V3, false));
     vout = c->ws_verts;
   }
-  TRY(launch_skin_fwd(c, B, c->ws_A, c->ws_vposed, vout));
+  if (stc) TRY(launch_skin_fwd_tc(c, B, c->ws_A16, c->ws_vposed, vout));
+  else TRY(launch_skin_fwd(c, B, c->ws_A, c->ws_vposed, vout));
   TRY(launch_joints(c, B, vout, cam, kp_gt, joints ? joints : c->ws_joints, kp_pred, kp_gt ? c->ws_dkp : nullptr,
                     kp_gt ? c->ws_part : nullptr, kp_gt ? c->ws_cnt : nullptr));
   c->saved_B = B;

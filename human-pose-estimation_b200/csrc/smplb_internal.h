@@ -30,7 +30,9 @@ struct smplb_ctx {
   cudaStream_t stream = nullptr;
   int V = 0, NB = 0, K = 0, max_batch = 0;
   int V3 = 0;       // 3V
-  int pitch = 0;    // row pitch (floats) of v_posed / dp / Dext: 3V rounded up to 128
+  int Vp = 0;       // V rounded up to 128
+  int pitch = 0;    // 3 * Vp: row pitch (floats) of v_posed / dp / Dext.  These are PLANAR: column c * Vp + v holds
+                    // coordinate c of vertex v (so a warp reads 32 vertices of one coordinate as one 128 B line)
   int ksplit = 1;   // split-K factor of the blend backward GEMM
   Tree tree;
   // ---- constants on the device
@@ -45,7 +47,7 @@ struct smplb_ctx {
   float *d_vcsr_val = nullptr;
   // ---- active vertices: rows of joint_regressor with a non-zero.  With no upstream d_verts
   //      the backward only has to walk these (every other vertex has a zero gradient).
-  int n_act = 0, pitch_act = 0;
+  int n_act = 0, Vpa = 0, pitch_act = 0;   // compact planar layout: column c * Vpa + a
   int use_compact = 1;             // smplb_debug_set("compact_bwd", 0) forces the dense walk (validation)
   int *d_act_idx = nullptr;
   float *d_act_W = nullptr;        // [n_act][24]
@@ -61,6 +63,12 @@ struct smplb_ctx {
   alignas(64) unsigned char map_d[128];   // CUtensorMap of Dt16
   int num_sms = 148;
   void *ws_x16 = nullptr;      // [B][256] fp16 operand rows
+  // ---- tcgen05 skinning path (k_skin_tc.cu)
+  bool skin_tc_ok = false;
+  int use_skin_tc = 1;         // smplb_debug_set("skin_tc", 0) selects the FP32 CUDA-core skinning kernel
+  void *d_W16 = nullptr;       // [Vp][128] fp16: W_hi | W_hi | W_lo | 0
+  alignas(64) unsigned char map_w[128];   // CUtensorMap of W16
+  void *ws_A16 = nullptr;      // [B*12][128] fp16: A_hi | A_lo | A_hi | 0, row (b, 4r+d)
   // ---- workspace, sized for max_batch (grown on demand)
   int ws_batch = 0;
   float *ws_x = nullptr;       // [B][KX]
@@ -161,7 +169,7 @@ __device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; 
 // ---- kernel launchers (device pointers only), one per stage -------------------------------
 // k_pose.cu
 int launch_pose_fwd(smplb_ctx *c, int B, const float *beta, const float *theta, float *Rs, float *J, float *A,
-                    float *Jtr, float *x, void *x16);
+                    float *Jtr, float *x, void *x16, void *A16);
 int launch_pose_bwd(smplb_ctx *c, int B, const float *theta, const float *Rs, const float *J, const float *A,
                     const float *dA_part, const float *dx_part, int ksplit, const float *d_Rs, float *d_beta,
                     float *d_theta);
@@ -175,6 +183,9 @@ int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part, bool 
 // k_blend_tc.cu
 int blend_tc_init(smplb_ctx *c);
 int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed);
+// k_skin_tc.cu
+int skin_tc_init(smplb_ctx *c);
+int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts);
 // k_skin.cu
 int launch_skin_fwd(smplb_ctx *c, int B, const float *A, const float *v_posed, float *verts);
 int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, const float *kp_gt, float *joints,
