@@ -14,8 +14,10 @@
 // tcgen05.ld, apply it to v_posed and write verts through a shared-memory transpose so both
 // global streams are fully coalesced.  The kernel is bound by those two streams.
 //
-// Persistent, warp-specialised: warp 0 TMA producer (W16 tile per vertex tile, A16 chunk per
-// tile), warp 1 MMA issuer + TMEM allocator, warps 2-5 epilogue; two TMEM accumulator stages.
+// Persistent, warp-specialised: warp 0 TMA producer of the MMA operands (W16 tile per vertex
+// tile, A16 chunk per tile), warp 1 MMA issuer + TMEM allocator, warps 2-5 epilogue, warp 6 TMA
+// producer of the v_posed tiles (a 4-deep ring, so ~100 KB of loads are in flight per SM: the
+// epilogue never waits on an HBM round trip); two TMEM accumulator stages.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -27,24 +29,29 @@
 #define ST_N (12 * ST_S)          // MMA N = 192
 #define ST_KP 128                 // padded K in shared memory (two 64-wide swizzle atoms)
 #define ST_ASTAGES 2
-#define ST_THREADS 192
+#define ST_PSTAGES 4
+#define ST_THREADS 224
 #define ST_W_BYTES (2 * ST_VT * 128)      // 32 KB: two k-blocks of 128 rows x 128 B
 #define ST_A_KB_BYTES (ST_N * 128)        // 24 KB: one k-block of the A16 chunk
 #define ST_A_BYTES (2 * ST_A_KB_BYTES)    // 48 KB
 #define ST_SM_W 0
 #define ST_SM_A (ST_W_BYTES)
-#define ST_SM_T (ST_SM_A + ST_ASTAGES * ST_A_BYTES)          // epilogue transpose staging: 4 warps x 96 floats
+#define ST_P_BYTES (3 * ST_S * ST_VT * 4)                    // 24 KB: v_posed tile [xyz][16 samples][128 vertices]
+#define ST_SM_P (ST_SM_A + ST_ASTAGES * ST_A_BYTES)
+#define ST_SM_T (ST_SM_P + ST_PSTAGES * ST_P_BYTES)          // epilogue transpose staging: 4 warps x 96 floats
 #define ST_SM_BAR (ST_SM_T + 4 * 96 * 4)
-#define ST_SM_TOTAL (ST_SM_BAR + 128)
+#define ST_SM_TOTAL (ST_SM_BAR + 256)
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
-    k_skin_tc(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_a, int B, int V, int Vp,
-              int n_vt, int n_ch, const float *__restrict__ v_posed, float *__restrict__ verts) {
+    k_skin_tc(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_a,
+              const __grid_constant__ CUtensorMap map_p, int B, int V, int Vp, int n_vt, int n_ch,
+              float *__restrict__ verts) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + ST_SM_BAR;
   const uint32_t full_a = bar0 + 0, empty_a = bar0 + 16, full_w = bar0 + 32, empty_w = bar0 + 40;
   const uint32_t tmem_full = bar0 + 48, tmem_empty = bar0 + 64;
+  const uint32_t full_p = bar0 + 128, empty_p = bar0 + 160;
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + ST_SM_BAR + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -58,6 +65,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
       mbar_init(empty_a + 8 * i, 1);
       mbar_init(tmem_full + 8 * i, 1);
       mbar_init(tmem_empty + 8 * i, 4);
+    }
+    for (int i = 0; i < ST_PSTAGES; ++i) {
+      mbar_init(full_p + 8 * i, 1);
+      mbar_init(empty_p + 8 * i, 4);   // one arrival per epilogue warp
     }
     mbar_init(full_w, 1);
     mbar_init(empty_w, 1);
@@ -134,17 +145,34 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
         }
       }
     }
+  } else if (warp == 6) {
+    // =========================== v_posed tile producer ===========================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        int vt = t / n_ch, ch = t % n_ch;
+        mbar_wait(empty_p + 8 * stage, phase ^ 1);
+        mbar_expect_tx(full_p + 8 * stage, ST_P_BYTES);
+        for (int cc = 0; cc < 3; ++cc)
+          tma_load_2d(sbase + ST_SM_P + stage * ST_P_BYTES + cc * (ST_S * ST_VT * 4), &map_p, cc * Vp + vt * ST_VT,
+                      ch * ST_S, full_p + 8 * stage);
+        if (++stage == ST_PSTAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
   } else {
     // =========================== epilogue (warps 2..5) ===========================
     const int q = warp & 3;                       // TMEM lane quarter: vertices 32q .. 32q+31 of the tile
     float *stg = reinterpret_cast<float *>(smem + ST_SM_T) + (warp - 2) * 96;
-    const size_t vp_row = 3 * (size_t)Vp;
-    int acc = 0, acc_phase = 0;
+    int acc = 0, acc_phase = 0, pst = 0, pphase = 0;
     for (int t = t0; t < t1; ++t) {
       int vt = t / n_ch, ch = t % n_ch;
       int v0 = vt * ST_VT + 32 * q;               // first vertex of this warp
-      int v = v0 + lane;
       int nv = min(32, V - v0);                   // valid vertices of this warp (<= 0: none)
+      mbar_wait(full_p + 8 * pst, pphase);          // v_posed tile landed in shared memory
+      const float *ptile = reinterpret_cast<const float *>(smem + ST_SM_P + pst * ST_P_BYTES) + 32 * q + lane;
       mbar_wait(tmem_full + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256;
@@ -164,8 +192,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
         for (int si = 0; si < 4; ++si) {
           int b = ch * ST_S + sg * 4 + si;
           if (b >= B || nv <= 0) continue;          // warp-uniform
-          const float *pr = v_posed + (size_t)b * vp_row + v;       // planar: three coalesced 128 B reads
-          float p0 = pr[0], p1 = pr[Vp], p2 = pr[2 * (size_t)Vp];
+          const float *pr = ptile + (sg * 4 + si) * ST_VT;          // [xyz][sample][vertex]
+          float p0 = pr[0], p1 = pr[ST_S * ST_VT], p2 = pr[2 * ST_S * ST_VT];
           const uint32_t *T = r + 12 * si;
           float o0 = fmaf(__uint_as_float(T[0]), p0, fmaf(__uint_as_float(T[1]), p1, fmaf(__uint_as_float(T[2]), p2, __uint_as_float(T[3]))));
           float o1 = fmaf(__uint_as_float(T[4]), p0, fmaf(__uint_as_float(T[5]), p1, fmaf(__uint_as_float(T[6]), p2, __uint_as_float(T[7]))));
@@ -182,6 +210,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
           if (lane + 32 < nflt) dst[lane + 32] = stg[lane + 32];
           if (lane + 64 < nflt) dst[lane + 64] = stg[lane + 64];
         }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_p + 8 * pst);        // this warp is done with the v_posed tile
+      if (++pst == ST_PSTAGES) {
+        pst = 0;
+        pphase ^= 1;
       }
       if (++acc == 2) {
         acc = 0;
@@ -251,12 +285,23 @@ int skin_tc_init(smplb_ctx *c) {
 
 int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts) {
   RET_IF(!c->skin_tc_ok, SMPLB_ESTATE, "tcgen05 skinning path is not initialised");
-  alignas(64) CUtensorMap map_a;
+  alignas(64) CUtensorMap map_a, map_p;
   TRY(make_map_f16(&map_a, (void *)A16, ST_KP, (uint64_t)B * 12, 64, ST_N));
+  {
+    // v_posed [B][3 * Vp] fp32, box = 128 vertices x 16 samples of one coordinate plane, no swizzle
+    cuuint64_t dims[2] = {(cuuint64_t)c->pitch, (cuuint64_t)B};
+    cuuint64_t strides[1] = {(cuuint64_t)c->pitch * 4};
+    cuuint32_t box[2] = {ST_VT, ST_S};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode2(&map_p, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)v_posed, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RET_IF(r != CUDA_SUCCESS, SMPLB_ECUDA, "cuTensorMapEncodeTiled(v_posed) failed with %d", (int)r);
+  }
   int n_vt = c->Vp / ST_VT, n_ch = cdiv(B, ST_S);
   int total = n_vt * n_ch;
   int grid = total < c->num_sms ? total : c->num_sms;
-  LAUNCH(c, "skin_fwd_tc", grid, ST_THREADS, ST_SM_TOTAL, k_skin_tc, *(const CUtensorMap *)c->map_w, map_a, B, c->V,
-         c->Vp, n_vt, n_ch, v_posed, verts);
+  LAUNCH(c, "skin_fwd_tc", grid, ST_THREADS, ST_SM_TOTAL, k_skin_tc, *(const CUtensorMap *)c->map_w, map_a, map_p, B,
+         c->V, c->Vp, n_vt, n_ch, verts);
   return 0;
 }

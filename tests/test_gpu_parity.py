@@ -352,3 +352,18 @@ def test_compact_backward_equals_dense_walk(smpl_full):
         ctx.debug_set("compact_bwd", 1)
     for k in ("d_beta", "d_theta", "d_cam"):
         assert rel_err(a[k], b[k]) < 2e-6, k
+
+
+def test_tcgen05_skinning_matches_fp32_kernel(smpl_full):
+    """T = W.A on the tensor cores (fp16 operands split into hi/lo so the product keeps
+    fp32-grade accuracy) against the FP32 CUDA-core skinning kernel."""
+    inp = synthetic.make_inputs(77, seed=31337)
+    ctx = smpl_full.ctx
+    try:
+        ctx.debug_set("skin_tc", 0)
+        v0, j0, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
+    finally:
+        ctx.debug_set("skin_tc", 1)
+    v1, j1, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
+    assert np.isfinite(v1).all()
+    assert rel_err(v1, v0) < 5e-6 and rel_err(j1, j0) < 5e-6
