@@ -56,8 +56,11 @@ def kernel_work(name, B):
         # name: (bound, bytes or flops per launch)
         "pose_fwd": ("hbm", B * (340 + 864 + 288 + 1152 + 288 + 4 * 224)),
         "blend_fwd_sgemm": ("tensor", 2.0 * B * 218 * 3 * V),
-        "blend_fwd_tc": ("hbm", B * vb + 2 * 240 * 3 * V),
+        "blend_fwd_tc": ("hbm", B * (vb + 512) + 2 * 256 * 3 * V),
         "skin_fwd": ("hbm", B * (2 * vb + 1152) + 24 * 4 * V),
+        "skin_fwd_tc": ("hbm", B * (2 * vb + 3072) + 2 * 128 * V),
+        "skin_bwd_active": ("hbm", B * (1152 + K * 12 + 4 * 1152 + 2 * 608 * 12)),
+        "blend_bwd_sgemm_active": ("tensor", 2.0 * B * 217 * 3 * 608),
         "joints_proj_kploss": ("hbm", B * (K * 32 * 32 + K * 12 + K * 20 + 12)),
         "skin_bwd": ("hbm", B * (2 * vb + 1152 + K * 12 + 4 * 1152)),
         "blend_bwd_sgemm": ("tensor", 2.0 * B * 217 * 3 * V),
@@ -270,11 +273,16 @@ def main():
     for p, s in zip(pin, host_sets):
         for k in s:
             p[k][...] = s[k]
-    eout = {"verts": None}
+    # outputs read back every step: loss, gradients, joints and projected keypoints, into pinned
+    # buffers; verts and Rs stay on the device (the trainer consumes them there)
+    eout = {"verts": None, "joints": runtime.pinned_empty((B, K, 3)), "kp_pred": runtime.pinned_empty((B, K, 2)),
+            "loss_parts": runtime.pinned_empty((4,)), "d_beta": runtime.pinned_empty((B, 10)),
+            "d_theta": runtime.pinned_empty((B, 72)), "d_cam": runtime.pinned_empty((B, 3))}
 
     def e2e_step(i):
         p = pin[i % NSET]
-        return smpl.step(p["beta"], p["theta"], p["cam"], p["kp_gt"], w_kp=60.0, want_verts=False, out=dict(eout))
+        return smpl.step(p["beta"], p["theta"], p["cam"], p["kp_gt"], w_kp=60.0, want_verts=False, out=eout,
+                         skip=("Rs",))
 
     for i in range(3):
         r = e2e_step(i)
@@ -285,7 +293,7 @@ def main():
     ctx.sync()
     e2e_s = time.perf_counter() - t0
     h2d = sum(v.nbytes for v in host_sets[0].values())
-    d2h = sum(r[k].nbytes for k in ("joints", "Rs", "kp_pred", "loss_parts", "d_beta", "d_theta", "d_cam"))
+    d2h = sum(r[k].nbytes for k in ("joints", "kp_pred", "loss_parts", "d_beta", "d_theta", "d_cam"))
 
     # ---- max over ranks
     if dist is not None:

@@ -280,6 +280,15 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
     return code;
   };
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(SMPLB_ECUDA);
+  {
+    // host-mode calls stage through stream-ordered allocations: keep the pool's memory across
+    // synchronisations instead of returning it to the driver after every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   size_t V = c->V;
   if ((rc = dev_upload(&c->d_vt, m->v_template, V * 3))) return fail(rc);
   if ((rc = dev_upload(&c->d_shapedirs, m->shapedirs, (size_t)c->NB * V * 3))) return fail(rc);

@@ -111,12 +111,14 @@ class SMPL(object):
 
     # -- one generator stage of Trainer.train_step + its backward -----------
     def step(self, beta, theta, cam, kp_gt, silhouette=None, w_kp=60.0, w_mesh=0.001, img_size=224.0,
-             backward=True, want_verts=True, kp_count_override=0, out=None):
+             backward=True, want_verts=True, kp_count_override=0, out=None, skip=()):
         """src/trainer.py:404-450 + :502 for one stage: SMPL forward, keypoint
         projection and loss, optional mesh-reprojection loss, and gradients
         w.r.t. beta/theta/cam.  `silhouette` = (points_xy [P,2], offsets [B+1])
         from ops.silhouette_csr.  Returns a dict.  `out` may hold preallocated
-        outputs of the right kind to avoid allocations in a timed loop."""
+        outputs of the right kind to avoid allocations in a timed loop; names in
+        `skip` (of "joints", "Rs", "kp_pred") are not returned (host mode: not
+        copied back)."""
         a = runtime.Args(self.ctx)
         N = int(beta.shape[0])
         V, K = self.size[0], self.num_keypoints
@@ -132,6 +134,9 @@ class SMPL(object):
         out = {} if out is None else out
 
         def o(name, shape, want=True):
+            if name in skip:
+                out[name] = None
+                return None, None
             if name in out and out[name] is not None:
                 x = out[name]
                 return x, (x.ptr if isinstance(x, runtime.DeviceArray) else x.ctypes.data)
