@@ -103,13 +103,13 @@ int launch_blend_fwd(smplb_ctx *c, int B, const float *x, float *v_posed) {
   return 0;
 }
 
-int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part, bool compact) {
+int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part, bool compact, int ksplit) {
   // compact: dp holds only the columns of the active vertices (rows of joint_regressor with a
   // non-zero), Dext_act the matching columns of Dext; every skipped column of dp is exactly 0.
   int pitch = compact ? c->pitch_act : c->pitch;
   const float *D = compact ? c->d_Dext_act : c->d_Dext;
-  int kchunk = cdiv(pitch / BK, c->ksplit) * BK;
-  dim3 grid(cdiv(KX, BN), cdiv(B, BM), c->ksplit);
+  int kchunk = cdiv(pitch / BK, ksplit) * BK;
+  dim3 grid(cdiv(KX, BN), cdiv(B, BM), ksplit);
   LAUNCH(c, compact ? "blend_bwd_sgemm_active" : "blend_bwd_sgemm", grid, 256, 0, k_sgemm<true>, B, KX, pitch, kchunk, dp,
          pitch, D, pitch, dx_part, KX);
   return 0;

@@ -312,16 +312,50 @@ int blend_tc_init(smplb_ctx *c) {
   return 0;
 }
 
-int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed) {
-  RET_IF(!c->tc_ok, SMPLB_ESTATE, "tcgen05 blend path is not initialised");
+// act: the same GEMM restricted to the active vertices (Dt16_act rows) -> v_posed_act [B][3*Vpa].
+int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed, bool act) {
+  RET_IF(!c->tc_ok || (act && !c->compact_ok), SMPLB_ESTATE, "tcgen05 blend path is not initialised");
+  int pitch = act ? c->pitch_act : c->pitch;
   alignas(64) CUtensorMap map_x, map_c;
   TRY(make_map_2d(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)x16, TC_KP, (uint64_t)B, TC_KP * 2, TC_KB, TC_BM));
-  TRY(make_map_2d(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)v_posed, (uint64_t)c->pitch, (uint64_t)B,
-                  (uint64_t)c->pitch * 4, 32, 32));
-  int n_mblk = cdiv(B, TC_BM), n_nblk = c->pitch / TC_BN;
+  TRY(make_map_2d(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)v_posed, (uint64_t)pitch, (uint64_t)B,
+                  (uint64_t)pitch * 4, 32, 32));
+  int n_mblk = cdiv(B, TC_BM), n_nblk = pitch / TC_BN;
   int total = n_mblk * n_nblk;
   int grid = total < c->num_sms ? total : c->num_sms;
-  LAUNCH(c, "blend_fwd_tc", grid, TC_THREADS, SM_TOTAL, k_blend_tc, map_x, *(const CUtensorMap *)c->map_d, map_c, n_mblk,
+  const CUtensorMap *md = (const CUtensorMap *)(act ? c->map_d_act : c->map_d);
+  LAUNCH(c, act ? "blend_fwd_tc_active" : "blend_fwd_tc", grid, TC_THREADS, SM_TOTAL, k_blend_tc, map_x, *md, map_c, n_mblk,
          n_nblk, c->tc_inv_scale);
+  return 0;
+}
+
+// Rows of a [rows][row_halves] fp16 matrix gathered by planar active index:
+// out[(cc * Vpa + a)][:] = in[(cc * Vp + act[a])][:] for cc < ncoord, zero for a >= n_act.
+__global__ void k_gather_rows16(int n_act, int Vpa, int Vp, int ncoord, int row_halves, const int *__restrict__ act,
+                                const __half *__restrict__ in, __half *__restrict__ out) {
+  int row = blockIdx.x;
+  int cc = row / Vpa, a = row % Vpa;
+  if (cc >= ncoord) return;
+  for (int k = threadIdx.x; k < row_halves; k += blockDim.x)
+    out[(size_t)row * row_halves + k] =
+        a < n_act ? in[((size_t)cc * Vp + act[a]) * row_halves + k] : __float2half_rn(0.f);
+}
+
+int compact_tc_init(smplb_ctx *c) {
+  c->compact_ok = false;
+  if (!c->tc_ok || !c->skin_tc_ok || c->n_act >= c->V || c->n_act == 0) return 0;
+  CUDA_TRY(cudaMalloc((void **)&c->d_Dt16_act, (size_t)c->pitch_act * TC_KP * sizeof(__half)));
+  CUDA_TRY(cudaMalloc((void **)&c->d_W16_act, (size_t)c->Vpa * 128 * sizeof(__half)));
+  k_gather_rows16<<<c->pitch_act, 128, 0, c->stream>>>(c->n_act, c->Vpa, c->Vp, 3, TC_KP, c->d_act_idx,
+                                                      (const __half *)c->d_Dt16, (__half *)c->d_Dt16_act);
+  k_gather_rows16<<<c->Vpa, 128, 0, c->stream>>>(c->n_act, c->Vpa, c->Vp, 1, 128, c->d_act_idx,
+                                                (const __half *)c->d_W16, (__half *)c->d_W16_act);
+  c->launches += 2;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  TRY(make_map_2d((CUtensorMap *)c->map_d_act, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c->d_Dt16_act, TC_KP,
+                  (uint64_t)c->pitch_act, TC_KP * 2, TC_KB, TC_BN));
+  TRY(make_map_2d((CUtensorMap *)c->map_w_act, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c->d_W16_act, 128, (uint64_t)c->Vpa,
+                  128 * 2, 64, 128));
+  c->compact_ok = true;
   return 0;
 }

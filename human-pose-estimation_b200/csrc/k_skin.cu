@@ -352,22 +352,30 @@ int launch_skin_fwd(smplb_ctx *c, int B, const float *A, const float *v_posed, f
   return 0;
 }
 
+// act: verts is the compact [B][n_act][3] tensor and the CSR indexes active slots.
 int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, const float *kp_gt, float *joints,
-                  float *kp_pred, float *dkp, float *part, int *cnt) {
-  LAUNCH(c, "joints_proj_kploss", B, 32 * c->K, 0, k_joints, B, c->V, c->K, c->d_kcsr_off, c->d_kcsr_idx,
-         c->d_kcsr_val, verts, cam, kp_gt, joints, kp_pred, dkp, part, cnt);
+                  float *kp_pred, float *dkp, float *part, int *cnt, bool act) {
+  LAUNCH(c, act ? "joints_proj_kploss_active" : "joints_proj_kploss", B, 32 * c->K, 0, k_joints, B,
+         act ? c->n_act : c->V, c->K, c->d_kcsr_off, act ? c->d_kcsr_slot : c->d_kcsr_idx, c->d_kcsr_val, verts, cam, kp_gt,
+         joints, kp_pred, dkp, part, cnt);
   return 0;
 }
 
 int launch_skin_bwd(smplb_ctx *c, int B, const float *A, const float *v_posed, const float *d_verts,
-                    const float *d_joints, float *dp, float *dA_part, bool compact) {
+                    const float *d_joints, float *dp, float *dA_part, int mode) {
+  // mode 0: every vertex.  mode 1: active vertices, v_posed gathered from the full tensor.
+  // mode 2: active vertices, v_posed is the compact v_posed_act (no gather).
   if (!(c->attr_done & 1u)) {
     CUDA_TRY(cudaFuncSetAttribute(k_skin_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SkinBwdSmem)));
     c->attr_done |= 1u;
   }
   dim3 grid(cdiv(B, SB_ST), VSPLIT);
-  if (compact) {
-    LAUNCH(c, "skin_bwd_active", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->n_act, c->V, c->K, c->Vp,
+  if (mode == 2) {
+    LAUNCH(c, "skin_bwd_active", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->n_act, c->n_act, c->K, c->Vpa,
+           c->Vpa, (const int *)nullptr, c->d_act_W, A, v_posed, (const float *)nullptr, d_joints, c->d_acsr_off,
+           c->d_acsr_k, c->d_acsr_val, dp, dA_part);
+  } else if (mode == 1) {
+    LAUNCH(c, "skin_bwd_active_gather", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->n_act, c->V, c->K, c->Vp,
            c->Vpa, c->d_act_idx, c->d_act_W, A, v_posed, (const float *)nullptr, d_joints, c->d_acsr_off,
            c->d_acsr_k, c->d_acsr_val, dp, dA_part);
   } else {

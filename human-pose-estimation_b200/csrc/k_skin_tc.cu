@@ -15,7 +15,7 @@
 // global streams are fully coalesced.  The kernel is bound by those two streams.
 //
 // Persistent, warp-specialised: warp 0 TMA producer of the MMA operands (W16 tile per vertex
-// tile, A16 chunk per tile), warp 1 MMA issuer + TMEM allocator, warps 2-5 epilogue, warp 6 TMA
+// tile, A16 chunk per tile), warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue, warp 10 TMA
 // producer of the v_posed tiles (a 4-deep ring, so ~100 KB of loads are in flight per SM: the
 // epilogue never waits on an HBM round trip); two TMEM accumulator stages.
 #include <cuda.h>
@@ -30,7 +30,7 @@
 #define ST_KP 128                 // padded K in shared memory (two 64-wide swizzle atoms)
 #define ST_ASTAGES 2
 #define ST_PSTAGES 4
-#define ST_THREADS 224
+#define ST_THREADS 352
 #define ST_W_BYTES (2 * ST_VT * 128)      // 32 KB: two k-blocks of 128 rows x 128 B
 #define ST_A_KB_BYTES (ST_N * 128)        // 24 KB: one k-block of the A16 chunk
 #define ST_A_BYTES (2 * ST_A_KB_BYTES)    // 48 KB
@@ -38,8 +38,7 @@
 #define ST_SM_A (ST_W_BYTES)
 #define ST_P_BYTES (3 * ST_S * ST_VT * 4)                    // 24 KB: v_posed tile [xyz][16 samples][128 vertices]
 #define ST_SM_P (ST_SM_A + ST_ASTAGES * ST_A_BYTES)
-#define ST_SM_T (ST_SM_P + ST_PSTAGES * ST_P_BYTES)          // epilogue transpose staging: 4 warps x 96 floats
-#define ST_SM_BAR (ST_SM_T + 4 * 96 * 4)
+#define ST_SM_BAR (ST_SM_P + ST_PSTAGES * ST_P_BYTES)
 #define ST_SM_TOTAL (ST_SM_BAR + 256)
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
@@ -64,11 +63,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
       mbar_init(full_a + 8 * i, 1);
       mbar_init(empty_a + 8 * i, 1);
       mbar_init(tmem_full + 8 * i, 1);
-      mbar_init(tmem_empty + 8 * i, 4);
+      mbar_init(tmem_empty + 8 * i, 8);   // one arrival per epilogue warp
     }
     for (int i = 0; i < ST_PSTAGES; ++i) {
       mbar_init(full_p + 8 * i, 1);
-      mbar_init(empty_p + 8 * i, 4);   // one arrival per epilogue warp
+      mbar_init(empty_p + 8 * i, 8);
     }
     mbar_init(full_w, 1);
     mbar_init(empty_w, 1);
@@ -145,7 +144,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 10) {
     // =========================== v_posed tile producer ===========================
     if (lane == 0) {
       int stage = 0, phase = 0;
@@ -163,52 +162,76 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
       }
     }
   } else {
-    // =========================== epilogue (warps 2..5) ===========================
-    const int q = warp & 3;                       // TMEM lane quarter: vertices 32q .. 32q+31 of the tile
-    float *stg = reinterpret_cast<float *>(smem + ST_SM_T) + (warp - 2) * 96;
+    // =========================== epilogue (warps 2..9) ===========================
+    // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31); each takes
+    // half of the tile's 16 samples, 4 samples at a time so the TMEM loads, the shared-memory
+    // reads of v_posed and the stores of one group overlap instead of serialising.
+    const int q = warp & 3;                       // vertices 32q .. 32q+31 of the tile
+    const int half = (warp - 2) >> 2;             // sample groups {2*half, 2*half+1}
     int acc = 0, acc_phase = 0, pst = 0, pphase = 0;
     for (int t = t0; t < t1; ++t) {
       int vt = t / n_ch, ch = t % n_ch;
       int v0 = vt * ST_VT + 32 * q;               // first vertex of this warp
-      int nv = min(32, V - v0);                   // valid vertices of this warp (<= 0: none)
-      mbar_wait(full_p + 8 * pst, pphase);          // v_posed tile landed in shared memory
-      const float *ptile = reinterpret_cast<const float *>(smem + ST_SM_P + pst * ST_P_BYTES) + 32 * q + lane;
+      int nflt = 3 * min(32, V - v0);             // floats of verts this warp owns per sample (<= 0: none)
+      mbar_wait(full_p + 8 * pst, pphase);        // v_posed tile landed in shared memory
+      float *ptile = reinterpret_cast<float *>(smem + ST_SM_P + pst * ST_P_BYTES) + 32 * q;
       mbar_wait(tmem_full + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256;
 #pragma unroll 1
-      for (int sg = 0; sg < ST_S / 4; ++sg) {
-        // T of 4 samples: 48 fp32 columns
-        uint32_t r[48];
+      for (int g2 = 0; g2 < 2; ++g2) {
+        const int sg = 2 * half + g2;
+        uint32_t r[48];                           // T of 4 samples: 48 fp32 columns
 #pragma unroll
         for (int i = 0; i < 12; ++i) tc_ld_32x4(trow + sg * 48 + i * 4, r + 4 * i);
+        float p[4][3];
+#pragma unroll
+        for (int si = 0; si < 4; ++si) {
+          const float *pr = ptile + (sg * 4 + si) * ST_VT + lane;   // [xyz][sample][vertex]
+          p[si][0] = pr[0];
+          p[si][1] = pr[ST_S * ST_VT];
+          p[si][2] = pr[2 * ST_S * ST_VT];
+        }
         tc_wait_ld();
-        if (sg == ST_S / 4 - 1) {
+        if (g2 == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);   // accumulator fully read
+          if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);   // this warp has read its share of the accumulator
         }
+        float o[4][3];
+#pragma unroll
+        for (int si = 0; si < 4; ++si) {
+          const uint32_t *T = r + 12 * si;
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr)
+            o[si][rr] = fmaf(__uint_as_float(T[4 * rr]), p[si][0],
+                             fmaf(__uint_as_float(T[4 * rr + 1]), p[si][1],
+                                  fmaf(__uint_as_float(T[4 * rr + 2]), p[si][2], __uint_as_float(T[4 * rr + 3]))));
+        }
+        // Transpose [vertex][xyz] in place: the 96 floats this warp owns per sample in the v_posed
+        // tile are reused as staging (every lane has its p in registers by now).  Float i of the
+        // warp's 96 lives at segment i / 32, lane slot i % 32: conflict-free both ways.
+        __syncwarp();
+#pragma unroll
+        for (int si = 0; si < 4; ++si) {
+          float *base = ptile + (sg * 4 + si) * ST_VT;
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr) {
+            int i = 3 * lane + rr;
+            base[(i >> 5) * (ST_S * ST_VT) + (i & 31)] = o[si][rr];
+          }
+        }
+        __syncwarp();
 #pragma unroll
         for (int si = 0; si < 4; ++si) {
           int b = ch * ST_S + sg * 4 + si;
-          if (b >= B || nv <= 0) continue;          // warp-uniform
-          const float *pr = ptile + (sg * 4 + si) * ST_VT;          // [xyz][sample][vertex]
-          float p0 = pr[0], p1 = pr[ST_S * ST_VT], p2 = pr[2 * ST_S * ST_VT];
-          const uint32_t *T = r + 12 * si;
-          float o0 = fmaf(__uint_as_float(T[0]), p0, fmaf(__uint_as_float(T[1]), p1, fmaf(__uint_as_float(T[2]), p2, __uint_as_float(T[3]))));
-          float o1 = fmaf(__uint_as_float(T[4]), p0, fmaf(__uint_as_float(T[5]), p1, fmaf(__uint_as_float(T[6]), p2, __uint_as_float(T[7]))));
-          float o2 = fmaf(__uint_as_float(T[8]), p0, fmaf(__uint_as_float(T[9]), p1, fmaf(__uint_as_float(T[10]), p2, __uint_as_float(T[11]))));
-          // transpose through shared memory: [vertex][xyz] is contiguous in verts
-          __syncwarp();
-          stg[3 * lane + 0] = o0;
-          stg[3 * lane + 1] = o1;
-          stg[3 * lane + 2] = o2;
-          __syncwarp();
-          float *dst = verts + ((size_t)b * V + v0) * 3;
-          int nflt = 3 * nv;
-          if (lane < nflt) dst[lane] = stg[lane];
-          if (lane + 32 < nflt) dst[lane + 32] = stg[lane + 32];
-          if (lane + 64 < nflt) dst[lane + 64] = stg[lane + 64];
+          if (b >= B) continue;                   // warp-uniform
+          const float *base = ptile + (sg * 4 + si) * ST_VT + lane;
+          float *dst = verts + ((size_t)b * V + v0) * 3 + lane;
+          float x0 = base[0], x1 = base[ST_S * ST_VT], x2 = base[2 * ST_S * ST_VT];
+          if (lane < nflt) __stcs(dst, x0);
+          if (lane + 32 < nflt) __stcs(dst + 32, x1);
+          if (lane + 64 < nflt) __stcs(dst + 64, x2);
         }
       }
       __syncwarp();
@@ -283,14 +306,16 @@ int skin_tc_init(smplb_ctx *c) {
   return 0;
 }
 
-int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts) {
-  RET_IF(!c->skin_tc_ok, SMPLB_ESTATE, "tcgen05 skinning path is not initialised");
+// act: the same kernel on the active vertices (W16_act, v_posed_act) -> verts_act [B][n_act][3].
+int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts, bool act) {
+  RET_IF(!c->skin_tc_ok || (act && !c->compact_ok), SMPLB_ESTATE, "tcgen05 skinning path is not initialised");
+  const int V = act ? c->n_act : c->V, Vp = act ? c->Vpa : c->Vp, pitch = act ? c->pitch_act : c->pitch;
   alignas(64) CUtensorMap map_a, map_p;
   TRY(make_map_f16(&map_a, (void *)A16, ST_KP, (uint64_t)B * 12, 64, ST_N));
   {
     // v_posed [B][3 * Vp] fp32, box = 128 vertices x 16 samples of one coordinate plane, no swizzle
-    cuuint64_t dims[2] = {(cuuint64_t)c->pitch, (cuuint64_t)B};
-    cuuint64_t strides[1] = {(cuuint64_t)c->pitch * 4};
+    cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)B};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
     cuuint32_t box[2] = {ST_VT, ST_S};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode2(&map_p, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)v_posed, dims, strides, box, estr,
@@ -298,10 +323,11 @@ int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_pose
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RET_IF(r != CUDA_SUCCESS, SMPLB_ECUDA, "cuTensorMapEncodeTiled(v_posed) failed with %d", (int)r);
   }
-  int n_vt = c->Vp / ST_VT, n_ch = cdiv(B, ST_S);
+  int n_vt = Vp / ST_VT, n_ch = cdiv(B, ST_S);
   int total = n_vt * n_ch;
   int grid = total < c->num_sms ? total : c->num_sms;
-  LAUNCH(c, "skin_fwd_tc", grid, ST_THREADS, ST_SM_TOTAL, k_skin_tc, *(const CUtensorMap *)c->map_w, map_a, map_p, B,
-         c->V, c->Vp, n_vt, n_ch, verts);
+  const CUtensorMap *mw = (const CUtensorMap *)(act ? c->map_w_act : c->map_w);
+  LAUNCH(c, act ? "skin_fwd_tc_active" : "skin_fwd_tc", grid, ST_THREADS, ST_SM_TOTAL, k_skin_tc, *mw, map_a, map_p, B, V,
+         Vp, n_vt, n_ch, verts);
   return 0;
 }

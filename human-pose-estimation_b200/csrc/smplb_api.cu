@@ -176,7 +176,7 @@ static void free_ws(smplb_ctx *c) {
                    (void **)&c->ws_vposed, (void **)&c->ws_verts, (void **)&c->ws_joints, (void **)&c->ws_kp,
                    (void **)&c->ws_dkp, (void **)&c->ws_djoints, (void **)&c->ws_dverts, (void **)&c->ws_dp, (void **)&c->ws_dA,
                    (void **)&c->ws_dx, (void **)&c->ws_part, (void **)&c->ws_cnt, (void **)&c->ws_theta,
-                   (void **)&c->ws_beta, (void **)&c->ws_gp, (void **)&c->ws_x16, (void **)&c->ws_dp_act, (void **)&c->ws_A16};
+                   (void **)&c->ws_beta, (void **)&c->ws_gp, (void **)&c->ws_x16, (void **)&c->ws_dp_act, (void **)&c->ws_A16, (void **)&c->ws_vposed_act, (void **)&c->ws_verts_act};
   for (void **p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -360,6 +360,12 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
       for (int j = 0; j < NJ; ++j) aW.push_back(m->weights[v * NJ + j]);
     }
     c->n_act = (int)act.size();
+    {
+      std::vector<int> slot_of(V, -1), kslot(kidx.size());
+      for (size_t a = 0; a < act.size(); ++a) slot_of[act[a]] = (int)a;
+      for (size_t e = 0; e < kidx.size(); ++e) kslot[e] = slot_of[kidx[e]];
+      if ((rc = dev_upload(&c->d_kcsr_slot, kslot.data(), kslot.size()))) return fail(rc);
+    }
     c->Vpa = std::max(128, cdiv(c->n_act, 128) * 128);
     c->pitch_act = 3 * c->Vpa;
     if ((rc = dev_upload(&c->d_act_idx, act.data(), act.size()))) return fail(rc);
@@ -382,6 +388,7 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
   if ((rc = ensure_ws(c, c->max_batch))) return fail(rc);
   if ((rc = blend_tc_init(c))) return fail(rc);
   if ((rc = skin_tc_init(c))) return fail(rc);
+  if ((rc = compact_tc_init(c))) return fail(rc);
   *out = c;
   return 0;
 }
@@ -394,7 +401,7 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
   free_ws(c);
   void *ptrs[] = {c->d_vt,       c->d_shapedirs, c->d_posedirs, c->d_W,        c->d_JR,       c->d_Dext,   c->d_J0,
                   c->d_Jdirs,    c->d_kcsr_off,  c->d_kcsr_idx, c->d_kcsr_val, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val,
-                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_W16,      c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
+                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_W16,      c->d_Dt16_act, c->d_W16_act,  c->d_kcsr_slot, c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
                   c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -553,18 +560,38 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   TRY(launch_pose_fwd(c, B, c->ws_beta, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, Jtr ? Jtr : c->ws_Jtr,
                       tc ? nullptr : c->ws_x, tc ? c->ws_x16 : nullptr, stc ? c->ws_A16 : nullptr));
   if (Rs) CUDA_TRY(cudaMemcpyAsync(Rs, c->ws_Rs, (size_t)B * NJ * 9 * 4, cudaMemcpyDeviceToDevice, c->stream));
-  if (tc) TRY(launch_blend_fwd_tc(c, B, c->ws_x16, c->ws_vposed));
-  else TRY(launch_blend_fwd(c, B, c->ws_x, c->ws_vposed));
+  // Keypoint path on the active vertices only (rows of joint_regressor with a non-zero): the
+  // same two tensor-core kernels on ~9 % of the vertices give joints without reading verts back.
+  bool compact = tc && stc && c->compact_ok && c->use_compact;
+  bool full = need_verts || !compact;
+  if (full) {
+    if (tc) TRY(launch_blend_fwd_tc(c, B, c->ws_x16, c->ws_vposed, false));
+    else TRY(launch_blend_fwd(c, B, c->ws_x, c->ws_vposed));
+  }
   float *vout = verts;
-  if (!vout) {
-    (void)need_verts;
+  if (full && !vout) {
     TRY(ensure_buf(c, &c->ws_verts, (size_t)c->ws_batch * c->V3, false));
     vout = c->ws_verts;
   }
-  if (stc) TRY(launch_skin_fwd_tc(c, B, c->ws_A16, c->ws_vposed, vout));
-  else TRY(launch_skin_fwd(c, B, c->ws_A, c->ws_vposed, vout));
-  TRY(launch_joints(c, B, vout, cam, kp_gt, joints ? joints : c->ws_joints, kp_pred, kp_gt ? c->ws_dkp : nullptr,
-                    kp_gt ? c->ws_part : nullptr, kp_gt ? c->ws_cnt : nullptr));
+  if (full) {
+    if (stc) TRY(launch_skin_fwd_tc(c, B, c->ws_A16, c->ws_vposed, vout, false));
+    else TRY(launch_skin_fwd(c, B, c->ws_A, c->ws_vposed, vout));
+  }
+  c->saved_full = full;
+  c->saved_verts = vout;
+  float *jout = joints ? joints : c->ws_joints;
+  if (compact) {
+    TRY(ensure_buf(c, &c->ws_vposed_act, (size_t)c->ws_batch * c->pitch_act, false));
+    TRY(ensure_buf(c, &c->ws_verts_act, (size_t)c->ws_batch * c->n_act * 3, false));
+    TRY(launch_blend_fwd_tc(c, B, c->ws_x16, c->ws_vposed_act, true));
+    TRY(launch_skin_fwd_tc(c, B, c->ws_A16, c->ws_vposed_act, c->ws_verts_act, true));
+    TRY(launch_joints(c, B, c->ws_verts_act, cam, kp_gt, jout, kp_pred, kp_gt ? c->ws_dkp : nullptr,
+                      kp_gt ? c->ws_part : nullptr, kp_gt ? c->ws_cnt : nullptr, true));
+  } else {
+    TRY(launch_joints(c, B, vout, cam, kp_gt, jout, kp_pred, kp_gt ? c->ws_dkp : nullptr, kp_gt ? c->ws_part : nullptr,
+                      kp_gt ? c->ws_cnt : nullptr, false));
+  }
+  c->saved_compact = compact;
   c->saved_B = B;
   return 0;
 }
@@ -584,10 +611,19 @@ static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const fl
     TRY(ensure_buf(c, &c->ws_dp, (size_t)c->ws_batch * c->pitch, true));
     dp = c->ws_dp;
   }
-  TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed, d_verts, d_joints, dp, c->ws_dA, compact));
-  TRY(launch_blend_bwd(c, B, dp, c->ws_dx, compact));
-  TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, c->ws_dx, c->ksplit, d_Rs, d_beta,
-                      d_theta));
+  if ((!compact || !c->saved_compact) && !c->saved_full) {
+    // the forward skipped the 6890-vertex tensors (no verts requested): rebuild v_posed now
+    if (c->tc_ok && c->use_tc) TRY(launch_blend_fwd_tc(c, B, c->ws_x16, c->ws_vposed, false));
+    else RET_IF(true, SMPLB_ESTATE, "v_posed was not saved by the forward");
+    c->saved_full = true;
+  }
+  if (compact && c->saved_compact)
+    TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed_act, nullptr, d_joints, dp, c->ws_dA, 2));
+  else
+    TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed, d_verts, d_joints, dp, c->ws_dA, compact ? 1 : 0));
+  int ks = compact ? 4 : c->ksplit;   // the compact contraction is 11x shorter: fewer split-K partials
+  TRY(launch_blend_bwd(c, B, dp, c->ws_dx, compact, ks));
+  TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, c->ws_dx, ks, d_Rs, d_beta, d_theta));
   return 0;
 }
 
@@ -852,8 +888,9 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
   if (have_mesh && !dpts) dpts = c->ws_scal;
 
   float *jbuf = ojoints ? ojoints : c->ws_joints;
-  TRY(smpl_forward_dev(c, B, dbeta, dtheta, overts, jbuf, oRs, nullptr, dcam, dkpgt, okp ? okp : c->ws_kp, true));
-  const float *vbuf = overts ? overts : c->ws_verts;
+  TRY(smpl_forward_dev(c, B, dbeta, dtheta, overts, jbuf, oRs, nullptr, dcam, dkpgt, okp ? okp : c->ws_kp,
+                       overts != nullptr || have_mesh));
+  const float *vbuf = c->saved_verts;
   TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, c->ws_scal + 0, c->ws_cnt64, c->ws_scal + 1));
   if (have_mesh) {
     TRY(launch_proj(c, B, c->V, vbuf, dcam, 1, img_size, img_size, c->ws_silpred));

@@ -55,6 +55,19 @@ struct smplb_ctx {
   float *d_acsr_val = nullptr;
   float *d_Dext_act = nullptr;     // [KX][pitch_act]
   float *ws_dp_act = nullptr;      // [B][pitch_act]
+  // compact keypoint path: the same blend / skinning kernels run on the active vertices only, so
+  // joints, the keypoint loss and its backward never touch the 6890-vertex tensors
+  void *d_Dt16_act = nullptr;      // [3*Vpa][256] fp16: rows of Dt16 gathered
+  void *d_W16_act = nullptr;       // [Vpa][128] fp16
+  alignas(64) unsigned char map_d_act[128];
+  alignas(64) unsigned char map_w_act[128];
+  int *d_kcsr_slot = nullptr;      // kcsr_idx re-indexed to active slots
+  float *ws_vposed_act = nullptr;  // [B][3*Vpa]
+  float *ws_verts_act = nullptr;   // [B][n_act][3]
+  bool compact_ok = false;
+  bool saved_full = false;         // ws_vposed holds the last forward's full v_posed
+  bool saved_compact = false;      // ws_vposed_act holds the last forward's compact v_posed
+  float *saved_verts = nullptr;    // where the last forward wrote verts (caller's buffer or ws_verts)
   // ---- tcgen05 blend path (k_blend_tc.cu)
   bool tc_ok = false;          // operands built, tensor map encoded
   int use_tc = 1;              // smplb_debug_set("blend_tc", 0) selects the FP32 CUDA-core GEMM (validation)
@@ -179,19 +192,20 @@ int launch_skew(smplb_ctx *c, int N, const float *vec, float *out);
 int launch_lrotmin(smplb_ctx *c, int B, const float *theta, float *out);
 // k_blend.cu
 int launch_blend_fwd(smplb_ctx *c, int B, const float *x, float *v_posed);
-int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part, bool compact);
+int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part, bool compact, int ksplit);
 // k_blend_tc.cu
 int blend_tc_init(smplb_ctx *c);
-int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed);
+int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed, bool act);
 // k_skin_tc.cu
 int skin_tc_init(smplb_ctx *c);
-int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts);
+int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts, bool act);
+int compact_tc_init(smplb_ctx *c);
 // k_skin.cu
 int launch_skin_fwd(smplb_ctx *c, int B, const float *A, const float *v_posed, float *verts);
 int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, const float *kp_gt, float *joints,
-                  float *kp_pred, float *dkp, float *part, int *cnt);
+                  float *kp_pred, float *dkp, float *part, int *cnt, bool act);
 int launch_skin_bwd(smplb_ctx *c, int B, const float *A, const float *v_posed, const float *d_verts,
-                    const float *d_joints, float *dp, float *dA_part, bool compact);
+                    const float *d_joints, float *dp, float *dA_part, int mode);
 int launch_proj(smplb_ctx *c, int B, int N, const float *X, const float *cam, int pixel, float im_w, float im_h,
                 float *out);
 int launch_proj_bwd(smplb_ctx *c, int B, int N, const float *X, const float *cam, const float *d_out, int pixel,
