@@ -506,6 +506,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->use_tc = value;
     return 0;
   }
+  if (!strcmp(key, "l2_chunk")) {
+    c->l2_chunk = value;
+    return 0;
+  }
   if (!strcmp(key, "skin_tc")) {
     c->use_skin_tc = value;
     return 0;
@@ -564,20 +568,31 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   // same two tensor-core kernels on ~9 % of the vertices give joints without reading verts back.
   bool compact = tc && stc && c->compact_ok && c->use_compact;
   bool full = need_verts || !compact;
-  if (full) {
-    if (tc) TRY(launch_blend_fwd_tc(c, B, c->ws_x16, c->ws_vposed, false));
-    else TRY(launch_blend_fwd(c, B, c->ws_x, c->ws_vposed));
-  }
   float *vout = verts;
   if (full && !vout) {
     TRY(ensure_buf(c, &c->ws_verts, (size_t)c->ws_batch * c->V3, false));
     vout = c->ws_verts;
   }
-  if (full) {
+  // L2-resident hand-over: blend and skinning run chunk by chunk over the samples, the
+  // v_posed of a chunk (chunk * 83 KB, 42 MB at 512) is written and read back inside the 126 MB
+  // L2 and the same buffer is reused by the next chunk, so v_posed never makes the HBM round
+  // trip.  The dense backward rebuilds v_posed when it needs it (saved_full = false).
+  int chunk = c->l2_chunk;
+  bool chunked = full && tc && stc && chunk > 0 && B > chunk;
+  if (full && chunked) {
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+      int nb = std::min(chunk, B - b0);
+      TRY(launch_blend_fwd_tc(c, nb, (const char *)c->ws_x16 + (size_t)b0 * 512, c->ws_vposed, false));
+      TRY(launch_skin_fwd_tc(c, nb, (const char *)c->ws_A16 + (size_t)b0 * 12 * 256, c->ws_vposed,
+                             vout + (size_t)b0 * c->V3, false));
+    }
+  } else if (full) {
+    if (tc) TRY(launch_blend_fwd_tc(c, B, c->ws_x16, c->ws_vposed, false));
+    else TRY(launch_blend_fwd(c, B, c->ws_x, c->ws_vposed));
     if (stc) TRY(launch_skin_fwd_tc(c, B, c->ws_A16, c->ws_vposed, vout, false));
     else TRY(launch_skin_fwd(c, B, c->ws_A, c->ws_vposed, vout));
   }
-  c->saved_full = full;
+  c->saved_full = full && !chunked;
   c->saved_verts = vout;
   float *jout = joints ? joints : c->ws_joints;
   if (compact) {

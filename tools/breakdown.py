@@ -24,6 +24,8 @@ if mesh:
     pts, offs = ops.silhouette_csr(synthetic.silhouette_points(seg), B)
     print("silhouette points:", len(pts), "mean per image", len(pts) / B)
     sil = (ctx.to_device(pts), ctx.to_device(offs, np.int32))
+if os.environ.get("L2_CHUNK"):
+    ctx.debug_set("l2_chunk", int(os.environ["L2_CHUNK"]))
 out = {}
 for it in range(3):
     smpl.step(d["beta"], d["theta"], d["cam"], d["kp_gt"], silhouette=sil, out=out)
