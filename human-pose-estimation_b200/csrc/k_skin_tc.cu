@@ -34,10 +34,10 @@
 #define ST_W_BYTES (2 * ST_VT * 128)      // 32 KB: two k-blocks of 128 rows x 128 B
 #define ST_A_KB_BYTES (ST_N * 128)        // 24 KB: one k-block of the A16 chunk
 #define ST_A_BYTES (2 * ST_A_KB_BYTES)    // 48 KB
-#define ST_SM_W 0
-#define ST_SM_A (ST_W_BYTES)
+#define ST_SM_A 0                                            // resident A16 chunk (reloaded when the sample chunk changes)
+#define ST_SM_W (ST_A_BYTES)                                 // W16 tile ring
 #define ST_P_BYTES (3 * ST_S * ST_VT * 4)                    // 24 KB: v_posed tile [xyz][16 samples][128 vertices]
-#define ST_SM_P (ST_SM_A + ST_ASTAGES * ST_A_BYTES)
+#define ST_SM_P (ST_SM_W + ST_ASTAGES * ST_W_BYTES)
 #define ST_SM_BAR (ST_SM_P + ST_PSTAGES * ST_P_BYTES)
 #define ST_SM_TOTAL (ST_SM_BAR + 256)
 
@@ -86,21 +86,25 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      int cur_vt = -1, w_loads = 0, stage = 0, phase = 0;
+      // tiles are ordered sample-chunk major: consecutive tiles of a CTA walk adjacent vertex
+      // tiles of the same 16 samples (adjacent 512 B / 1536 B segments of the same v_posed /
+      // verts rows).  The A16 chunk is loaded once per chunk, W16 tiles (L2-resident, 1.8 MB in
+      // total) stream through a 2-deep ring.
+      int cur_ch = -1, a_loads = 0, stage = 0, phase = 0;
       for (int t = t0; t < t1; ++t) {
-        int vt = t / n_ch, ch = t % n_ch;
-        if (vt != cur_vt) {
-          if (w_loads > 0) mbar_wait(empty_w, (w_loads - 1) & 1);
-          mbar_expect_tx(full_w, ST_W_BYTES);
+        int ch = t / n_vt, vt = t % n_vt;
+        if (ch != cur_ch) {
+          if (a_loads > 0) mbar_wait(empty_w, (a_loads - 1) & 1);
+          mbar_expect_tx(full_w, ST_A_BYTES);
           for (int kb = 0; kb < 2; ++kb)
-            tma_load_2d(sbase + ST_SM_W + kb * (ST_VT * 128), &map_w, kb * 64, vt * ST_VT, full_w);
-          ++w_loads;
-          cur_vt = vt;
+            tma_load_2d(sbase + ST_SM_A + kb * ST_A_KB_BYTES, &map_a, kb * 64, ch * ST_N, full_w);
+          ++a_loads;
+          cur_ch = ch;
         }
         mbar_wait(empty_a + 8 * stage, phase ^ 1);
-        mbar_expect_tx(full_a + 8 * stage, ST_A_BYTES);
+        mbar_expect_tx(full_a + 8 * stage, ST_W_BYTES);
         for (int kb = 0; kb < 2; ++kb)
-          tma_load_2d(sbase + ST_SM_A + stage * ST_A_BYTES + kb * ST_A_KB_BYTES, &map_a, kb * 64, ch * ST_N,
+          tma_load_2d(sbase + ST_SM_W + stage * ST_W_BYTES + kb * (ST_VT * 128), &map_w, kb * 64, vt * ST_VT,
                       full_a + 8 * stage);
         if (++stage == ST_ASTAGES) {
           stage = 0;
@@ -112,19 +116,19 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(ST_VT, ST_N);
-      int cur_vt = -1, w_loads = 0, stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      int cur_ch = -1, a_loads = 0, stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int t = t0; t < t1; ++t) {
-        int vt = t / n_ch;
-        if (vt != cur_vt) {
-          mbar_wait(full_w, w_loads & 1);
-          ++w_loads;
-          cur_vt = vt;
+        int ch = t / n_vt;
+        if (ch != cur_ch) {
+          mbar_wait(full_w, a_loads & 1);
+          ++a_loads;
+          cur_ch = ch;
         }
         mbar_wait(tmem_empty + 8 * acc, acc_phase ^ 1);
         mbar_wait(full_a + 8 * stage, phase);
         tc_fence_after();
         uint32_t d_tmem = tmem_base + acc * 256;
-        uint32_t w_addr = sbase + ST_SM_W, a_addr = sbase + ST_SM_A + stage * ST_A_BYTES;
+        uint32_t w_addr = sbase + ST_SM_W + stage * ST_W_BYTES, a_addr = sbase + ST_SM_A;
         // K = 80: four 16-wide steps in the first swizzle atom, one in the second
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -132,8 +136,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
         tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + ST_VT * 128), umma_desc_sw128(a_addr + ST_A_KB_BYTES), idesc, 1);
         tc_commit(empty_a + 8 * stage);
         tc_commit(tmem_full + 8 * acc);
-        bool last_of_vt = (t + 1 == t1) || ((t + 1) / n_ch != vt);
-        if (last_of_vt) tc_commit(empty_w);
+        bool last_of_ch = (t + 1 == t1) || ((t + 1) / n_vt != ch);
+        if (last_of_ch) tc_commit(empty_w);
         if (++stage == ST_ASTAGES) {
           stage = 0;
           phase ^= 1;
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
     if (lane == 0) {
       int stage = 0, phase = 0;
       for (int t = t0; t < t1; ++t) {
-        int vt = t / n_ch, ch = t % n_ch;
+        int ch = t / n_vt, vt = t % n_vt;
         mbar_wait(empty_p + 8 * stage, phase ^ 1);
         mbar_expect_tx(full_p + 8 * stage, ST_P_BYTES);
         for (int cc = 0; cc < 3; ++cc)
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
     const int half = (warp - 2) >> 2;             // sample groups {2*half, 2*half+1}
     int acc = 0, acc_phase = 0, pst = 0, pphase = 0;
     for (int t = t0; t < t1; ++t) {
-      int vt = t / n_ch, ch = t % n_ch;
+      int ch = t / n_vt, vt = t % n_vt;
       int v0 = vt * ST_VT + 32 * q;               // first vertex of this warp
       int nflt = 3 * min(32, V - v0);             // floats of verts this warp owns per sample (<= 0: none)
       mbar_wait(full_p + 8 * pst, pphase);        // v_posed tile landed in shared memory

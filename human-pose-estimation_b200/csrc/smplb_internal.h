@@ -65,7 +65,7 @@ struct smplb_ctx {
   float *ws_vposed_act = nullptr;  // [B][3*Vpa]
   float *ws_verts_act = nullptr;   // [B][n_act][3]
   bool compact_ok = false;
-  int l2_chunk = 512;              // samples per L2-resident blend->skin chunk (0 = off); smplb_debug_set("l2_chunk", n)
+  int l2_chunk = 0;                // samples per L2-resident blend->skin chunk (0 = off); smplb_debug_set("l2_chunk", n)
   bool saved_full = false;         // ws_vposed holds the last forward's full v_posed
   bool saved_compact = false;      // ws_vposed_act holds the last forward's compact v_posed
   float *saved_verts = nullptr;    // where the last forward wrote verts (caller's buffer or ws_verts)
