@@ -14,7 +14,7 @@
 // the epilogue multiplies by 2^-s (exact).
 //
 // Kernel shape: persistent, one CTA per SM, warp-specialised:
-//   warp 0   TMA producer (x16 tile per output tile, Dt16 tile per N block)
+//   warp 0   TMA producer (x16 tile per sample block, Dt16 tiles through a 2-deep ring)
 //   warp 1   tcgen05.mma issuer (one lane), TMEM allocator
 //   warps 2-5  epilogue: tcgen05.ld -> scale -> swizzled smem staging -> TMA store
 // Tile 128 (samples) x 128 (vertex coordinates); two TMEM accumulator stages so the MMAs of
@@ -85,22 +85,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      int cur_n = -1, b_loads = 0, stage = 0, phase = 0;
+      // tiles are ordered sample-block major: consecutive tiles of a CTA write adjacent 512 B
+      // column ranges of the same 128 v_posed rows.  The x16 tile is loaded once per sample
+      // block; Dt16 tiles (10.6 MB in total, L2-resident) stream through a 2-deep ring.
+      int cur_m = -1, x_loads = 0, stage = 0, phase = 0;
       for (int t = t0; t < t1; ++t) {
-        int n = t / n_mblk, m = t % n_mblk;
-        if (n != cur_n) {
-          if (b_loads > 0) mbar_wait(empty_b, (b_loads - 1) & 1);   // MMAs of the previous N block retired
+        int m = t / n_nblk, n = t % n_nblk;
+        if (m != cur_m) {
+          if (x_loads > 0) mbar_wait(empty_b, (x_loads - 1) & 1);   // MMAs of the previous sample block retired
           mbar_expect_tx(full_b, TC_NKB * TILE_KB_BYTES);
           for (int kb = 0; kb < TC_NKB; ++kb)
-            tma_load_2d(sbase + SM_B_OFF + kb * TILE_KB_BYTES, &map_d, kb * TC_KB, n * TC_BN, full_b);
-          ++b_loads;
-          cur_n = n;
+            tma_load_2d(sbase + SM_B_OFF + kb * TILE_KB_BYTES, &map_x, kb * TC_KB, m * TC_BM, full_b);
+          ++x_loads;
+          cur_m = m;
         }
         mbar_wait(empty_a + 8 * stage, phase ^ 1);
         mbar_expect_tx(full_a + 8 * stage, TC_NKB * TILE_KB_BYTES);
         for (int kb = 0; kb < TC_NKB; ++kb)
-          tma_load_2d(sbase + SM_A_OFF + stage * (TC_NKB * TILE_KB_BYTES) + kb * TILE_KB_BYTES, &map_x, kb * TC_KB,
-                      m * TC_BM, full_a + 8 * stage);
+          tma_load_2d(sbase + SM_A_OFF + stage * (TC_NKB * TILE_KB_BYTES) + kb * TILE_KB_BYTES, &map_d, kb * TC_KB,
+                      n * TC_BN, full_a + 8 * stage);
         if (++stage == TC_ASTAGES) {
           stage = 0;
           phase ^= 1;
@@ -110,22 +113,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      int cur_n = -1, b_loads = 0, stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      int cur_m = -1, x_loads = 0, stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int t = t0; t < t1; ++t) {
-        int n = t / n_mblk;
-        if (n != cur_n) {
-          mbar_wait(full_b, b_loads & 1);
-          ++b_loads;
-          cur_n = n;
+        int m = t / n_nblk;
+        if (m != cur_m) {
+          mbar_wait(full_b, x_loads & 1);
+          ++x_loads;
+          cur_m = m;
         }
         mbar_wait(tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
-        mbar_wait(full_a + 8 * stage, phase);             // x16 tile landed
+        mbar_wait(full_a + 8 * stage, phase);             // Dt16 tile landed
         tc_fence_after();
         uint32_t d_tmem = tmem_base + acc * TC_BN;
 #pragma unroll
         for (int kb = 0; kb < TC_NKB; ++kb) {
-          uint32_t a_addr = sbase + SM_A_OFF + stage * (TC_NKB * TILE_KB_BYTES) + kb * TILE_KB_BYTES;
-          uint32_t b_addr = sbase + SM_B_OFF + kb * TILE_KB_BYTES;
+          // MMA "A" (M = samples) is the resident x16 tile, "B" (N = coordinates) the ring stage
+          uint32_t a_addr = sbase + SM_B_OFF + kb * TILE_KB_BYTES;
+          uint32_t b_addr = sbase + SM_A_OFF + stage * (TC_NKB * TILE_KB_BYTES) + kb * TILE_KB_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_KB / 16; ++k) {
             // advance 16 fp16 = 32 B inside the 128 B swizzle atom
@@ -134,10 +138,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             tc_mma_f16(d_tmem, ad, bd, TC_IDESC, (kb | k) != 0);
           }
         }
-        tc_commit(empty_a + 8 * stage);      // smem stage reusable once these MMAs retire
+        tc_commit(empty_a + 8 * stage);      // ring stage reusable once these MMAs retire
         tc_commit(tmem_full + 8 * acc);      // accumulator ready for the epilogue
-        bool last_of_n = (t + 1 == t1) || ((t + 1) / n_mblk != n);
-        if (last_of_n) tc_commit(empty_b);
+        bool last_of_m = (t + 1 == t1) || ((t + 1) / n_nblk != m);
+        if (last_of_m) tc_commit(empty_b);
         if (++stage == TC_ASTAGES) {
           stage = 0;
           phase ^= 1;
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t stage_base = sbase + SM_C_OFF + (warp - 2) * 8192;
     int acc = 0, acc_phase = 0, buf = 0;
     for (int t = t0; t < t1; ++t) {
-      int n = t / n_mblk, m = t % n_mblk;
+      int m = t / n_nblk, n = t % n_nblk;
       mbar_wait(tmem_full + 8 * acc, acc_phase);
       tc_fence_after();
 #pragma unroll 1
