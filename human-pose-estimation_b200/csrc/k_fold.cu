@@ -1,0 +1,268 @@
+// Folded keypoint path: joints and their backward without touching the vertices.
+//
+// joints_k = sum_v JR_vk verts_v with verts_v = sum_j W_vj (A_R_j p_v + A_t_j), p_v = D_v x
+//          = sum_j [ A_R_j (G_kj x) + A_t_j c_kj ],
+//   G_kj = sum_v JR_vk W_vj D_v   (3 x 218, model constant),   c_kj = sum_v JR_vk W_vj,
+//   x = [pose_feature(207) ; beta ; 1]
+// -- exact algebra for src/tf_smpl/batch_smpl.py:110-155 restricted to the keypoint output
+// (SURVEY.md section 0.6 / appendix B).  Per batch this is one GEMM U = x G^T ([B,218]x[218,1368])
+// and a per-body contraction with the 24 transforms; the backward is the mirror image:
+//   dA_j += dj_k (x) [u_kj ; c_kj],   du_kj = A_R_j^T dj_k,   dx = du G   ([B,1368]x[1368,218]).
+// Both GEMMs run on tcgen05 (k_gemm_tc.cu) with fp16 operands split hi/lo along K; du is scaled
+// per body by a power of two (its magnitude follows the loss scale) and unscaled in k_pose_bwd.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "smplb_internal.h"
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------- create time
+// G[(k*24+j)*3+c][xk] and cc[k*24+j] in fp64 accumulation over the vertices keypoint k touches.
+__global__ void __launch_bounds__(224) k_fold_build(int Vp, int pitch, const int *__restrict__ koff,
+                                                    const int *__restrict__ kidx, const float *__restrict__ kval,
+                                                    const float *__restrict__ W, const float *__restrict__ Dext,
+                                                    float *__restrict__ G, float *__restrict__ cc) {
+  int k = blockIdx.x / NJ, j = blockIdx.x % NJ;
+  int xk = threadIdx.x;   // 0..223
+  double a0 = 0, a1 = 0, a2 = 0, ac = 0;
+  for (int e = koff[k]; e < koff[k + 1]; ++e) {
+    int v = kidx[e];
+    double w = (double)kval[e] * (double)W[(size_t)v * NJ + j];
+    const float *d = Dext + (size_t)xk * pitch + v;
+    a0 += w * (double)d[0];
+    a1 += w * (double)d[Vp];
+    a2 += w * (double)d[2 * (size_t)Vp];
+    ac += w;
+  }
+  size_t n = (size_t)(k * NJ + j) * 3;
+  G[(n + 0) * KX + xk] = (float)a0;
+  G[(n + 1) * KX + xk] = (float)a1;
+  G[(n + 2) * KX + xk] = (float)a2;
+  if (xk == 0) cc[k * NJ + j] = (float)ac;
+}
+
+// GEMM operands.  G16 [NUp][704]: G_hi | G_lo | G_hi | 0 (pairs with x_hi | x_hi | x_lo).
+// Gt16 [224][3*NUp]: Gt_hi | Gt_hi | Gt_lo (pairs with du_hi | du_lo | du_hi).  Values are scaled
+// by `scale` (a power of two) first.
+__global__ void k_fold_operands(int nu, int nup, float scale, const float *__restrict__ G, __half *__restrict__ G16,
+                                __half *__restrict__ Gt16) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nup * KX) return;
+  int n = i / KX, xk = i % KX;
+  float g = n < nu ? G[(size_t)n * KX + xk] * scale : 0.f;
+  __half hi = __float2half_rn(g);
+  __half lo = __float2half_rn(g - __half2float(hi));
+  __half *r1 = G16 + (size_t)n * 704;
+  r1[xk] = hi;
+  r1[KX + xk] = lo;
+  r1[2 * KX + xk] = hi;
+  if (xk < 32) r1[3 * KX + xk] = __float2half_rn(0.f);
+  __half *r2 = Gt16 + (size_t)xk * (3 * nup);
+  r2[n] = hi;
+  r2[nup + n] = hi;
+  r2[2 * nup + n] = lo;
+}
+
+// ---------------------------------------------------------------------------------- forward
+// CTA = one body, warp k = keypoint k, lane j = joint j: joints_k = sum_j A_j [u_kj ; c_kj],
+// then projection and the per-body part of the keypoint loss (same tail as k_joints).
+__global__ void k_fold_fwd(int B, int K, int ldu, const float *__restrict__ U, const float *__restrict__ cc,
+                           const float *__restrict__ A, const float *__restrict__ cam, const float *__restrict__ kp_gt,
+                           float *__restrict__ joints, float *__restrict__ kp_pred, float *__restrict__ dkp,
+                           float *__restrict__ part, int *__restrict__ cnt) {
+  __shared__ float s_l[MAXK];
+  __shared__ int s_c[MAXK];
+  int b = blockIdx.x;
+  int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (lane < NJ) {
+    const float *u = U + (size_t)b * ldu + (size_t)(k * NJ + lane) * 3;
+    float u0 = u[0], u1 = u[1], u2 = u[2], c = cc[k * NJ + lane];
+    const float4 *a = reinterpret_cast<const float4 *>(A + ((size_t)b * NJ + lane) * 12);
+    float4 r0 = a[0], r1 = a[1], r2 = a[2];
+    x = fmaf(r0.x, u0, fmaf(r0.y, u1, fmaf(r0.z, u2, r0.w * c)));
+    y = fmaf(r1.x, u0, fmaf(r1.y, u1, fmaf(r1.z, u2, r1.w * c)));
+    z = fmaf(r2.x, u0, fmaf(r2.y, u1, fmaf(r2.z, u2, r2.w * c)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x += __shfl_xor_sync(FULL, x, o);
+    y += __shfl_xor_sync(FULL, y, o);
+    z += __shfl_xor_sync(FULL, z, o);
+  }
+  if (lane == 0) {
+    size_t bk = (size_t)b * K + k;
+    joints[bk * 3 + 0] = x;
+    joints[bk * 3 + 1] = y;
+    joints[bk * 3 + 2] = z;
+    float l = 0.f;
+    int cn = 0;
+    if (cam) {
+      float s = cam[b * 3 + 0], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
+      float px = s * (x + tx), py = s * (y + ty);
+      if (kp_pred) {
+        kp_pred[bk * 2 + 0] = px;
+        kp_pred[bk * 2 + 1] = py;
+      }
+      if (kp_gt) {
+        float gx = kp_gt[bk * 3 + 0], gy = kp_gt[bk * 3 + 1], vis = kp_gt[bk * 3 + 2];
+        float dx = px - gx, dy = py - gy;
+        l = vis * fabsf(dx) + vis * fabsf(dy);
+        cn = (vis != 0.0f) ? 2 : 0;
+        if (dkp) {
+          dkp[bk * 2 + 0] = vis * (float)((dx > 0.f) - (dx < 0.f));
+          dkp[bk * 2 + 1] = vis * (float)((dy > 0.f) - (dy < 0.f));
+        }
+      }
+    }
+    s_l[k] = l;
+    s_c[k] = cn;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && part) {
+    float tl = 0.f;
+    int tc = 0;
+    for (int q = 0; q < K; ++q) {
+      tl += s_l[q];
+      tc += s_c[q];
+    }
+    part[b] = tl;
+    cnt[b] = tc;
+  }
+}
+
+// --------------------------------------------------------------------------------- backward
+// CTA = one body, warp k, lane j.  du_kj = A_R_j^T dj_k -> fp16 hi/lo operand row scaled by
+// 2^-e_b (e_b from the body's max |du|); dA_j = sum_k dj_k (x) [u_kj ; c_kj] summed over the
+// warps in fixed order -> dA_part[0][b] (the other VSPLIT partials are not read: n_parts = 1).
+__global__ void k_fold_bwd(int B, int K, int ldu, int nup, const float *__restrict__ U, const float *__restrict__ cc,
+                           const float *__restrict__ A, const float *__restrict__ d_joints, float *__restrict__ dA,
+                           __half *__restrict__ du16, float *__restrict__ rowscale) {
+  __shared__ float s_dA[MAXK][NJ * 12];
+  __shared__ float s_max[MAXK];
+  int b = blockIdx.x;
+  int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float du0 = 0.f, du1 = 0.f, du2 = 0.f;
+  if (lane < NJ) {
+    const float *dj = d_joints + ((size_t)b * K + k) * 3;
+    float g0 = dj[0], g1 = dj[1], g2 = dj[2];
+    const float *u = U + (size_t)b * ldu + (size_t)(k * NJ + lane) * 3;
+    float u4[4] = {u[0], u[1], u[2], cc[k * NJ + lane]};
+    const float *a = A + ((size_t)b * NJ + lane) * 12;
+    du0 = a[0] * g0 + a[4] * g1 + a[8] * g2;     // A_R^T dj
+    du1 = a[1] * g0 + a[5] * g1 + a[9] * g2;
+    du2 = a[2] * g0 + a[6] * g1 + a[10] * g2;
+    float gg[3] = {g0, g1, g2};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int d = 0; d < 4; ++d) s_dA[k][lane * 12 + 4 * r + d] = gg[r] * u4[d];
+  }
+  float m = fmaxf(fabsf(du0), fmaxf(fabsf(du1), fabsf(du2)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  if (lane == 0) s_max[k] = m;
+  __syncthreads();
+  float mx = 0.f;
+  for (int q = 0; q < K; ++q) mx = fmaxf(mx, s_max[q]);
+  // power-of-two scale that brings max |du| to [1, 2): exact to apply and to undo
+  int e = 0;
+  if (mx > 0.f && isfinite(mx)) frexpf(mx, &e);
+  float inv = ldexpf(1.0f, 1 - e), sc = ldexpf(1.0f, e - 1);
+  if (!(mx > 0.f)) {
+    inv = 1.0f;
+    sc = 1.0f;
+  }
+  if (threadIdx.x == 0) rowscale[b] = sc;
+  if (lane < NJ) {
+    __half *row = du16 + (size_t)b * (3 * nup);
+    int n = (k * NJ + lane) * 3;
+    float d3[3] = {du0 * inv, du1 * inv, du2 * inv};
+#pragma unroll
+    for (int cI = 0; cI < 3; ++cI) {
+      __half hi = __float2half_rn(d3[cI]);
+      __half lo = __float2half_rn(d3[cI] - __half2float(hi));
+      row[n + cI] = hi;
+      row[nup + n + cI] = lo;
+      row[2 * nup + n + cI] = hi;
+    }
+  }
+  for (int i = threadIdx.x; i < NJ * 12; i += blockDim.x) {
+    float s = 0.f;
+    for (int q = 0; q < K; ++q) s += s_dA[q][i];
+    dA[(size_t)b * (NJ * 12) + i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------- host
+int tc_make_map(void *map, int is_f32, void *ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                uint32_t box_inner, uint32_t box_outer);
+int launch_gemm_tc(smplb_ctx *c, const char *name, int M, int N, int K, const void *A16, const void *map_b, float *C,
+                   int ldc, int ksplit, float scale);
+
+__global__ void k_absmax_f(size_t n, const float *__restrict__ x, unsigned int *__restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+int fold_init(smplb_ctx *c) {
+  c->fold_ok = false;
+  if (!c->tc_ok) return 0;
+  int nu = 3 * NJ * c->K;
+  int nup = cdiv(nu, 128) * 128;
+  c->fold_nu = nu;
+  c->fold_nup = nup;
+  CUDA_TRY(cudaMalloc((void **)&c->d_G, (size_t)nu * KX * 4));
+  CUDA_TRY(cudaMalloc((void **)&c->d_cc, (size_t)NJ * c->K * 4));
+  k_fold_build<<<c->K * NJ, 224, 0, c->stream>>>(c->Vp, c->pitch, c->d_kcsr_off, c->d_kcsr_idx, c->d_kcsr_val, c->d_W,
+                                                c->d_Dext, c->d_G, c->d_cc);
+  unsigned int *d_max = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d_max, 4));
+  CUDA_TRY(cudaMemsetAsync(d_max, 0, 4, c->stream));
+  k_absmax_f<<<148, 256, 0, c->stream>>>((size_t)nu * KX, c->d_G, d_max);
+  unsigned int bits = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bits, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  cudaFree(d_max);
+  float mx;
+  memcpy(&mx, &bits, 4);
+  int s = 0;
+  if (mx > 0.f && isfinite(mx)) s = (int)floorf(log2f(1024.0f / mx));
+  s = s < -8 ? -8 : (s > 24 ? 24 : s);
+  c->fold_scale = ldexpf(1.0f, s);
+  c->fold_inv_scale = ldexpf(1.0f, -s);
+  CUDA_TRY(cudaMalloc((void **)&c->d_G16, (size_t)nup * 704 * 2));
+  CUDA_TRY(cudaMalloc((void **)&c->d_Gt16, (size_t)KX * 3 * nup * 2));
+  k_fold_operands<<<cdiv(nup * KX, 256), 256, 0, c->stream>>>(nu, nup, c->fold_scale, c->d_G, (__half *)c->d_G16,
+                                                             (__half *)c->d_Gt16);
+  c->launches += 3;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  TRY(tc_make_map(c->map_g1, 0, c->d_G16, 704, (uint64_t)nup, 704 * 2, 64, 128));
+  TRY(tc_make_map(c->map_g2, 0, c->d_Gt16, (uint64_t)3 * nup, (uint64_t)KX, (uint64_t)3 * nup * 2, 64, 128));
+  c->fold_ok = true;
+  return 0;
+}
+
+// U [B][nup] = x G^T, then joints / projection / kp-loss partials.
+int launch_fold_fwd(smplb_ctx *c, int B, const void *x16b, const float *A, const float *cam, const float *kp_gt,
+                    float *joints, float *kp_pred, float *dkp, float *part, int *cnt) {
+  RET_IF(!c->fold_ok, SMPLB_ESTATE, "folded keypoint path is not initialised");
+  TRY(launch_gemm_tc(c, "fold_gemm_u", B, c->fold_nup, 704, x16b, c->map_g1, c->ws_U, c->fold_nup, 1, c->fold_inv_scale));
+  LAUNCH(c, "fold_joints_proj_kploss", B, 32 * c->K, 0, k_fold_fwd, B, c->K, c->fold_nup, c->ws_U, c->d_cc, A, cam, kp_gt,
+         joints, kp_pred, dkp, part, cnt);
+  return 0;
+}
+
+// dA (one partial) and dx partials [ksplit][rows_per][KX] (+ per-body scale) from d_joints.
+int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, float *dA_part, float *dx_part, int ksplit) {
+  RET_IF(!c->fold_ok, SMPLB_ESTATE, "folded keypoint path is not initialised");
+  LAUNCH(c, "fold_bwd_du_dA", B, 32 * c->K, 0, k_fold_bwd, B, c->K, c->fold_nup, c->fold_nup, c->ws_U, c->d_cc, A, d_joints,
+         dA_part, (__half *)c->ws_du16, c->ws_rowscale);
+  TRY(launch_gemm_tc(c, "fold_gemm_dx", B, KX, 3 * c->fold_nup, c->ws_du16, c->map_g2, dx_part, KX, ksplit,
+                     c->fold_inv_scale));
+  return 0;
+}

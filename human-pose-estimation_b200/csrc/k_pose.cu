@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
                                                   const float *__restrict__ Jdirs, float *__restrict__ Rs,
                                                   float *__restrict__ Jout, float *__restrict__ A,
                                                   float *__restrict__ Jtr, float *__restrict__ x,
-                                                  __half *__restrict__ x16, __half *__restrict__ A16) {
+                                                  __half *__restrict__ x16, __half *__restrict__ A16,
+                                                  __half *__restrict__ x16b) {
   int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -165,6 +166,32 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
       }
       xr[k] = __float2half_rn(v);
     }
+  }
+  if (x16b) {
+    // operand row of the folded keypoint GEMM (k_fold.cu): x = [pose_feature | beta | 1 | 0..]
+    // (224 wide) as x_hi | x_hi | x_lo | 0 (704 halves)
+    __half *xr = x16b + (size_t)b * 704;
+    if (act && j >= 1) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) {
+        float val = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+        __half hi = __float2half_rn(val);
+        int k = (j - 1) * 9 + e;
+        xr[k] = hi;
+        xr[KX + k] = hi;
+        xr[2 * KX + k] = __float2half_rn(val - __half2float(hi));
+      }
+    }
+    for (int k = NPF + lane; k < KX; k += 32) {
+      float val = 0.0f;
+      if (k < NPF + NB) val = beta[(size_t)b * NB + (k - NPF)];
+      else if (k == NPF + NB) val = 1.0f;
+      __half hi = __float2half_rn(val);
+      xr[k] = hi;
+      xr[KX + k] = hi;
+      xr[2 * KX + k] = __float2half_rn(val - __half2float(hi));
+    }
+    xr[3 * KX + lane] = __float2half_rn(0.f);
   }
   if (x) {
     // tail of the operand row: beta, the constant 1 that multiplies v_template, zero padding
@@ -221,7 +248,8 @@ struct PoseBwdSmem {
 __global__ void __launch_bounds__(32 * PB_WARPS)
     k_pose_bwd(int B, int NB, Tree tree, const float *__restrict__ theta, const float *__restrict__ Rs,
                const float *__restrict__ Jin, const float *__restrict__ A, const float *__restrict__ dA_part,
-               const float *__restrict__ dx_part, int ksplit, const float *__restrict__ d_Rs,
+               int n_dA_parts, const float *__restrict__ dx_part, int ksplit, int dx_rows,
+               const float *__restrict__ rowscale, const float *__restrict__ d_Rs,
                const float *__restrict__ Jdirs, float *__restrict__ d_beta, float *__restrict__ d_theta) {
   __shared__ PoseBwdSmem sm[PB_WARPS];
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -233,7 +261,7 @@ __global__ void __launch_bounds__(32 * PB_WARPS)
     float dA[12];
 #pragma unroll
     for (int e = 0; e < 12; ++e) dA[e] = 0.0f;
-    for (int sp = 0; sp < VSPLIT; ++sp) {
+    for (int sp = 0; sp < n_dA_parts; ++sp) {
       const float *src = dA_part + ((size_t)sp * B + b) * (NJ * 12) + j * 12;
 #pragma unroll
       for (int e = 0; e < 12; ++e) dA[e] += src[e];
@@ -301,8 +329,8 @@ __global__ void __launch_bounds__(32 * PB_WARPS)
       float g = S.dR[j][e];
       if (j >= 1) {
         float acc = 0.0f;
-        for (int ks = 0; ks < ksplit; ++ks) acc += dx_part[((size_t)ks * B + b) * KX + (j - 1) * 9 + e];
-        g += acc;
+        for (int ks = 0; ks < ksplit; ++ks) acc += dx_part[((size_t)ks * dx_rows + b) * KX + (j - 1) * 9 + e];
+        g += rowscale ? acc * rowscale[b] : acc;
       }
       if (d_Rs) g += d_Rs[((size_t)b * NJ + j) * 9 + e];
       G[e] = g;
@@ -317,7 +345,8 @@ __global__ void __launch_bounds__(32 * PB_WARPS)
   if (lane < NB) {
     // d beta = Jdirs^T dJ + (dp . shapedirs^T), the latter from the blend backward GEMM
     float acc = 0.0f;
-    for (int ks = 0; ks < ksplit; ++ks) acc += dx_part[((size_t)ks * B + b) * KX + NPF + lane];
+    for (int ks = 0; ks < ksplit; ++ks) acc += dx_part[((size_t)ks * dx_rows + b) * KX + NPF + lane];
+    if (rowscale) acc *= rowscale[b];
     for (int jc = 0; jc < NJ * 3; ++jc) acc = fmaf(Jdirs[(size_t)jc * NB + lane], S.dJ[jc / 3][jc % 3], acc);
     d_beta[(size_t)b * NB + lane] = acc;
   }
@@ -399,17 +428,17 @@ int launch_lrotmin(smplb_ctx *c, int B, const float *theta, float *out) {
 }
 
 int launch_pose_fwd(smplb_ctx *c, int B, const float *beta, const float *theta, float *Rs, float *J, float *A,
-                    float *Jtr, float *x, void *x16, void *A16) {
+                    float *Jtr, float *x, void *x16, void *A16, void *x16b) {
   LAUNCH(c, "pose_fwd", cdiv(B, 4), 128, 0, k_pose_fwd, B, c->NB, c->tree, beta, theta, c->d_J0, c->d_Jdirs, Rs, J, A,
-         Jtr, x, (__half *)x16, (__half *)A16);
+         Jtr, x, (__half *)x16, (__half *)A16, (__half *)x16b);
   return 0;
 }
 
 int launch_pose_bwd(smplb_ctx *c, int B, const float *theta, const float *Rs, const float *J, const float *A,
-                    const float *dA_part, const float *dx_part, int ksplit, const float *d_Rs, float *d_beta,
-                    float *d_theta) {
+                    const float *dA_part, int n_dA_parts, const float *dx_part, int ksplit, int dx_rows,
+                    const float *rowscale, const float *d_Rs, float *d_beta, float *d_theta) {
   LAUNCH(c, "pose_bwd", cdiv(B, PB_WARPS), 32 * PB_WARPS, 0, k_pose_bwd, B, c->NB, c->tree, theta, Rs, J, A, dA_part,
-         dx_part, ksplit, d_Rs, c->d_Jdirs, d_beta, d_theta);
+         n_dA_parts, dx_part, ksplit, dx_rows, rowscale, d_Rs, c->d_Jdirs, d_beta, d_theta);
   return 0;
 }
 

@@ -176,7 +176,8 @@ static void free_ws(smplb_ctx *c) {
                    (void **)&c->ws_vposed, (void **)&c->ws_verts, (void **)&c->ws_joints, (void **)&c->ws_kp,
                    (void **)&c->ws_dkp, (void **)&c->ws_djoints, (void **)&c->ws_dverts, (void **)&c->ws_dp, (void **)&c->ws_dA,
                    (void **)&c->ws_dx, (void **)&c->ws_part, (void **)&c->ws_cnt, (void **)&c->ws_theta,
-                   (void **)&c->ws_beta, (void **)&c->ws_gp, (void **)&c->ws_x16, (void **)&c->ws_dp_act, (void **)&c->ws_A16, (void **)&c->ws_vposed_act, (void **)&c->ws_verts_act};
+                   (void **)&c->ws_beta, (void **)&c->ws_gp, (void **)&c->ws_x16, (void **)&c->ws_dp_act, (void **)&c->ws_A16, (void **)&c->ws_vposed_act, (void **)&c->ws_verts_act, (void **)&c->ws_U, (void **)&c->ws_du16,
+                   (void **)&c->ws_rowscale, (void **)&c->ws_x16b};
   for (void **p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -201,6 +202,13 @@ static int ensure_ws(smplb_ctx *c, int B) {
   size_t nb = (size_t)n;
   WS_ALLOC(ws_x, nb * KX);
   WS_ALLOC(ws_x16, nb * 128);   // 256 halves per row
+  if (c->fold_nup) {
+    WS_ALLOC(ws_U, nb * c->fold_nup);
+    WS_ALLOC(ws_du16, nb * 3 * c->fold_nup / 2);
+    CUDA_TRY(cudaMemsetAsync(c->ws_du16, 0, nb * 3 * c->fold_nup * 2, c->stream));
+    WS_ALLOC(ws_rowscale, nb);
+    WS_ALLOC(ws_x16b, nb * 352);
+  }
   WS_ALLOC(ws_A16, nb * 12 * 64);   // 12 rows x 128 halves per sample; columns 72..127 stay zero
   CUDA_TRY(cudaMemsetAsync(c->ws_A16, 0, nb * 12 * 64 * 4, c->stream));
   WS_ALLOC(ws_Rs, nb * NJ * 9);
@@ -213,7 +221,7 @@ static int ensure_ws(smplb_ctx *c, int B) {
   WS_ALLOC(ws_dkp, nb * c->K * 2);
   WS_ALLOC(ws_djoints, nb * c->K * 3);
   WS_ALLOC(ws_dA, (size_t)VSPLIT * nb * NJ * 12);
-  WS_ALLOC(ws_dx, (size_t)c->ksplit * nb * KX);
+  WS_ALLOC(ws_dx, std::max((size_t)c->ksplit * nb, (size_t)2 * (nb + 128)) * KX);
   WS_ALLOC(ws_part, nb);
   WS_ALLOC(ws_cnt, nb);
   WS_ALLOC(ws_theta, nb * 72);
@@ -385,10 +393,11 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
     return fail(SMPLB_ECUDA);
   cudaMemset(c->ws_scal, 0, 64 * 4);
   cudaMemset(c->ws_cnt64, 0, 8 * sizeof(long long));
-  if ((rc = ensure_ws(c, c->max_batch))) return fail(rc);
   if ((rc = blend_tc_init(c))) return fail(rc);
   if ((rc = skin_tc_init(c))) return fail(rc);
   if ((rc = compact_tc_init(c))) return fail(rc);
+  if ((rc = fold_init(c))) return fail(rc);
+  if ((rc = ensure_ws(c, c->max_batch))) return fail(rc);
   *out = c;
   return 0;
 }
@@ -401,7 +410,7 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
   free_ws(c);
   void *ptrs[] = {c->d_vt,       c->d_shapedirs, c->d_posedirs, c->d_W,        c->d_JR,       c->d_Dext,   c->d_J0,
                   c->d_Jdirs,    c->d_kcsr_off,  c->d_kcsr_idx, c->d_kcsr_val, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val,
-                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_W16,      c->d_Dt16_act, c->d_W16_act,  c->d_kcsr_slot, c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
+                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_W16,      c->d_G,        c->d_cc,       c->d_G16,      c->d_Gt16,     c->d_Dt16_act, c->d_W16_act,  c->d_kcsr_slot, c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
                   c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -506,6 +515,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->use_tc = value;
     return 0;
   }
+  if (!strcmp(key, "fold")) {
+    c->use_fold = value;
+    return 0;
+  }
   if (!strcmp(key, "l2_chunk")) {
     c->l2_chunk = value;
     return 0;
@@ -561,13 +574,15 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   CUDA_TRY(cudaMemcpyAsync(c->ws_theta, theta, (size_t)B * 72 * 4, cudaMemcpyDeviceToDevice, c->stream));
   bool tc = c->tc_ok && c->use_tc;
   bool stc = c->skin_tc_ok && c->use_skin_tc;
+  bool fold = tc && c->fold_ok && c->use_fold;
   TRY(launch_pose_fwd(c, B, c->ws_beta, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, Jtr ? Jtr : c->ws_Jtr,
-                      tc ? nullptr : c->ws_x, tc ? c->ws_x16 : nullptr, stc ? c->ws_A16 : nullptr));
+                      tc ? nullptr : c->ws_x, tc ? c->ws_x16 : nullptr, stc ? c->ws_A16 : nullptr,
+                      fold ? c->ws_x16b : nullptr));
   if (Rs) CUDA_TRY(cudaMemcpyAsync(Rs, c->ws_Rs, (size_t)B * NJ * 9 * 4, cudaMemcpyDeviceToDevice, c->stream));
   // Keypoint path on the active vertices only (rows of joint_regressor with a non-zero): the
   // same two tensor-core kernels on ~9 % of the vertices give joints without reading verts back.
-  bool compact = tc && stc && c->compact_ok && c->use_compact;
-  bool full = need_verts || !compact;
+  bool compact = !fold && tc && stc && c->compact_ok && c->use_compact;
+  bool full = need_verts || !(compact || fold);
   float *vout = verts;
   if (full && !vout) {
     TRY(ensure_buf(c, &c->ws_verts, (size_t)c->ws_batch * c->V3, false));
@@ -595,7 +610,12 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   c->saved_full = full && !chunked;
   c->saved_verts = vout;
   float *jout = joints ? joints : c->ws_joints;
-  if (compact) {
+  c->saved_fold = fold;
+  if (fold) {
+    // joints from x and A alone (k_fold.cu): one small GEMM + a per-body contraction
+    TRY(launch_fold_fwd(c, B, c->ws_x16b, c->ws_A, cam, kp_gt, jout, kp_pred, kp_gt ? c->ws_dkp : nullptr,
+                        kp_gt ? c->ws_part : nullptr, kp_gt ? c->ws_cnt : nullptr));
+  } else if (compact) {
     TRY(ensure_buf(c, &c->ws_vposed_act, (size_t)c->ws_batch * c->pitch_act, false));
     TRY(ensure_buf(c, &c->ws_verts_act, (size_t)c->ws_batch * c->n_act * 3, false));
     TRY(launch_blend_fwd_tc(c, B, c->ws_x16, c->ws_vposed_act, true));
@@ -615,6 +635,14 @@ static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const fl
                              float *d_beta, float *d_theta) {
   RET_IF(c->saved_B != B, SMPLB_ESTATE, "smplb_smpl_backward(B=%d) without a matching forward (saved B=%d)", B,
          c->saved_B);
+  if (d_verts == nullptr && d_joints != nullptr && c->saved_fold) {
+    // gradient arrives through the keypoints only: folded backward, no per-vertex work
+    int rows = cdiv(B, 128) * 128;
+    TRY(launch_fold_bwd(c, B, c->ws_A, d_joints, c->ws_dA, c->ws_dx, 2));
+    TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, 1, c->ws_dx, 2, rows, c->ws_rowscale, d_Rs,
+                        d_beta, d_theta));
+    return 0;
+  }
   // No upstream gradient on verts: only vertices the keypoint regressor touches carry a
   // gradient, so walk just those (exact: the skipped terms are zeros).
   bool compact = (d_verts == nullptr) && c->use_compact && c->n_act < c->V;
@@ -638,7 +666,8 @@ static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const fl
     TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed, d_verts, d_joints, dp, c->ws_dA, compact ? 1 : 0));
   int ks = compact ? 4 : c->ksplit;   // the compact contraction is 11x shorter: fewer split-K partials
   TRY(launch_blend_bwd(c, B, dp, c->ws_dx, compact, ks));
-  TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, c->ws_dx, ks, d_Rs, d_beta, d_theta));
+  TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, VSPLIT, c->ws_dx, ks, B, nullptr, d_Rs, d_beta,
+                      d_theta));
   return 0;
 }
 

@@ -69,6 +69,20 @@ struct smplb_ctx {
   bool saved_full = false;         // ws_vposed holds the last forward's full v_posed
   bool saved_compact = false;      // ws_vposed_act holds the last forward's compact v_posed
   float *saved_verts = nullptr;    // where the last forward wrote verts (caller's buffer or ws_verts)
+  // ---- folded keypoint path (k_fold.cu): joints and their backward from x and A alone
+  bool fold_ok = false;
+  int use_fold = 1;                // smplb_debug_set("fold", 0) falls back to the per-vertex keypoint path
+  int fold_nu = 0, fold_nup = 0;   // 3 * 24 * K and its round-up to 128
+  float *d_G = nullptr, *d_cc = nullptr;
+  void *d_G16 = nullptr, *d_Gt16 = nullptr;
+  alignas(64) unsigned char map_g1[128];
+  alignas(64) unsigned char map_g2[128];
+  float fold_scale = 1.f, fold_inv_scale = 1.f;
+  float *ws_U = nullptr;           // [B][fold_nup]
+  void *ws_du16 = nullptr;         // [B][3 * fold_nup] fp16
+  float *ws_rowscale = nullptr;    // [B]
+  void *ws_x16b = nullptr;         // [B][704] fp16: x_hi | x_hi | x_lo | 0
+  bool saved_fold = false;
   // ---- tcgen05 blend path (k_blend_tc.cu)
   bool tc_ok = false;          // operands built, tensor map encoded
   int use_tc = 1;              // smplb_debug_set("blend_tc", 0) selects the FP32 CUDA-core GEMM (validation)
@@ -183,10 +197,10 @@ __device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; 
 // ---- kernel launchers (device pointers only), one per stage -------------------------------
 // k_pose.cu
 int launch_pose_fwd(smplb_ctx *c, int B, const float *beta, const float *theta, float *Rs, float *J, float *A,
-                    float *Jtr, float *x, void *x16, void *A16);
+                    float *Jtr, float *x, void *x16, void *A16, void *x16b);
 int launch_pose_bwd(smplb_ctx *c, int B, const float *theta, const float *Rs, const float *J, const float *A,
-                    const float *dA_part, const float *dx_part, int ksplit, const float *d_Rs, float *d_beta,
-                    float *d_theta);
+                    const float *dA_part, int n_dA_parts, const float *dx_part, int ksplit, int dx_rows,
+                    const float *rowscale, const float *d_Rs, float *d_beta, float *d_theta);
 int launch_rodrigues(smplb_ctx *c, int N, const float *theta, float *R);
 int launch_global_rigid(smplb_ctx *c, int B, const float *Rs, const float *Js, float *new_J, float *A44);
 int launch_skew(smplb_ctx *c, int N, const float *vec, float *out);
@@ -197,6 +211,11 @@ int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part, bool 
 // k_blend_tc.cu
 int blend_tc_init(smplb_ctx *c);
 int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed, bool act);
+// k_fold.cu
+int fold_init(smplb_ctx *c);
+int launch_fold_fwd(smplb_ctx *c, int B, const void *x16b, const float *A, const float *cam, const float *kp_gt,
+                    float *joints, float *kp_pred, float *dkp, float *part, int *cnt);
+int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, float *dA_part, float *dx_part, int ksplit);
 // k_skin_tc.cu
 int skin_tc_init(smplb_ctx *c);
 int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts, bool act);

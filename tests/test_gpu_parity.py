@@ -367,3 +367,39 @@ def test_tcgen05_skinning_matches_fp32_kernel(smpl_full):
     v1, j1, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
     assert np.isfinite(v1).all()
     assert rel_err(v1, v0) < 5e-6 and rel_err(j1, j0) < 5e-6
+
+
+def test_folded_keypoint_path_matches_per_vertex_path(smpl_full):
+    """joints / kp loss / gradients from the folded formulation (G x, no vertices) against the
+    per-vertex keypoint path; both are checked against the oracle elsewhere, this pins them to
+    each other at a tighter level."""
+    inp = synthetic.make_inputs(150, seed=2718)
+    ctx = smpl_full.ctx
+    a = smpl_full.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"])
+    a = {k: np.array(v) for k, v in a.items()}
+    try:
+        ctx.debug_set("fold", 0)
+        b = smpl_full.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"])
+    finally:
+        ctx.debug_set("fold", 1)
+    assert np.array_equal(a["verts"], b["verts"])                    # the verts path is untouched
+    for k, tol in (("joints", 3e-6), ("kp_pred", 3e-6), ("d_beta", 2e-5), ("d_theta", 2e-5), ("d_cam", 2e-5)):
+        assert rel_err(a[k], b[k]) < tol, k
+    assert a["loss_parts"][1] == b["loss_parts"][1]
+    assert abs(a["loss_parts"][3] - b["loss_parts"][3]) < 1e-5 * abs(b["loss_parts"][3])
+    # joints-only forward (get_skin=False) never touches the 6890-vertex tensors
+    j = smpl_full(inp["beta"], inp["theta"])
+    assert rel_err(j, a["joints"]) < 1e-6
+    # backward with upstream on joints and Rs only goes through the folded path
+    rng = np.random.default_rng(3)
+    dj = rng.normal(size=(150, 19, 3)).astype(np.float32)
+    dR = rng.normal(size=(150, 24, 3, 3)).astype(np.float32)
+    smpl_full(inp["beta"], inp["theta"], get_skin=True)
+    db1, dt1 = smpl_full.backward(d_joints=dj, d_Rs=dR)
+    try:
+        ctx.debug_set("fold", 0)
+        smpl_full(inp["beta"], inp["theta"], get_skin=True)
+        db0, dt0 = smpl_full.backward(d_joints=dj, d_Rs=dR)
+    finally:
+        ctx.debug_set("fold", 1)
+    assert rel_err(db1, db0) < 2e-5 and rel_err(dt1, dt0) < 2e-5
