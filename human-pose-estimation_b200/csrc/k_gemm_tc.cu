@@ -200,7 +200,9 @@ int launch_gemm_tc(smplb_ctx *c, const char *name, int M, int N, int K, const vo
   int rows_per = n_mblk * G_BM;
   alignas(64) CUtensorMap map_a, map_c;
   TRY(tc_make_map(&map_a, 0, (void *)A16, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, G_KB, G_BM));
-  TRY(tc_make_map(&map_c, 1, (void *)C, (uint64_t)ldc, (uint64_t)ksplit * rows_per, (uint64_t)ldc * 4, 32, 32));
+  // one split: clip the stores at the real M; several: the caller's buffer holds rows_per rows per split
+  uint64_t c_rows = ksplit == 1 ? (uint64_t)M : (uint64_t)ksplit * rows_per;
+  TRY(tc_make_map(&map_c, 1, (void *)C, (uint64_t)ldc, c_rows, (uint64_t)ldc * 4, 32, 32));
   int total = n_mblk * n_nblk * ksplit;
   int grid = total < c->num_sms ? total : c->num_sms;
   LAUNCH(c, name, grid, G_THREADS, G_SM_TOTAL, k_gemm_tc, map_a, *(const CUtensorMap *)map_b, map_c, n_mblk, n_nblk, n_kblk,
