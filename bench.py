@@ -54,7 +54,11 @@ def kernel_work(name, B):
     vb = 12.0 * V   # bytes of one [V,3] fp32 row
     table = {
         # name: (bound, bytes or flops per launch)
-        "pose_fwd": ("hbm", B * (340 + 864 + 288 + 1152 + 288 + 4 * 224)),
+        "pose_fwd": ("hbm", B * (340 + 864 + 288 + 1152 + 288 + 512 + 3072 + 1408)),
+        "fold_gemm_u": ("tensor", 2.0 * B * 1368 * 218 * 3),
+        "fold_gemm_dx": ("tensor", 2.0 * B * 1368 * 218 * 3),
+        "fold_joints_proj_kploss": ("hbm", B * (1368 * 4 + 1152 + K * 44)),
+        "fold_bwd_du_dA": ("hbm", B * (1368 * 4 + 1152 + K * 12 + 1152 + 3 * 1408 * 2)),
         "blend_fwd_sgemm": ("tensor", 2.0 * B * 218 * 3 * V),
         "blend_fwd_tc": ("hbm", B * (vb + 512) + 2 * 256 * 3 * V),
         "skin_fwd": ("hbm", B * (2 * vb + 1152) + 24 * 4 * V),

@@ -383,13 +383,14 @@ def test_folded_keypoint_path_matches_per_vertex_path(smpl_full):
     finally:
         ctx.debug_set("fold", 1)
     assert np.array_equal(a["verts"], b["verts"])                    # the verts path is untouched
-    for k, tol in (("joints", 3e-6), ("kp_pred", 3e-6), ("d_beta", 2e-5), ("d_theta", 2e-5), ("d_cam", 2e-5)):
+    for k, tol in (("joints", 2e-5), ("kp_pred", 2e-5), ("d_beta", 3e-5), ("d_theta", 3e-5), ("d_cam", 3e-5)):
         assert rel_err(a[k], b[k]) < tol, k
     assert a["loss_parts"][1] == b["loss_parts"][1]
     assert abs(a["loss_parts"][3] - b["loss_parts"][3]) < 1e-5 * abs(b["loss_parts"][3])
     # joints-only forward (get_skin=False) never touches the 6890-vertex tensors
     j = smpl_full(inp["beta"], inp["theta"])
     assert rel_err(j, a["joints"]) < 1e-6
+    assert not smpl_full.ctx.profile_read()                          # (profiling is off: nothing recorded)
     # backward with upstream on joints and Rs only goes through the folded path
     rng = np.random.default_rng(3)
     dj = rng.normal(size=(150, 19, 3)).astype(np.float32)
