@@ -35,11 +35,11 @@ ProfScope::ProfScope(smplb_ctx *ctx, const char *name) : c(ctx) {
       cudaEventCreate(e);
     }
   }
-  cudaEventRecord(r.e0, c->stream);
+  cudaEventRecord(r.e0, c->cur);
 }
 ProfScope::~ProfScope() {
   if (!r.e0) return;
-  cudaEventRecord(r.e1, c->stream);
+  cudaEventRecord(r.e1, c->cur);
   c->prof.push_back(r);
 }
 
@@ -106,6 +106,7 @@ struct Stager {
   do {                                                                  \
     RET_IF(!(c), SMPLB_EINVAL, "null context");                         \
     CUDA_TRY(cudaSetDevice((c)->device));                               \
+    (c)->cur = (c)->stream;                                             \
   } while (0)
 #define CHECK_MEM(mem) RET_IF((mem) != SMPLB_HOST && (mem) != SMPLB_DEVICE, SMPLB_EINVAL, "mem must be SMPLB_HOST or SMPLB_DEVICE")
 
@@ -287,7 +288,12 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
     smplb_destroy(c);
     return code;
   };
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(SMPLB_ECUDA);
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess)
+    return fail(SMPLB_ECUDA);
+  c->cur = c->stream;
   {
     // host-mode calls stage through stream-ordered allocations: keep the pool's memory across
     // synchronisations instead of returning it to the driver after every call
@@ -423,6 +429,12 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
     cudaEventDestroy(r.e1);
   }
   for (auto e : c->event_pool) cudaEventDestroy(e);
+  if (c->stream2) {
+    cudaStreamSynchronize(c->stream2);
+    cudaStreamDestroy(c->stream2);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -515,6 +527,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->use_tc = value;
     return 0;
   }
+  if (!strcmp(key, "overlap")) {
+    c->use_overlap = value;
+    return 0;
+  }
   if (!strcmp(key, "fold")) {
     c->use_fold = value;
     return 0;
@@ -537,6 +553,7 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
 extern "C" int smplb_profile_enable(smplb_ctx *c, int on) {
   RET_IF(!c, SMPLB_EINVAL, "null context");
   c->profile = on != 0;
+  c->profile_serial = on != 0;   // per-kernel events are only meaningful without stream overlap
   return 0;
 }
 extern "C" int smplb_profile_read(smplb_ctx *c, char *buf, size_t buflen) {
@@ -566,6 +583,16 @@ extern "C" int smplb_profile_read(smplb_ctx *c, char *buf, size_t buflen) {
 }
 
 // --------------------------------------------------------------------------------- SMPL fwd/bwd
+// The 6890-vertex blend + skinning run on stream2 while the keypoint path continues on the
+// main stream; whoever needs verts / v_posed on the main stream joins first.
+static int join_verts(smplb_ctx *c) {
+  if (c->verts_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    c->verts_pending = false;
+  }
+  return 0;
+}
+
 static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float *theta, float *verts, float *joints,
                             float *Rs, float *Jtr, const float *cam, const float *kp_gt, float *kp_pred,
                             bool need_verts) {
@@ -594,6 +621,12 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   // trip.  The dense backward rebuilds v_posed when it needs it (saved_full = false).
   int chunk = c->l2_chunk;
   bool chunked = full && tc && stc && chunk > 0 && B > chunk;
+  bool overlap = full && (fold || compact) && c->use_overlap && !c->profile_serial;
+  if (overlap) {
+    CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    c->cur = c->stream2;
+  }
   if (full && chunked) {
     for (int b0 = 0; b0 < B; b0 += chunk) {
       int nb = std::min(chunk, B - b0);
@@ -608,6 +641,15 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
     else TRY(launch_skin_fwd(c, B, c->ws_A, c->ws_vposed, vout));
   }
   c->saved_full = full && !chunked;
+  if (overlap) {
+    cudaError_t e1 = cudaEventRecord(c->ev_join, c->stream2);
+    c->cur = c->stream;
+    c->verts_pending = true;
+    if (e1 != cudaSuccess) {
+      smplb_set_error("cudaEventRecord(ev_join) failed: %s", cudaGetErrorString(e1));
+      return SMPLB_ECUDA;
+    }
+  }
   c->saved_verts = vout;
   float *jout = joints ? joints : c->ws_joints;
   c->saved_fold = fold;
@@ -635,6 +677,7 @@ static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const fl
                              float *d_beta, float *d_theta) {
   RET_IF(c->saved_B != B, SMPLB_ESTATE, "smplb_smpl_backward(B=%d) without a matching forward (saved B=%d)", B,
          c->saved_B);
+  if (d_verts != nullptr || !c->saved_fold) TRY(join_verts(c));   // the per-vertex backward reads v_posed
   if (d_verts == nullptr && d_joints != nullptr && c->saved_fold) {
     // gradient arrives through the keypoints only: folded backward, no per-vertex work
     int rows = cdiv(B, 128) * 128;
@@ -682,6 +725,7 @@ extern "C" int smplb_smpl_forward(smplb_ctx *c, int B, const float *beta, const 
   float *dRs = st.out(Rs, (size_t)B * NJ * 9), *dJtr = st.out(J_transformed, (size_t)B * NJ * 3);
   RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
   TRY(smpl_forward_dev(c, B, dbeta, dtheta, dverts, djoints, dRs, dJtr, nullptr, nullptr, nullptr, verts != nullptr));
+  TRY(join_verts(c));
   return st.finish();
 }
 
@@ -937,6 +981,7 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
   const float *vbuf = c->saved_verts;
   TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, c->ws_scal + 0, c->ws_cnt64, c->ws_scal + 1));
   if (have_mesh) {
+    TRY(join_verts(c));
     TRY(launch_proj(c, B, c->V, vbuf, dcam, 1, img_size, img_size, c->ws_silpred));
     TRY(launch_mesh_loss(c, B, c->V, dpts, doff, P, c->ws_silpred, c->ws_scal + 2, bwd ? c->ws_dsil : nullptr,
                          c->ws_silcnt, c->ws_mesh_part, nullptr, nullptr));
@@ -958,6 +1003,7 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
     }
     TRY(smpl_backward_dev(c, B, dverts, c->ws_djoints, nullptr, odb, odt));
   }
+  TRY(join_verts(c));
   return st.finish();
 }
 

@@ -27,7 +27,12 @@ struct ProfRec {
 
 struct smplb_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;    // main stream: everything the caller orders against
+  cudaStream_t stream2 = nullptr;   // side stream: the 6890-vertex blend + skinning, overlapped with the keypoint path
+  cudaStream_t cur = nullptr;       // stream the LAUNCH macro uses
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool verts_pending = false;       // stream2 work not yet joined into the main stream
+  int use_overlap = 1;              // smplb_debug_set("overlap", 0) keeps everything on the main stream
   int V = 0, NB = 0, K = 0, max_batch = 0;
   int V3 = 0;       // 3V
   int Vp = 0;       // V rounded up to 128
@@ -135,6 +140,7 @@ struct smplb_ctx {
   cudaEvent_t timer0[16] = {}, timer1[16] = {};
   int64_t launches = 0;
   bool profile = false;
+  bool profile_serial = false;
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
   // NCCL (dlopen'ed)
@@ -179,7 +185,7 @@ struct ProfScope {
   do {                                                                                      \
     {                                                                                       \
       ProfScope _ps((ctx), (name));                                                         \
-      kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                      \
+      kernel<<<(grid), (block), (smem), (ctx)->cur>>>(__VA_ARGS__);                         \
     }                                                                                       \
     (ctx)->launches++;                                                                      \
     cudaError_t _le = cudaGetLastError();                                                   \
