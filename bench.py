@@ -258,7 +258,6 @@ def main():
     sampler.start()
     time.sleep(0.15)
     launches0 = ctx.launch_count()
-    ctx.profile(True)
     barrier()
     ctx.timer_start(0)
     for i in range(args.steps):
@@ -266,9 +265,15 @@ def main():
     ctx.timer_stop(0)
     ms_total = ctx.timer_ms(0)
     barrier()
+    launches = ctx.launch_count() - launches0
+    # per-kernel launch durations: the same K steps again with CUDA events around every launch
+    # (the library then keeps all kernels on one stream so each duration is clean)
+    ctx.profile(True)
+    for i in range(args.steps):
+        gpu_step(i)
     prof = ctx.profile_read()
     ctx.profile(False)
-    launches = ctx.launch_count() - launches0
+    barrier()
     clocks = sampler.finish()
     loss_parts = out["loss_parts"].numpy()
 
@@ -285,7 +290,7 @@ def main():
 
     def e2e_step(i):
         p = pin[i % NSET]
-        return smpl.step(p["beta"], p["theta"], p["cam"], p["kp_gt"], w_kp=60.0, want_verts=False, out=eout,
+        return smpl.step(p["beta"], p["theta"], p["cam"], p["kp_gt"], w_kp=60.0, want_verts="device", out=eout,
                          skip=("Rs",))
 
     for i in range(3):
@@ -343,7 +348,11 @@ def main():
                        "global_batch": world * B, "parallelism": "batch-sharded x%d" % world,
                        "l2": "per-step working set (verts + v_posed + dp, ~1.0 GB) exceeds the 126 MB L2; inputs rotate "
                              "over %d buffer sets" % NSET,
-                       "timing": "CUDA events on the context stream; per-kernel events enabled in the timed region"},
+                       "timing": "value: CUDA events around the K steps on the context stream (6890-vertex path overlapped on a "
+                                 "second stream inside the library); roofline / kernels_ms_per_step: the same K steps repeated "
+                                 "with events around every launch, single stream",
+                       "e2e": "host-buffer smpl.step: pinned H2D of beta/theta/cam/kp_gt, D2H of loss, gradients, joints, "
+                              "keypoints; verts are computed and stay in device memory"},
             "roofline": roof,
             "step_algorithmic_gbs": e2e_algo, "step_algorithmic_frac_of_hbm": e2e_algo / peaks["hbm"],
             "kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},

@@ -48,6 +48,7 @@ SIGNATURES = {
     "smplb_debug_set": [_P, C.c_char_p, _I],
     "smplb_smpl_forward": [_P, _I, _P, _P, _P, _P, _P, _P, _I],
     "smplb_smpl_backward": [_P, _I, _P, _P, _P, _P, _P, _I],
+    "smplb_last_verts": [_P, C.POINTER(_P)],
     "smplb_rodrigues": [_P, _I, _P, _P, _I],
     "smplb_global_rigid": [_P, _I, _P, _P, _P, _P, _I],
     "smplb_skew": [_P, _I, _P, _P, _I],

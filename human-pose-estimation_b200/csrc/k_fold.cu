@@ -195,6 +195,177 @@ __global__ void k_fold_bwd(int B, int K, int ldu, int nup, const float *__restri
   }
 }
 
+// ------------------------------------------------------------------ warp-per-body variants
+// One warp per body, 8 bodies per CTA: far fewer, fuller CTAs than the CTA-per-body kernels
+// above (which remain as the readable reference of the same arithmetic).
+#define FW_WARPS 8
+
+// Forward: lane k owns keypoint k and loops over the 24 joints (A staged in shared memory).
+__global__ void __launch_bounds__(32 * FW_WARPS)
+    k_fold_fwd_w(int B, int K, int ldu, const float *__restrict__ U, const float *__restrict__ cc,
+                 const float *__restrict__ A, const float *__restrict__ cam, const float *__restrict__ kp_gt,
+                 float *__restrict__ joints, float *__restrict__ kp_pred, float *__restrict__ dkp,
+                 float *__restrict__ part, int *__restrict__ cnt) {
+  __shared__ __align__(16) float sA[FW_WARPS][NJ * 12];
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int b = blockIdx.x * FW_WARPS + w;
+  if (b >= B) return;
+  for (int i = lane; i < NJ * 12; i += 32) sA[w][i] = A[(size_t)b * NJ * 12 + i];
+  __syncwarp();
+  float x = 0.f, y = 0.f, z = 0.f, l = 0.f;
+  int cn = 0;
+  if (lane < K) {
+    const float *u = U + (size_t)b * ldu + (size_t)lane * NJ * 3;
+    const float *c = cc + lane * NJ;
+#pragma unroll 4
+    for (int j = 0; j < NJ; ++j) {
+      float u0 = u[3 * j], u1 = u[3 * j + 1], u2 = u[3 * j + 2], cj = c[j];
+      const float4 *a = reinterpret_cast<const float4 *>(sA[w] + j * 12);
+      float4 r0 = a[0], r1 = a[1], r2 = a[2];
+      x += fmaf(r0.x, u0, fmaf(r0.y, u1, fmaf(r0.z, u2, r0.w * cj)));
+      y += fmaf(r1.x, u0, fmaf(r1.y, u1, fmaf(r1.z, u2, r1.w * cj)));
+      z += fmaf(r2.x, u0, fmaf(r2.y, u1, fmaf(r2.z, u2, r2.w * cj)));
+    }
+    size_t bk = (size_t)b * K + lane;
+    joints[bk * 3 + 0] = x;
+    joints[bk * 3 + 1] = y;
+    joints[bk * 3 + 2] = z;
+    if (cam) {
+      float s = cam[b * 3 + 0], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
+      float px = s * (x + tx), py = s * (y + ty);
+      if (kp_pred) {
+        kp_pred[bk * 2 + 0] = px;
+        kp_pred[bk * 2 + 1] = py;
+      }
+      if (kp_gt) {
+        float gx = kp_gt[bk * 3 + 0], gy = kp_gt[bk * 3 + 1], vis = kp_gt[bk * 3 + 2];
+        float dx = px - gx, dy = py - gy;
+        l = vis * fabsf(dx) + vis * fabsf(dy);
+        cn = (vis != 0.0f) ? 2 : 0;
+        if (dkp) {
+          dkp[bk * 2 + 0] = vis * (float)((dx > 0.f) - (dx < 0.f));
+          dkp[bk * 2 + 1] = vis * (float)((dy > 0.f) - (dy < 0.f));
+        }
+      }
+    }
+  }
+  if (part) {
+    // fixed-order sum over the keypoints (lane 0 adds k = 0, 1, ... in turn)
+    float tl = 0.f;
+    int tc = 0;
+    for (int q = 0; q < K; ++q) {
+      tl += __shfl_sync(FULL, l, q);
+      tc += __shfl_sync(FULL, cn, q);
+    }
+    if (lane == 0) {
+      part[b] = tl;
+      cnt[b] = tc;
+    }
+  }
+}
+
+// Backward: (phase A, lane k) dj_k either given or formed from the unscaled keypoint-loss
+// gradient, the camera and gscale / *den -- then d_cam falls out too; (phase B, lane j)
+// du_kj = A_R_j^T dj_k, dA_j = sum_k dj_k (x) [u_kj ; c_kj] with no cross-lane reduction.
+__global__ void __launch_bounds__(32 * FW_WARPS)
+    k_fold_bwd_w(int B, int K, int ldu, int nup, const float *__restrict__ U, const float *__restrict__ cc,
+                 const float *__restrict__ A, const float *__restrict__ d_joints, const float *__restrict__ dkp,
+                 const float *__restrict__ joints, const float *__restrict__ cam, float gscale,
+                 const long long *__restrict__ den, float *__restrict__ d_cam, float *__restrict__ dA,
+                 __half *__restrict__ du16, float *__restrict__ rowscale) {
+  __shared__ float sdj[FW_WARPS][MAXK * 3];
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int b = blockIdx.x * FW_WARPS + w;
+  if (b >= B) return;
+  if (dkp) {
+    float sc = gscale;
+    if (den) {
+      long long dv = *den;
+      sc = dv > 0 ? gscale / (float)dv : 0.0f;
+    }
+    float s = cam[b * 3 + 0], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
+    float gx = 0.f, gy = 0.f, as = 0.f;
+    if (lane < K) {
+      size_t bk = (size_t)b * K + lane;
+      gx = dkp[bk * 2 + 0] * sc;
+      gy = dkp[bk * 2 + 1] * sc;
+      as = gx * (joints[bk * 3 + 0] + tx) + gy * (joints[bk * 3 + 1] + ty);
+      sdj[w][lane * 3 + 0] = s * gx;
+      sdj[w][lane * 3 + 1] = s * gy;
+      sdj[w][lane * 3 + 2] = 0.0f;
+    }
+    if (d_cam) {
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      for (int q = 0; q < K; ++q) {   // fixed order
+        c0 += __shfl_sync(FULL, as, q);
+        c1 += __shfl_sync(FULL, gx, q);
+        c2 += __shfl_sync(FULL, gy, q);
+      }
+      if (lane == 0) {
+        d_cam[b * 3 + 0] = c0;
+        d_cam[b * 3 + 1] = s * c1;
+        d_cam[b * 3 + 2] = s * c2;
+      }
+    }
+  } else {
+    for (int i = lane; i < K * 3; i += 32) sdj[w][i] = d_joints[(size_t)b * K * 3 + i];
+  }
+  __syncwarp();
+  int j = lane < NJ ? lane : NJ - 1;
+  const float *a = A + ((size_t)b * NJ + j) * 12;
+  float ar[9] = {a[0], a[1], a[2], a[4], a[5], a[6], a[8], a[9], a[10]};
+  const float *u = U + (size_t)b * ldu + (size_t)j * 3;
+  float acc[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) acc[e] = 0.f;
+  float m = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float g0 = sdj[w][3 * k], g1 = sdj[w][3 * k + 1], g2 = sdj[w][3 * k + 2];
+    float du0 = ar[0] * g0 + ar[3] * g1 + ar[6] * g2;
+    float du1 = ar[1] * g0 + ar[4] * g1 + ar[7] * g2;
+    float du2 = ar[2] * g0 + ar[5] * g1 + ar[8] * g2;
+    m = fmaxf(m, fmaxf(fabsf(du0), fmaxf(fabsf(du1), fabsf(du2))));
+    const float *uk = u + (size_t)k * NJ * 3;
+    float u4[4] = {uk[0], uk[1], uk[2], cc[k * NJ + j]};
+    float gg[3] = {g0, g1, g2};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int d = 0; d < 4; ++d) acc[4 * r + d] = fmaf(gg[r], u4[d], acc[4 * r + d]);
+  }
+  if (lane >= NJ) m = 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  int e = 0;
+  float inv = 1.0f, sc2 = 1.0f;
+  if (m > 0.f && isfinite(m)) {
+    frexpf(m, &e);
+    inv = ldexpf(1.0f, 1 - e);
+    sc2 = ldexpf(1.0f, e - 1);
+  }
+  if (lane == 0) rowscale[b] = sc2;
+  if (lane < NJ) {
+    float *o = dA + ((size_t)b * NJ + j) * 12;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) o[q] = acc[q];
+    __half *row = du16 + (size_t)b * (3 * nup);
+    for (int k = 0; k < K; ++k) {
+      float g0 = sdj[w][3 * k], g1 = sdj[w][3 * k + 1], g2 = sdj[w][3 * k + 2];
+      float d3[3] = {(ar[0] * g0 + ar[3] * g1 + ar[6] * g2) * inv, (ar[1] * g0 + ar[4] * g1 + ar[7] * g2) * inv,
+                     (ar[2] * g0 + ar[5] * g1 + ar[8] * g2) * inv};
+      int n = (k * NJ + j) * 3;
+#pragma unroll
+      for (int cI = 0; cI < 3; ++cI) {
+        __half hi = __float2half_rn(d3[cI]);
+        __half lo = __float2half_rn(d3[cI] - __half2float(hi));
+        row[n + cI] = hi;
+        row[nup + n + cI] = lo;
+        row[2 * nup + n + cI] = hi;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------- host
 int tc_make_map(void *map, int is_f32, void *ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                 uint32_t box_inner, uint32_t box_outer);
@@ -252,16 +423,31 @@ int launch_fold_fwd(smplb_ctx *c, int B, const void *x16b, const float *A, const
                     float *joints, float *kp_pred, float *dkp, float *part, int *cnt) {
   RET_IF(!c->fold_ok, SMPLB_ESTATE, "folded keypoint path is not initialised");
   TRY(launch_gemm_tc(c, "fold_gemm_u", B, c->fold_nup, 704, x16b, c->map_g1, c->ws_U, c->fold_nup, 1, c->fold_inv_scale));
-  LAUNCH(c, "fold_joints_proj_kploss", B, 32 * c->K, 0, k_fold_fwd, B, c->K, c->fold_nup, c->ws_U, c->d_cc, A, cam, kp_gt,
-         joints, kp_pred, dkp, part, cnt);
+  if (c->fold_warp_kernels) {
+    LAUNCH(c, "fold_joints_proj_kploss", cdiv(B, FW_WARPS), 32 * FW_WARPS, 0, k_fold_fwd_w, B, c->K, c->fold_nup, c->ws_U,
+           c->d_cc, A, cam, kp_gt, joints, kp_pred, dkp, part, cnt);
+  } else {
+    LAUNCH(c, "fold_joints_proj_kploss_cta", B, 32 * c->K, 0, k_fold_fwd, B, c->K, c->fold_nup, c->ws_U, c->d_cc, A, cam,
+           kp_gt, joints, kp_pred, dkp, part, cnt);
+  }
   return 0;
 }
 
 // dA (one partial) and dx partials [ksplit][rows_per][KX] (+ per-body scale) from d_joints.
-int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, float *dA_part, float *dx_part, int ksplit) {
+// Either d_joints is given, or (dkp, joints, cam, gscale, den) from which the kernel forms
+// d_joints = s * dkp * gscale / *den itself and also writes d_cam.
+int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, const float *dkp, const float *joints,
+                    const float *cam, float gscale, const long long *den, float *d_cam, float *dA_part, float *dx_part,
+                    int ksplit) {
   RET_IF(!c->fold_ok, SMPLB_ESTATE, "folded keypoint path is not initialised");
-  LAUNCH(c, "fold_bwd_du_dA", B, 32 * c->K, 0, k_fold_bwd, B, c->K, c->fold_nup, c->fold_nup, c->ws_U, c->d_cc, A, d_joints,
-         dA_part, (__half *)c->ws_du16, c->ws_rowscale);
+  if (c->fold_warp_kernels) {
+    LAUNCH(c, "fold_bwd_du_dA", cdiv(B, FW_WARPS), 32 * FW_WARPS, 0, k_fold_bwd_w, B, c->K, c->fold_nup, c->fold_nup, c->ws_U,
+           c->d_cc, A, d_joints, dkp, joints, cam, gscale, den, d_cam, dA_part, (__half *)c->ws_du16, c->ws_rowscale);
+  } else {
+    RET_IF(!d_joints, SMPLB_EINVAL, "the CTA-per-body fold backward needs d_joints");
+    LAUNCH(c, "fold_bwd_du_dA_cta", B, 32 * c->K, 0, k_fold_bwd, B, c->K, c->fold_nup, c->fold_nup, c->ws_U, c->d_cc, A,
+           d_joints, dA_part, (__half *)c->ws_du16, c->ws_rowscale);
+  }
   TRY(launch_gemm_tc(c, "fold_gemm_dx", B, KX, 3 * c->fold_nup, c->ws_du16, c->map_g2, dx_part, KX, ksplit,
                      c->fold_inv_scale));
   return 0;

@@ -75,6 +75,44 @@ __global__ void __launch_bounds__(1024) k_reduce_kp(int B, const float *__restri
   }
 }
 
+// Single-GPU, keypoint-loss-only steps: reduce and finalize in one launch (no all-reduce or
+// mesh term has to come in between).
+__global__ void __launch_bounds__(1024) k_reduce_finalize(int B, const float *__restrict__ part,
+                                                          const int *__restrict__ cnt, float w_kp, long long count_override,
+                                                          float *__restrict__ scal, long long *__restrict__ kp_cnt,
+                                                          float *__restrict__ out) {
+  __shared__ float red[1024];
+  __shared__ long long redc[1024];
+  int t = threadIdx.x;
+  float s = 0.f;
+  long long c = 0;
+  for (int i = t; i < B; i += 1024) {
+    s += part[i];
+    c += cnt[i];
+  }
+  red[t] = s;
+  redc[t] = c;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) {
+      red[t] += red[t + o];
+      redc[t] += redc[t + o];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    long long den = count_override > 0 ? count_override : redc[0];
+    float kp = den > 0 ? red[0] / (float)den : 0.0f;
+    scal[0] = red[0];
+    scal[1] = (float)redc[0];
+    out[0] = red[0];
+    out[1] = (float)redc[0];
+    out[2] = 0.0f;
+    out[3] = w_kp * kp;
+    *kp_cnt = den;
+  }
+}
+
 // scal = {kp abs_sum, kp num_present as float, mesh sum} -- already all-reduced over the ranks
 // when a communicator is attached.  loss_parts = {abs_sum, num_present, mesh sum,
 // w_kp * abs_sum / num_present + w_mesh * mesh}; kp_cnt receives the count the backward
@@ -335,6 +373,13 @@ int launch_reduce_kp(smplb_ctx *c, int B, const float *part, const int *cnt, flo
 int launch_finalize_loss(smplb_ctx *c, float w_kp, float w_mesh, long long count_override, int have_mesh,
                          float *loss_parts) {
   LAUNCH(c, "finalize_loss", 1, 1, 0, k_finalize_loss, w_kp, w_mesh, count_override, have_mesh, c->ws_scal,
+         c->ws_cnt64, loss_parts);
+  return 0;
+}
+
+int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long long count_override, float *loss_parts) {
+  (void)w_mesh;
+  LAUNCH(c, "reduce_finalize_kp", 1, 1024, 0, k_reduce_finalize, B, c->ws_part, c->ws_cnt, w_kp, count_override, c->ws_scal,
          c->ws_cnt64, loss_parts);
   return 0;
 }

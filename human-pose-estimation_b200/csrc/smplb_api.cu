@@ -527,6 +527,14 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->use_tc = value;
     return 0;
   }
+  if (!strcmp(key, "keep_verts")) {
+    c->keep_verts = value;
+    return 0;
+  }
+  if (!strcmp(key, "fold_warp")) {
+    c->fold_warp_kernels = value;
+    return 0;
+  }
   if (!strcmp(key, "overlap")) {
     c->use_overlap = value;
     return 0;
@@ -609,7 +617,7 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   // Keypoint path on the active vertices only (rows of joint_regressor with a non-zero): the
   // same two tensor-core kernels on ~9 % of the vertices give joints without reading verts back.
   bool compact = !fold && tc && stc && c->compact_ok && c->use_compact;
-  bool full = need_verts || !(compact || fold);
+  bool full = need_verts || c->keep_verts || !(compact || fold);
   float *vout = verts;
   if (full && !vout) {
     TRY(ensure_buf(c, &c->ws_verts, (size_t)c->ws_batch * c->V3, false));
@@ -681,7 +689,7 @@ static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const fl
   if (d_verts == nullptr && d_joints != nullptr && c->saved_fold) {
     // gradient arrives through the keypoints only: folded backward, no per-vertex work
     int rows = cdiv(B, 128) * 128;
-    TRY(launch_fold_bwd(c, B, c->ws_A, d_joints, c->ws_dA, c->ws_dx, 2));
+    TRY(launch_fold_bwd(c, B, c->ws_A, d_joints, nullptr, nullptr, nullptr, 1.0f, nullptr, nullptr, c->ws_dA, c->ws_dx, 2));
     TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, 1, c->ws_dx, 2, rows, c->ws_rowscale, d_Rs,
                         d_beta, d_theta));
     return 0;
@@ -741,6 +749,12 @@ extern "C" int smplb_smpl_backward(smplb_ctx *c, int B, const float *d_verts, co
   RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
   TRY(smpl_backward_dev(c, B, dv, dj, dr, db, dt));
   return st.finish();
+}
+
+extern "C" int smplb_last_verts(smplb_ctx *c, const float **dptr) {
+  RET_IF(!c || !dptr, SMPLB_EINVAL, "null argument");
+  *dptr = c->saved_full || c->saved_verts ? c->saved_verts : nullptr;
+  return 0;
 }
 
 extern "C" int smplb_rodrigues(smplb_ctx *c, int N, const float *theta, float *R, int mem) {
@@ -979,29 +993,44 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
   TRY(smpl_forward_dev(c, B, dbeta, dtheta, overts, jbuf, oRs, nullptr, dcam, dkpgt, okp ? okp : c->ws_kp,
                        overts != nullptr || have_mesh));
   const float *vbuf = c->saved_verts;
-  TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, c->ws_scal + 0, c->ws_cnt64, c->ws_scal + 1));
-  if (have_mesh) {
-    TRY(join_verts(c));
-    TRY(launch_proj(c, B, c->V, vbuf, dcam, 1, img_size, img_size, c->ws_silpred));
-    TRY(launch_mesh_loss(c, B, c->V, dpts, doff, P, c->ws_silpred, c->ws_scal + 2, bwd ? c->ws_dsil : nullptr,
-                         c->ws_silcnt, c->ws_mesh_part, nullptr, nullptr));
-  }
-  if (c->nccl_comm && c->nranks > 1) {
-    // the path's one exchange: {kp numerator, kp count, mesh sum} summed over the batch shards
-    if (!have_mesh) CUDA_TRY(cudaMemsetAsync(c->ws_scal + 2, 0, 4, c->stream));
-    TRY(smplb_comm_allreduce_sum(c, c->ws_scal, 3));
-  }
-  TRY(launch_finalize_loss(c, w_kp, w_mesh, (long long)kp_count_override, have_mesh ? 1 : 0, oloss));
-  if (bwd) {
-    // d kp loss -> d joints, d cam; scale w_kp / num_present (global count if overridden)
-    TRY(launch_proj_bwd(c, B, K, jbuf, dcam, c->ws_dkp, 0, 0.f, 0.f, w_kp, c->ws_cnt64, 0, c->ws_djoints, odc));
-    const float *dverts = nullptr;
+  bool comm = c->nccl_comm && c->nranks > 1;
+  if (!have_mesh && !comm) {
+    TRY(launch_reduce_finalize(c, B, w_kp, w_mesh, (long long)kp_count_override, oloss));
+  } else {
+    TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, c->ws_scal + 0, c->ws_cnt64, c->ws_scal + 1));
     if (have_mesh) {
-      TRY(ensure_buf(c, &c->ws_dverts, (size_t)c->ws_batch * c->V3, false));
-      TRY(launch_proj_bwd(c, B, c->V, vbuf, dcam, c->ws_dsil, 1, img_size, img_size, w_mesh, nullptr, 1, c->ws_dverts, odc));
-      dverts = c->ws_dverts;
+      TRY(join_verts(c));
+      TRY(launch_proj(c, B, c->V, vbuf, dcam, 1, img_size, img_size, c->ws_silpred));
+      TRY(launch_mesh_loss(c, B, c->V, dpts, doff, P, c->ws_silpred, c->ws_scal + 2, bwd ? c->ws_dsil : nullptr,
+                           c->ws_silcnt, c->ws_mesh_part, nullptr, nullptr));
     }
-    TRY(smpl_backward_dev(c, B, dverts, c->ws_djoints, nullptr, odb, odt));
+    if (comm) {
+      // the path's one exchange: {kp numerator, kp count, mesh sum} summed over the batch shards
+      if (!have_mesh) CUDA_TRY(cudaMemsetAsync(c->ws_scal + 2, 0, 4, c->stream));
+      TRY(smplb_comm_allreduce_sum(c, c->ws_scal, 3));
+    }
+    TRY(launch_finalize_loss(c, w_kp, w_mesh, (long long)kp_count_override, have_mesh ? 1 : 0, oloss));
+  }
+  if (bwd) {
+    if (!have_mesh && c->saved_fold && c->fold_warp_kernels) {
+      // keypoint-only backward: d kp loss -> d joints, d cam, du, dA in one kernel, then the GEMM
+      RET_IF(c->saved_B != B, SMPLB_ESTATE, "internal: forward state lost");
+      int rows = cdiv(B, 128) * 128;
+      TRY(launch_fold_bwd(c, B, c->ws_A, nullptr, c->ws_dkp, jbuf, dcam, w_kp, c->ws_cnt64, odc, c->ws_dA, c->ws_dx, 2));
+      TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, 1, c->ws_dx, 2, rows, c->ws_rowscale,
+                          nullptr, odb, odt));
+    } else {
+      // d kp loss -> d joints, d cam; scale w_kp / num_present (global count if overridden)
+      TRY(launch_proj_bwd(c, B, K, jbuf, dcam, c->ws_dkp, 0, 0.f, 0.f, w_kp, c->ws_cnt64, 0, c->ws_djoints, odc));
+      const float *dverts = nullptr;
+      if (have_mesh) {
+        TRY(ensure_buf(c, &c->ws_dverts, (size_t)c->ws_batch * c->V3, false));
+        TRY(launch_proj_bwd(c, B, c->V, vbuf, dcam, c->ws_dsil, 1, img_size, img_size, w_mesh, nullptr, 1, c->ws_dverts,
+                            odc));
+        dverts = c->ws_dverts;
+      }
+      TRY(smpl_backward_dev(c, B, dverts, c->ws_djoints, nullptr, odb, odt));
+    }
   }
   TRY(join_verts(c));
   return st.finish();

@@ -32,6 +32,7 @@ struct smplb_ctx {
   cudaStream_t cur = nullptr;       // stream the LAUNCH macro uses
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool verts_pending = false;       // stream2 work not yet joined into the main stream
+  int keep_verts = 0;               // smplb_debug_set("keep_verts", 1): always compute verts (device-resident workspace)
   int use_overlap = 1;              // smplb_debug_set("overlap", 0) keeps everything on the main stream
   int V = 0, NB = 0, K = 0, max_batch = 0;
   int V3 = 0;       // 3V
@@ -88,6 +89,7 @@ struct smplb_ctx {
   float *ws_rowscale = nullptr;    // [B]
   void *ws_x16b = nullptr;         // [B][704] fp16: x_hi | x_hi | x_lo | 0
   bool saved_fold = false;
+  int fold_warp_kernels = 1;       // smplb_debug_set("fold_warp", 0): CTA-per-body reference kernels
   // ---- tcgen05 blend path (k_blend_tc.cu)
   bool tc_ok = false;          // operands built, tensor map encoded
   int use_tc = 1;              // smplb_debug_set("blend_tc", 0) selects the FP32 CUDA-core GEMM (validation)
@@ -221,7 +223,10 @@ int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed, bo
 int fold_init(smplb_ctx *c);
 int launch_fold_fwd(smplb_ctx *c, int B, const void *x16b, const float *A, const float *cam, const float *kp_gt,
                     float *joints, float *kp_pred, float *dkp, float *part, int *cnt);
-int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, float *dA_part, float *dx_part, int ksplit);
+int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, const float *dkp, const float *joints,
+                    const float *cam, float gscale, const long long *den, float *d_cam, float *dA_part, float *dx_part,
+                    int ksplit);
+int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long long count_override, float *loss_parts);
 // k_skin_tc.cu
 int skin_tc_init(smplb_ctx *c);
 int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts, bool act);

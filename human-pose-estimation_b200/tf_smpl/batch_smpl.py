@@ -116,7 +116,9 @@ class SMPL(object):
         projection and loss, optional mesh-reprojection loss, and gradients
         w.r.t. beta/theta/cam.  `silhouette` = (points_xy [P,2], offsets [B+1])
         from ops.silhouette_csr.  Returns a dict.  `out` may hold preallocated
-        outputs of the right kind to avoid allocations in a timed loop; names in
+        outputs of the right kind to avoid allocations in a timed loop;
+        want_verts="device" (host-buffer calls) computes verts but leaves them in
+        device memory (out["verts_device_ptr"]) instead of copying 339 MB back; names in
         `skip` (of "joints", "Rs", "kp_pred") are not returned (host mode: not
         copied back)."""
         a = runtime.Args(self.ctx)
@@ -144,7 +146,7 @@ class SMPL(object):
             out[name] = x
             return x, p
 
-        _, pv = o("verts", (N, V, 3), want_verts or silhouette is not None)
+        _, pv = o("verts", (N, V, 3), want_verts is True)
         _, pj = o("joints", (N, K, 3))
         _, pR = o("Rs", (N, 24, 3, 3))
         _, pkp = o("kp_pred", (N, K, 2))
@@ -152,6 +154,21 @@ class SMPL(object):
         _, pdb = o("d_beta", (N, self.num_betas), backward)
         _, pdt = o("d_theta", (N, 72), backward)
         _, pdc = o("d_cam", (N, 3), backward)
-        check(lib().smplb_step(self.ctx.handle, N, pb, pt, pc, pk, pp, po, P, float(w_kp), float(w_mesh),
-                               float(img_size), int(kp_count_override), pv, pj, pR, pkp, pl, pdb, pdt, pdc, a.mem))
+        if want_verts == "device":
+            self.ctx.debug_set("keep_verts", 1)
+        try:
+            check(lib().smplb_step(self.ctx.handle, N, pb, pt, pc, pk, pp, po, P, float(w_kp), float(w_mesh),
+                                   float(img_size), int(kp_count_override), pv, pj, pR, pkp, pl, pdb, pdt, pdc, a.mem))
+        finally:
+            if want_verts == "device":
+                self.ctx.debug_set("keep_verts", 0)
+        if want_verts == "device":
+            out["verts_device_ptr"] = self.last_verts_ptr()
         return out
+
+    def last_verts_ptr(self):
+        """Device address of the verts of the last call (workspace or caller buffer), or None."""
+        import ctypes as C
+        p = C.c_void_p()
+        check(lib().smplb_last_verts(self.ctx.handle, C.byref(p)))
+        return p.value

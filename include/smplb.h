@@ -98,7 +98,8 @@ int smplb_launch_count(smplb_ctx *ctx, int64_t *count);
 int smplb_profile_enable(smplb_ctx *ctx, int on);
 int smplb_profile_read(smplb_ctx *ctx, char *buf, size_t buflen); /* "name ms count\n" lines; resets */
 /* Test hook: key "blend_tc" = 0 routes the blend contraction through the FP32 CUDA-core GEMM
- * that cross-checks the tcgen05 kernel (default 1). */
+ * that cross-checks the tcgen05 kernel (default 1); "skin_tc", "fold", "compact_bwd",
+ * "overlap" likewise select cross-check paths; "keep_verts" see smplb_last_verts. */
 int smplb_debug_set(smplb_ctx *ctx, const char *key, int value);
 
 /* ---- SMPL.__call__(beta, theta, get_skin) (batch_smpl.py:88-160) ------------------ *
@@ -114,6 +115,14 @@ int smplb_smpl_forward(smplb_ctx *ctx, int B, const float *beta, const float *th
  * Outputs d_beta [B,10], d_theta [B,72].                                             */
 int smplb_smpl_backward(smplb_ctx *ctx, int B, const float *d_verts, const float *d_joints,
                         const float *d_Rs, float *d_beta, float *d_theta, int mem);
+
+/* Device pointer to the verts [B,V,3] of the last forward / step (the caller's buffer in
+ * device mode, else a workspace of the context that stays valid until the next call); NULL if
+ * the last call did not compute verts.  With smplb_debug_set(ctx, "keep_verts", 1) host-mode
+ * calls that pass verts == NULL still compute them and keep them on the device -- what a
+ * trainer wants: the 339 MB stay in HBM for the renderer / mesh loss, only the small
+ * results cross PCIe.                                                                 */
+int smplb_last_verts(smplb_ctx *ctx, const float **dptr);
 
 /* ---- src/tf_smpl/batch_lbs.py stand-alone entry points ---------------------------- */
 /* batch_rodrigues(theta) (batch_lbs.py:42-64): theta [N,3] -> R [N,3,3].            */
