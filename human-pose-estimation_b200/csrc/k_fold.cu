@@ -418,11 +418,17 @@ int fold_init(smplb_ctx *c) {
   return 0;
 }
 
-// U [B][nup] = x G^T, then joints / projection / kp-loss partials.
+// U [B][nup] = x G^T.
+int launch_fold_gemm_u(smplb_ctx *c, int B, const void *x16b) {
+  RET_IF(!c->fold_ok, SMPLB_ESTATE, "folded keypoint path is not initialised");
+  return launch_gemm_tc(c, "fold_gemm_u", B, c->fold_nup, 704, x16b, c->map_g1, c->ws_U, c->fold_nup, 1, c->fold_inv_scale);
+}
+
+// joints / projection / kp-loss partials from U and A.
 int launch_fold_fwd(smplb_ctx *c, int B, const void *x16b, const float *A, const float *cam, const float *kp_gt,
                     float *joints, float *kp_pred, float *dkp, float *part, int *cnt) {
   RET_IF(!c->fold_ok, SMPLB_ESTATE, "folded keypoint path is not initialised");
-  TRY(launch_gemm_tc(c, "fold_gemm_u", B, c->fold_nup, 704, x16b, c->map_g1, c->ws_U, c->fold_nup, 1, c->fold_inv_scale));
+  (void)x16b;   // U was produced by launch_fold_gemm_u
   if (c->fold_warp_kernels) {
     LAUNCH(c, "fold_joints_proj_kploss", cdiv(B, FW_WARPS), 32 * FW_WARPS, 0, k_fold_fwd_w, B, c->K, c->fold_nup, c->ws_U,
            c->d_cc, A, cam, kp_gt, joints, kp_pred, dkp, part, cnt);

@@ -16,7 +16,7 @@
 //
 // Persistent, warp-specialised: warp 0 TMA producer of the MMA operands (W16 tile per vertex
 // tile, A16 chunk per tile), warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue, warp 10 TMA
-// producer of the v_posed tiles (a 4-deep ring, so ~100 KB of loads are in flight per SM: the
+// producer of the v_posed tiles (a 3-deep ring, so ~70 KB of loads are in flight per SM: the
 // epilogue never waits on an HBM round trip); two TMEM accumulator stages.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -29,7 +29,7 @@
 #define ST_N (12 * ST_S)          // MMA N = 192
 #define ST_KP 128                 // padded K in shared memory (two 64-wide swizzle atoms)
 #define ST_ASTAGES 2
-#define ST_PSTAGES 4
+#define ST_PSTAGES 3
 #define ST_THREADS 352
 #define ST_W_BYTES (2 * ST_VT * 128)      // 32 KB: two k-blocks of 128 rows x 128 B
 #define ST_A_KB_BYTES (ST_N * 128)        // 24 KB: one k-block of the A16 chunk

@@ -629,6 +629,9 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   // trip.  The dense backward rebuilds v_posed when it needs it (saved_full = false).
   int chunk = c->l2_chunk;
   bool chunked = full && tc && stc && chunk > 0 && B > chunk;
+  // the fold GEMM needs TMEM and ~160 KB of shared memory, which the persistent blend / skinning
+  // CTAs would deny it: issue it before forking so only the light per-body kernels overlap them
+  if (fold) TRY(launch_fold_gemm_u(c, B, c->ws_x16b));
   bool overlap = full && (fold || compact) && c->use_overlap && !c->profile_serial;
   if (overlap) {
     CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));

@@ -221,6 +221,7 @@ int blend_tc_init(smplb_ctx *c);
 int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed, bool act);
 // k_fold.cu
 int fold_init(smplb_ctx *c);
+int launch_fold_gemm_u(smplb_ctx *c, int B, const void *x16b);
 int launch_fold_fwd(smplb_ctx *c, int B, const void *x16b, const float *A, const float *cam, const float *kp_gt,
                     float *joints, float *kp_pred, float *dkp, float *part, int *cnt);
 int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, const float *dkp, const float *joints,
