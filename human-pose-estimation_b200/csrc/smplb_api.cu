@@ -444,13 +444,13 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
 extern "C" int smplb_malloc(smplb_ctx *c, void **dptr, size_t bytes) {
   CHECK_CTX(c);
   RET_IF(!dptr, SMPLB_EINVAL, "null dptr");
-  CUDA_TRY(cudaMalloc(dptr, bytes ? bytes : 1));
+  // stream-ordered pool allocation: no device synchronisation, memory is reused across calls
+  CUDA_TRY(cudaMallocAsync(dptr, bytes ? bytes : 1, c->stream));
   return 0;
 }
 extern "C" int smplb_free(smplb_ctx *c, void *dptr) {
   CHECK_CTX(c);
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
-  CUDA_TRY(cudaFree(dptr));
+  if (dptr) CUDA_TRY(cudaFreeAsync(dptr, c->stream));   // ordered after every use on the context's stream
   return 0;
 }
 extern "C" int smplb_host_alloc(void **hptr, size_t bytes) {
