@@ -332,6 +332,9 @@ def main():
                 ach = amount / avg_s / 1e12
                 roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                         "frac": ach / peaks["tf_sust"], "traffic": None}
+            tpath = os.path.join(ROOT, "profiles", "r01", "ncu_traffic.json")
+            if os.path.isfile(tpath) and B == BATCH:
+                roof["traffic"] = json.load(open(tpath)).get(name)
             roof["kernel"] = name
             roof["avg_launch_us"] = avg_s * 1e6
             roof["peak_source"] = peaks["src"]
