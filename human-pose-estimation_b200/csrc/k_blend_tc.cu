@@ -16,7 +16,7 @@
 // Kernel shape: persistent, one CTA per SM, warp-specialised:
 //   warp 0   TMA producer (x16 tile per sample block, Dt16 tiles through a 2-deep ring)
 //   warp 1   tcgen05.mma issuer (one lane), TMEM allocator
-//   warps 2-5  epilogue: tcgen05.ld -> scale -> swizzled smem staging -> TMA store
+//   warps 2-9  epilogue: tcgen05.ld -> scale -> swizzled smem staging -> TMA store
 // Tile 128 (samples) x 128 (vertex coordinates); two TMEM accumulator stages so the MMAs of
 // tile i+1 overlap the epilogue of tile i.  The kernel is bound by its fp32 output stream.
 #include <cuda.h>
@@ -31,7 +31,7 @@
 #define TC_KB 64           // K elements per 128-byte swizzle atom
 #define TC_NKB (TC_KP / TC_KB)
 #define TC_ASTAGES 2
-#define TC_THREADS 192
+#define TC_THREADS 320
 
 #define SM_B_OFF 0
 #define SM_A_OFF (64 * 1024)
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(full_a + 8 * i, 1);
       mbar_init(empty_a + 8 * i, 1);
       mbar_init(tmem_full + 8 * i, 1);
-      mbar_init(tmem_empty + 8 * i, 4);   // one arrival per epilogue warp
+      mbar_init(tmem_empty + 8 * i, 8);   // one arrival per epilogue warp
     }
     mbar_init(full_b, 1);
     mbar_init(empty_b, 1);
@@ -153,29 +153,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else {
-    // =========================== epilogue (warps 2..5) ===========================
+    // =========================== epilogue (warps 2..9) ===========================
+    // Two warps per TMEM lane quarter, each taking two of the tile's four 32-column chunks, so
+    // TMEM loads, shared-memory staging and TMA stores of different chunks overlap.
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const uint32_t stage_base = sbase + SM_C_OFF + (warp - 2) * 8192;
-    int acc = 0, acc_phase = 0, buf = 0;
+    const int half = (warp - 2) >> 2;             // column chunks {2*half, 2*half+1}
+    const uint32_t stage_base = sbase + SM_C_OFF + (warp - 2) * 4096;
+    int acc = 0, acc_phase = 0;
     for (int t = t0; t < t1; ++t) {
       int m = t / n_nblk, n = t % n_nblk;
       mbar_wait(tmem_full + 8 * acc, acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int cch = 0; cch < TC_BN / 32; ++cch) {
-        uint32_t r[32];
-        tc_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * TC_BN + cch * 32, r);
-        tc_wait_ld();
-        if (cch == TC_BN / 32 - 1) {
-          // all of this accumulator has been read into registers: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
-        }
-        // the staging buffer we are about to overwrite was read by the TMA store issued 2 chunks ago
-        if (lane == 0) tma_wait_read<1>();
+      uint32_t r0[32], r1[32];
+      const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + acc * TC_BN + (2 * half) * 32;
+      tc_ld_32x32(tbase, r0);
+      tc_ld_32x32(tbase + 32, r1);
+      tc_wait_ld();
+      // both chunks are in registers: hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const uint32_t *r = cc == 0 ? r0 : r1;
+        // the staging buffer was read by this warp's previous TMA store
+        if (lane == 0) tma_wait_read<0>();
         __syncwarp();
-        uint32_t row_addr = stage_base + buf * 4096 + lane * 128;
+        uint32_t row_addr = stage_base + lane * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 v;
@@ -190,10 +194,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&map_c, stage_base + buf * 4096, n * TC_BN + cch * 32, m * TC_BM + 32 * q);
+          tma_store_2d(&map_c, stage_base, n * TC_BN + (2 * half + cc) * 32, m * TC_BM + 32 * q);
           tma_commit();
         }
-        buf ^= 1;
       }
       if (++acc == 2) {
         acc = 0;

@@ -56,7 +56,8 @@ struct Stager {
   std::vector<void *> temps;
   std::vector<Out> outs;
   bool failed = false;
-  Stager(smplb_ctx *ctx, int m) : c(ctx), mem(m) {}
+  bool async = false;
+  Stager(smplb_ctx *ctx, int m) : c(ctx), mem(m == SMPLB_HOST_ASYNC ? SMPLB_HOST : m), async(m == SMPLB_HOST_ASYNC) {}
   void *alloc(size_t bytes) {
     void *d = nullptr;
     if (cudaMallocAsync(&d, bytes ? bytes : 4, c->stream) != cudaSuccess) {
@@ -89,7 +90,7 @@ struct Stager {
         if (cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) failed = true;
       for (void *t : temps) cudaFreeAsync(t, c->stream);
       temps.clear();
-      cudaError_t e = cudaStreamSynchronize(c->stream);
+      cudaError_t e = async ? cudaSuccess : cudaStreamSynchronize(c->stream);
       if (e != cudaSuccess || failed) {
         smplb_set_error("host-mode staging failed: %s", cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
         rc = SMPLB_ECUDA;
@@ -108,7 +109,9 @@ struct Stager {
     CUDA_TRY(cudaSetDevice((c)->device));                               \
     (c)->cur = (c)->stream;                                             \
   } while (0)
-#define CHECK_MEM(mem) RET_IF((mem) != SMPLB_HOST && (mem) != SMPLB_DEVICE, SMPLB_EINVAL, "mem must be SMPLB_HOST or SMPLB_DEVICE")
+#define CHECK_MEM(mem)                                                                                   \
+  RET_IF((mem) != SMPLB_HOST && (mem) != SMPLB_DEVICE && (mem) != SMPLB_HOST_ASYNC, SMPLB_EINVAL,         \
+         "mem must be SMPLB_HOST, SMPLB_DEVICE or SMPLB_HOST_ASYNC")
 
 // ------------------------------------------------------------------------------- create-time
 // J0 = J_regressor^T v_template and Jdirs = J_regressor^T shapedirs in fp64 (one-off constant

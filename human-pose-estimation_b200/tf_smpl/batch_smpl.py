@@ -111,7 +111,7 @@ class SMPL(object):
 
     # -- one generator stage of Trainer.train_step + its backward -----------
     def step(self, beta, theta, cam, kp_gt, silhouette=None, w_kp=60.0, w_mesh=0.001, img_size=224.0,
-             backward=True, want_verts=True, kp_count_override=0, out=None, skip=()):
+             backward=True, want_verts=True, kp_count_override=0, out=None, skip=(), nowait=False):
         """src/trainer.py:404-450 + :502 for one stage: SMPL forward, keypoint
         projection and loss, optional mesh-reprojection loss, and gradients
         w.r.t. beta/theta/cam.  `silhouette` = (points_xy [P,2], offsets [B+1])
@@ -120,7 +120,8 @@ class SMPL(object):
         want_verts="device" (host-buffer calls) computes verts but leaves them in
         device memory (out["verts_device_ptr"]) instead of copying 339 MB back; names in
         `skip` (of "joints", "Rs", "kp_pred") are not returned (host mode: not
-        copied back)."""
+        copied back).  nowait=True (host mode, pinned arrays only) returns without
+        synchronising; call ctx.sync() before reading the outputs."""
         a = runtime.Args(self.ctx)
         N = int(beta.shape[0])
         V, K = self.size[0], self.num_keypoints
@@ -158,7 +159,8 @@ class SMPL(object):
             self.ctx.debug_set("keep_verts", 1)
         try:
             check(lib().smplb_step(self.ctx.handle, N, pb, pt, pc, pk, pp, po, P, float(w_kp), float(w_mesh),
-                                   float(img_size), int(kp_count_override), pv, pj, pR, pkp, pl, pdb, pdt, pdc, a.mem))
+                                   float(img_size), int(kp_count_override), pv, pj, pR, pkp, pl, pdb, pdt, pdc,
+                                   2 if (nowait and a.mem == runtime.HOST) else a.mem))
         finally:
             if want_verts == "device":
                 self.ctx.debug_set("keep_verts", 0)

@@ -20,7 +20,10 @@
  *     SMPLB_HOST (pageable or pinned host memory; the call copies in, runs,
  *     copies out and returns when the outputs are valid) or SMPLB_DEVICE
  *     (device memory from smplb_malloc; the call is asynchronous on the
- *     context's stream, order with smplb_sync or smplb_timer_*).
+ *     context's stream, order with smplb_sync or smplb_timer_*).  SMPLB_HOST_ASYNC is
+ *     SMPLB_HOST without the final synchronisation: buffers must be pinned
+ *     (smplb_host_alloc) and outputs are valid after smplb_sync -- lets a caller keep two
+ *     contexts in flight so copies of one step overlap the kernels of the other.
  *   - a pointer documented "may be NULL" is an optional output/input.
  *   - a context is bound to one device, owns one stream and is not thread-safe.
  */
@@ -38,6 +41,7 @@ extern "C" {
 
 #define SMPLB_HOST 0
 #define SMPLB_DEVICE 1
+#define SMPLB_HOST_ASYNC 2 /* host buffers (pinned), no synchronisation at return */
 
 #define SMPLB_OK 0
 #define SMPLB_EINVAL (-1)   /* bad argument                         */
