@@ -226,64 +226,73 @@ def main():
 
     peaks = load_peaks()
     model = synthetic.make_model(seed=0)
-    smpl = SMPL(model, device=local, max_batch=B)
+    # Two contexts per GPU (own streams + workspace) take alternate steps, so the latency-bound
+    # per-body kernels of one step fill the gaps of the other step's streaming kernels.
+    engines = [SMPL(model, device=local, max_batch=B) for _ in range(2)]
+    smpl = engines[0]
     ctx = smpl.ctx
     if world > 1:
-        uid = [runtime.Context.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(world, rank, uid[0])
+        for e in engines:
+            uid = [runtime.Context.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            e.ctx.comm_init(world, rank, uid[0])
 
     # inputs: 4 rotating sets so no step re-reads what the previous one left in L2
     NSET = 4
     host_sets = [synthetic.make_inputs(B, seed=1000 + rank * 17 + i) for i in range(NSET)]
-    dev_sets = [{k: ctx.to_device(v) for k, v in s.items()} for s in host_sets]
-    out = {}
+    dev_sets = [[{k: e.ctx.to_device(v) for k, v in s.items()} for s in host_sets] for e in engines]
+    outs = [{}, {}]
+
+    def sync_all():
+        for e in engines:
+            e.ctx.sync()
 
     def barrier():
-        ctx.sync()
+        sync_all()
         if dist is not None:
             dist.barrier()
-        ctx.sync()
+        sync_all()
 
-    def gpu_step(i):
-        d = dev_sets[i % NSET]
-        smpl.step(d["beta"], d["theta"], d["cam"], d["kp_gt"], w_kp=60.0, out=out)
+    def gpu_step(i, n_eng=2):
+        e = i % n_eng
+        d = dev_sets[e][i % NSET]
         # with world > 1 the context holds an NCCL communicator and smplb_step all-reduces
         # {kp numerator, kp count, mesh sum} inside the call (the path's one exchange)
+        engines[e].step(d["beta"], d["theta"], d["cam"], d["kp_gt"], w_kp=60.0, out=outs[e])
 
-    for i in range(W):
+    for i in range(2 * W):
         gpu_step(i)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.15)
-    launches0 = ctx.launch_count()
+    launches0 = sum(e.ctx.launch_count() for e in engines)
     barrier()
     ctx.timer_start(0)
+    engines[1].ctx.order_after(ctx)                 # engine 1 starts after the start event
     for i in range(args.steps):
         gpu_step(i)
+    ctx.order_after(engines[1].ctx)                 # the stop event waits for both engines
     ctx.timer_stop(0)
     ms_total = ctx.timer_ms(0)
     barrier()
-    launches = ctx.launch_count() - launches0
-    # per-kernel launch durations: the same K steps again with CUDA events around every launch
+    launches = sum(e.ctx.launch_count() for e in engines) - launches0
+    # per-kernel launch durations: K steps on ONE context with CUDA events around every launch
     # (the library then keeps all kernels on one stream so each duration is clean)
     ctx.profile(True)
     for i in range(args.steps):
-        gpu_step(i)
+        gpu_step(i, 1)
     prof = ctx.profile_read()
     ctx.profile(False)
     barrier()
     clocks = sampler.finish()
-    loss_parts = out["loss_parts"].numpy()
+    loss_parts = outs[0]["loss_parts"].numpy()
 
     # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region.
     # Two contexts (each with its own streams and workspace) alternate steps, so the PCIe copies
     # of one step overlap the kernels of the other -- the double buffering any input pipeline
     # does.  Every step still copies ITS inputs H2D from pinned memory and ITS loss + gradients
     # D2H; verts (339 MB) and Rs are computed and stay in device memory.
-    smpl_b = SMPL(model, device=local, max_batch=B)
-    engines = [smpl, smpl_b]
     pin = [{k: runtime.pinned_empty(v.shape) for k, v in s.items()} for s in host_sets]
     for p, s in zip(pin, host_sets):
         for k in s:
@@ -362,9 +371,10 @@ def main():
                        "global_batch": world * B, "parallelism": "batch-sharded x%d" % world,
                        "l2": "per-step working set (verts + v_posed + dp, ~1.0 GB) exceeds the 126 MB L2; inputs rotate "
                              "over %d buffer sets" % NSET,
-                       "timing": "value: CUDA events around the K steps on the context stream (6890-vertex path overlapped on a "
-                                 "second stream inside the library); roofline / kernels_ms_per_step: the same K steps repeated "
-                                 "with events around every launch, single stream",
+                       "timing": "value: CUDA events around the K steps, which alternate between two contexts of the GPU "
+                                 "(each overlaps its 6890-vertex kernels with its keypoint path on a second stream); "
+                                 "roofline / kernels_ms_per_step: K more steps on one context with events around every "
+                                 "launch, single stream",
                        "e2e": "host-buffer smpl.step on two alternating contexts (copies of one step overlap kernels of the "
                               "other): per step pinned H2D of beta/theta/cam/kp_gt and D2H of loss + d_beta/d_theta/d_cam; "
                               "verts are computed and stay in device memory"},

@@ -38,6 +38,7 @@ SIGNATURES = {
     "smplb_memcpy_d2h": [_P, _P, _P, _SZ],
     "smplb_memset": [_P, _P, _I, _SZ],
     "smplb_sync": [_P],
+    "smplb_order_after": [_P, _P],
     "smplb_flush_l2": [_P, _SZ],
     "smplb_timer_start": [_P, _I],
     "smplb_timer_stop": [_P, _I],

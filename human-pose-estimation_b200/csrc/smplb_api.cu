@@ -485,6 +485,17 @@ extern "C" int smplb_sync(smplb_ctx *c) {
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return 0;
 }
+extern "C" int smplb_order_after(smplb_ctx *c, smplb_ctx *other) {
+  CHECK_CTX(c);
+  RET_IF(!other, SMPLB_EINVAL, "null context");
+  RET_IF(other->device != c->device, SMPLB_EINVAL, "contexts live on different devices");
+  cudaEvent_t ev;
+  CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(ev, other->stream));
+  CUDA_TRY(cudaStreamWaitEvent(c->stream, ev, 0));
+  CUDA_TRY(cudaEventDestroy(ev));   // released once the wait has been satisfied
+  return 0;
+}
 extern "C" int smplb_flush_l2(smplb_ctx *c, size_t bytes) {
   CHECK_CTX(c);
   if (bytes > c->flush_bytes) {

@@ -105,6 +105,10 @@ class Context(object):
     def sync(self):
         check(lib().smplb_sync(self.handle))
 
+    def order_after(self, other):
+        """Work enqueued on this context from now on runs after what `other` has enqueued."""
+        check(lib().smplb_order_after(self.handle, other.handle))
+
     def flush_l2(self, nbytes=256 << 20):
         check(lib().smplb_flush_l2(self.handle, int(nbytes)))
 

@@ -89,6 +89,9 @@ int smplb_memcpy_h2d(smplb_ctx *ctx, void *dst, const void *src, size_t bytes); 
 int smplb_memcpy_d2h(smplb_ctx *ctx, void *dst, const void *src, size_t bytes); /* async on ctx stream */
 int smplb_memset(smplb_ctx *ctx, void *dst, int value, size_t bytes);
 int smplb_sync(smplb_ctx *ctx);
+/* Orders everything enqueued on `ctx` from now on after the work already enqueued on `other`
+ * (an event wait between the two contexts' streams; no host synchronisation).        */
+int smplb_order_after(smplb_ctx *ctx, smplb_ctx *other);
 /* Writes `bytes` of a private scratch buffer (bench: evict L2 between timed steps). */
 int smplb_flush_l2(smplb_ctx *ctx, size_t bytes);
 /* CUDA-event timers on the context's stream; slot in [0,16). */
