@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--engines", type=int, default=2, help="contexts in flight per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -228,7 +229,8 @@ def main():
     model = synthetic.make_model(seed=0)
     # Two contexts per GPU (own streams + workspace) take alternate steps, so the latency-bound
     # per-body kernels of one step fill the gaps of the other step's streaming kernels.
-    engines = [SMPL(model, device=local, max_batch=B) for _ in range(2)]
+    NE = max(1, args.engines)
+    engines = [SMPL(model, device=local, max_batch=B) for _ in range(NE)]
     smpl = engines[0]
     ctx = smpl.ctx
     if world > 1:
@@ -241,7 +243,7 @@ def main():
     NSET = 4
     host_sets = [synthetic.make_inputs(B, seed=1000 + rank * 17 + i) for i in range(NSET)]
     dev_sets = [[{k: e.ctx.to_device(v) for k, v in s.items()} for s in host_sets] for e in engines]
-    outs = [{}, {}]
+    outs = [{} for _ in engines]
 
     def sync_all():
         for e in engines:
@@ -253,14 +255,14 @@ def main():
             dist.barrier()
         sync_all()
 
-    def gpu_step(i, n_eng=2):
+    def gpu_step(i, n_eng=NE):
         e = i % n_eng
         d = dev_sets[e][i % NSET]
         # with world > 1 the context holds an NCCL communicator and smplb_step all-reduces
         # {kp numerator, kp count, mesh sum} inside the call (the path's one exchange)
         engines[e].step(d["beta"], d["theta"], d["cam"], d["kp_gt"], w_kp=60.0, out=outs[e])
 
-    for i in range(2 * W):
+    for i in range(NE * W):
         gpu_step(i)
     barrier()
     sampler = ClockSampler(local)
@@ -269,10 +271,12 @@ def main():
     launches0 = sum(e.ctx.launch_count() for e in engines)
     barrier()
     ctx.timer_start(0)
-    engines[1].ctx.order_after(ctx)                 # engine 1 starts after the start event
+    for e in engines[1:]:
+        e.ctx.order_after(ctx)                      # the other engines start after the start event
     for i in range(args.steps):
         gpu_step(i)
-    ctx.order_after(engines[1].ctx)                 # the stop event waits for both engines
+    for e in engines[1:]:
+        ctx.order_after(e.ctx)                      # the stop event waits for every engine
     ctx.timer_stop(0)
     ms_total = ctx.timer_ms(0)
     barrier()
@@ -302,15 +306,15 @@ def main():
     losses = []
 
     def e2e_step(i):
-        e = i % 2
-        engines[e].ctx.sync()                       # results of step i-2 (same engine) are on the host now
-        if i >= 2:
+        e = i % NE
+        engines[e].ctx.sync()                       # results of step i-NE (same engine) are on the host now
+        if i >= NE:
             losses.append(float(eouts[e]["loss_parts"][3]))
         p = pin[i % NSET]
         engines[e].step(p["beta"], p["theta"], p["cam"], p["kp_gt"], w_kp=60.0, want_verts="device", out=eouts[e],
                         skip=("Rs", "joints", "kp_pred"), nowait=True)
 
-    for i in range(4):
+    for i in range(2 * NE):
         e2e_step(i)
     for e in engines:
         e.ctx.sync()
@@ -368,7 +372,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "SMPL fwd+bwd (beta/theta/cam) + kp reprojection loss, B=%d per GPU, V=6890, K=19, "
                                    "dense skinning weights (BASELINE config 2)" % B,
-                       "global_batch": world * B, "parallelism": "batch-sharded x%d" % world,
+                       "global_batch": world * B, "parallelism": "batch-sharded x%d" % world, "contexts_in_flight_per_gpu": NE,
                        "l2": "per-step working set (verts + v_posed + dp, ~1.0 GB) exceeds the 126 MB L2; inputs rotate "
                              "over %d buffer sets" % NSET,
                        "timing": "value: CUDA events around the K steps, which alternate between two contexts of the GPU "
