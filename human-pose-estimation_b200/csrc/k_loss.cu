@@ -141,14 +141,172 @@ __device__ __forceinline__ float d2_expand(float ax, float ay, float a2, float b
 #define MT 256     // threads per CTA of the NN kernels
 #define MTILE 1024 // points staged per shared-memory tile
 
+// ---- uniform-grid acceleration of the nearest-neighbour search -----------------------------
+// The reference scans every (pixel, vertex) pair.  Here each point set of each image is binned
+// into a GRID_G x GRID_G grid over its bounding box and a query walks Chebyshev rings of cells
+// around its own cell, stopping once every unvisited cell is provably farther than the best
+// candidate.  Candidates are compared with the SAME fp32 expansion as the brute-force scan
+// (and the smaller index on equal values), and the stopping rule carries a margin that bounds
+// the rounding error of that expansion, so the result is bit-identical to the full scan
+// (tests/test_gpu_parity.py::test_mesh_grid_search_equals_brute_force) at ~1/40 of the pairs.
+#define GRID_G 32
+#define GRID_NC (GRID_G * GRID_G)
+#define GP_STRIDE 8   // x0, y0, x1, y1, inv_h, h, max |p|^2, -
+
+// One CTA per (set, image): set 0 = projected vertices, set 1 = silhouette pixels.
+__global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restrict__ pts, const int *__restrict__ offsets,
+                                                    const float *__restrict__ sil_pred, float *__restrict__ gparam,
+                                                    int *__restrict__ gstart, float4 *__restrict__ sortedB,
+                                                    float4 *__restrict__ sortedA) {
+  __shared__ float red[4][256];
+  __shared__ int hist[GRID_NC];
+  __shared__ int scan[256];
+  int sel = blockIdx.x, i = blockIdx.y, t = threadIdx.x;
+  int p0 = offsets[i];
+  int n = sel == 0 ? V : offsets[i + 1] - p0;
+  const float *src = sel == 0 ? sil_pred + (size_t)i * V * 2 : pts + (size_t)p0 * 2;
+  float4 *dst = sel == 0 ? sortedB + (size_t)i * V : sortedA + p0;
+  float *gp = gparam + ((size_t)i * 2 + sel) * GP_STRIDE;
+  int *gs = gstart + ((size_t)i * 2 + sel) * (GRID_NC + 1);
+  float mnx = 3.4e38f, mny = 3.4e38f, mxx = -3.4e38f, mxy = -3.4e38f;
+  for (int k = t; k < n; k += 256) {
+    float x = src[2 * k], y = src[2 * k + 1];
+    mnx = fminf(mnx, x);
+    mny = fminf(mny, y);
+    mxx = fmaxf(mxx, x);
+    mxy = fmaxf(mxy, y);
+  }
+  red[0][t] = mnx;
+  red[1][t] = mny;
+  red[2][t] = mxx;
+  red[3][t] = mxy;
+  for (int k = t; k < GRID_NC; k += 256) hist[k] = 0;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) {
+      red[0][t] = fminf(red[0][t], red[0][t + o]);
+      red[1][t] = fminf(red[1][t], red[1][t + o]);
+      red[2][t] = fmaxf(red[2][t], red[2][t + o]);
+      red[3][t] = fmaxf(red[3][t], red[3][t + o]);
+    }
+    __syncthreads();
+  }
+  float x0 = red[0][0], y0 = red[1][0], x1 = red[2][0], y1 = red[3][0];
+  if (n == 0) {
+    x0 = y0 = x1 = y1 = 0.f;
+  }
+  float ext = fmaxf(x1 - x0, y1 - y0);
+  float h = ext > 0.f ? ext / GRID_G : 1.0f;
+  float inv_h = 1.0f / h;
+  for (int k = t; k < n; k += 256) {
+    float x = src[2 * k], y = src[2 * k + 1];
+    int cx = min(GRID_G - 1, max(0, (int)((x - x0) * inv_h)));
+    int cy = min(GRID_G - 1, max(0, (int)((y - y0) * inv_h)));
+    atomicAdd(&hist[cy * GRID_G + cx], 1);
+  }
+  __syncthreads();
+  // exclusive scan of the 1024 counts: 4 cells per thread + block scan
+  int c0 = hist[4 * t], c1 = hist[4 * t + 1], c2 = hist[4 * t + 2], c3 = hist[4 * t + 3];
+  scan[t] = c0 + c1 + c2 + c3;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    int v = t >= o ? scan[t - o] : 0;
+    __syncthreads();
+    scan[t] += v;
+    __syncthreads();
+  }
+  int base = scan[t] - (c0 + c1 + c2 + c3);
+  __syncthreads();
+  hist[4 * t] = base;                 // hist now holds the running cursors
+  hist[4 * t + 1] = base + c0;
+  hist[4 * t + 2] = base + c0 + c1;
+  hist[4 * t + 3] = base + c0 + c1 + c2;
+  gs[4 * t] = base;
+  gs[4 * t + 1] = base + c0;
+  gs[4 * t + 2] = base + c0 + c1;
+  gs[4 * t + 3] = base + c0 + c1 + c2;
+  if (t == 255) gs[GRID_NC] = n;
+  __syncthreads();
+  for (int k = t; k < n; k += 256) {
+    float x = src[2 * k], y = src[2 * k + 1];
+    int cx = min(GRID_G - 1, max(0, (int)((x - x0) * inv_h)));
+    int cy = min(GRID_G - 1, max(0, (int)((y - y0) * inv_h)));
+    int pos = atomicAdd(&hist[cy * GRID_G + cx], 1);
+    dst[pos] = make_float4(x, y, __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __int_as_float(k));
+  }
+  if (t == 0) {
+    gp[0] = x0;
+    gp[1] = y0;
+    gp[2] = x1;
+    gp[3] = y1;
+    gp[4] = inv_h;
+    gp[5] = h;
+    gp[6] = fmaxf(x0 * x0, x1 * x1) + fmaxf(y0 * y0, y1 * y1);
+    gp[7] = 0.f;
+  }
+}
+
+// Nearest candidate of query q in a binned set.  QUERY_IS_A: q is a pixel (a), candidates are
+// vertices (b); otherwise the roles in the expansion are swapped.  Returns the candidate's
+// ORIGINAL index (smaller index on equal values == first index of a full in-order scan).
+template <bool QUERY_IS_A>
+__device__ __forceinline__ void grid_search(float qx, float qy, float q2, const float4 *__restrict__ sorted,
+                                            const int *__restrict__ gs, const float *__restrict__ gp, float margin,
+                                            float &best, int &bi) {
+  float x0 = gp[0], y0 = gp[1], x1 = gp[2], y1 = gp[3], inv_h = gp[4], h = gp[5];
+  float qcx = fminf(fmaxf(qx, x0), x1), qcy = fminf(fmaxf(qy, y0), y1);   // projection onto the bounding box
+  float outside2 = (qx - qcx) * (qx - qcx) + (qy - qcy) * (qy - qcy);
+  int cx = min(GRID_G - 1, max(0, (int)((qcx - x0) * inv_h)));
+  int cy = min(GRID_G - 1, max(0, (int)((qcy - y0) * inv_h)));
+  best = 3.4e38f;
+  bi = 0x7fffffff;
+  int rmax = max(max(cx, GRID_G - 1 - cx), max(cy, GRID_G - 1 - cy));
+  for (int r = 0; r <= rmax; ++r) {
+    int ylo = cy - r, yhi = cy + r;
+    for (int y = max(ylo, 0); y <= min(yhi, GRID_G - 1); ++y) {
+      bool full_row = (y == ylo) || (y == yhi);
+      int xa = max(cx - r, 0), xb = min(cx + r, GRID_G - 1);
+      // full rows of the ring are one contiguous cell range; inner rows contribute their two end cells
+      int nseg = full_row ? 1 : 2;
+      for (int sgi = 0; sgi < nseg; ++sgi) {
+        int c_lo, c_hi;
+        if (full_row) {
+          c_lo = y * GRID_G + xa;
+          c_hi = y * GRID_G + xb;
+        } else {
+          int x = sgi == 0 ? cx - r : cx + r;
+          if (x < 0 || x > GRID_G - 1) continue;
+          c_lo = c_hi = y * GRID_G + x;
+        }
+        for (int k = gs[c_lo]; k < gs[c_hi + 1]; ++k) {
+          float4 cnd = sorted[k];
+          float d = QUERY_IS_A ? d2_expand(qx, qy, q2, cnd.x, cnd.y, cnd.z) : d2_expand(cnd.x, cnd.y, cnd.z, qx, qy, q2);
+          int id = __float_as_int(cnd.w);
+          if (d < best || (d == best && id < bi)) {
+            best = d;
+            bi = id;
+          }
+        }
+      }
+    }
+    // every unvisited cell is at Chebyshev ring >= r + 1: its points are >= r * h from the
+    // projected query (0.9999 covers the rounding of the cell assignment)
+    float rh = (float)r * h;
+    if (rh * rh * 0.9999f + outside2 > best + margin) break;
+  }
+}
+
 // pixel -> nearest vertex (ind_AB, ops.py:68): thread = pixel a of image i, scans all vertices
 // in index order with a strict '<' so the first minimal index wins (tf.argmin).  Adds the L1
 // term |A_a - B_nn| (ops.py:98) to a per-CTA partial and the integer sign sums of its gradient
 // to cnt[i][nn][0..1].
+template <bool GRID>
 __global__ void __launch_bounds__(MT) k_mesh_ab(int V, const float *__restrict__ pts, const int *__restrict__ offsets,
                                                 const float *__restrict__ sil_pred, float *__restrict__ part,
-                                                int *__restrict__ cnt, int *__restrict__ ind_ab) {
-  __shared__ float4 s4[MTILE];   // (x, y, |.|^2, -) of the staged vertices: one broadcast LDS.128 per pair
+                                                int *__restrict__ cnt, int *__restrict__ ind_ab,
+                                                const float *__restrict__ gparam, const int *__restrict__ gstart,
+                                                const float4 *__restrict__ sortedB) {
+  __shared__ float4 s4[GRID ? 1 : MTILE];   // (x, y, |.|^2, -) of the staged vertices: one broadcast LDS.128 per pair
   __shared__ float red[MT];
   int i = blockIdx.y;
   int p0 = offsets[i], np = offsets[i + 1] - p0;
@@ -166,6 +324,11 @@ __global__ void __launch_bounds__(MT) k_mesh_ab(int V, const float *__restrict__
     float a2 = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));
     float best = 3.4e38f;
     int bi = 0;
+    if (GRID) {
+      const float *gpB = gparam + ((size_t)i * 2 + 0) * GP_STRIDE, *gpA = gparam + ((size_t)i * 2 + 1) * GP_STRIDE;
+      float margin = 32.0f * 5.9604645e-8f * fmaxf(gpA[6], gpB[6]);
+      if (ok) grid_search<true>(ax, ay, a2, sortedB + (size_t)i * V, gstart + ((size_t)i * 2 + 0) * (GRID_NC + 1), gpB, margin, best, bi);
+    } else
     for (int v0 = 0; v0 < V; v0 += MTILE) {
       int nv = min(MTILE, V - v0);
       __syncthreads();
@@ -203,10 +366,13 @@ __global__ void __launch_bounds__(MT) k_mesh_ab(int V, const float *__restrict__
 
 // vertex -> nearest pixel (ind_BA, ops.py:69): thread = vertex b, scans all pixels of image i
 // in order.  Adds the L2 term ||B_b - A_nn|| (ops.py:92) and writes its gradient (unit vector).
+template <bool GRID>
 __global__ void __launch_bounds__(MT) k_mesh_ba(int V, const float *__restrict__ pts, const int *__restrict__ offsets,
                                                 const float *__restrict__ sil_pred, float *__restrict__ part,
-                                                float *__restrict__ d_sil, int *__restrict__ ind_ba) {
-  __shared__ float4 s4[MTILE];
+                                                float *__restrict__ d_sil, int *__restrict__ ind_ba,
+                                                const float *__restrict__ gparam, const int *__restrict__ gstart,
+                                                const float4 *__restrict__ sortedA) {
+  __shared__ float4 s4[GRID ? 1 : MTILE];
   __shared__ float red[MT];
   int i = blockIdx.y;
   int p0 = offsets[i], np = offsets[i + 1] - p0;
@@ -221,6 +387,13 @@ __global__ void __launch_bounds__(MT) k_mesh_ba(int V, const float *__restrict__
   float b2 = __fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by));
   float best = 3.4e38f;
   int ai = -1;
+  if (GRID) {
+    if (ok && np > 0) {
+      const float *gpB = gparam + ((size_t)i * 2 + 0) * GP_STRIDE, *gpA = gparam + ((size_t)i * 2 + 1) * GP_STRIDE;
+      float margin = 32.0f * 5.9604645e-8f * fmaxf(gpA[6], gpB[6]);
+      grid_search<false>(bx, by, b2, sortedA + p0, gstart + ((size_t)i * 2 + 1) * (GRID_NC + 1), gpA, margin, best, ai);
+    }
+  } else
   for (int a0 = 0; a0 < np; a0 += MTILE) {
     int na = min(MTILE, np - a0);
     __syncthreads();
@@ -387,15 +560,37 @@ int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long l
 #define MESH_AB_BLOCKS 32
 int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *offsets, int P, const float *sil_pred,
                      float *loss, float *d_sil_pred, int *cnt_scratch, float *part_scratch, int *ind_ab, int *ind_ba) {
-  (void)P;
   int n_ba_blocks = cdiv(V, MT);
   float *part_ab = part_scratch;
   float *part_ba = part_scratch + (size_t)B * MESH_AB_BLOCKS;
-  if (d_sil_pred) CUDA_TRY(cudaMemsetAsync(cnt_scratch, 0, (size_t)B * V * 2 * sizeof(int), c->stream));
-  LAUNCH(c, "mesh_nn_pixel_to_vertex", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab, V, pts, offsets, sil_pred, part_ab,
-         d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab);
-  LAUNCH(c, "mesh_nn_vertex_to_pixel", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba, V, pts, offsets, sil_pred, part_ba,
-         d_sil_pred, ind_ba);
+  if (d_sil_pred) CUDA_TRY(cudaMemsetAsync(cnt_scratch, 0, (size_t)B * V * 2 * sizeof(int), c->cur));
+  if (c->use_mesh_grid) {
+    // grid workspace: per image and set 8 floats + 1025 ints, sorted copies of both point sets
+    size_t need = (size_t)B * 2 * GP_STRIDE * 4 + (size_t)B * 2 * (GRID_NC + 1) * 4 + ((size_t)B * V + (size_t)P + 16) * 16 + 256;
+    if (need > c->ws_grid_cap) {
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      if (c->ws_grid) CUDA_TRY(cudaFree(c->ws_grid));
+      c->ws_grid = nullptr;
+      CUDA_TRY(cudaMalloc(&c->ws_grid, need));
+      c->ws_grid_cap = need;
+    }
+    char *w = (char *)c->ws_grid;
+    float4 *sortedB = (float4 *)w;
+    float4 *sortedA = sortedB + (size_t)B * V;
+    float *gparam = (float *)(sortedA + P + 16);
+    int *gstart = (int *)(gparam + (size_t)B * 2 * GP_STRIDE);
+    LAUNCH(c, "mesh_grid_build", dim3(2, B), 256, 0, k_grid_build, V, pts, offsets, sil_pred, gparam, gstart, sortedB, sortedA);
+    LAUNCH(c, "mesh_nn_pixel_to_vertex_grid", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab<true>, V, pts, offsets, sil_pred,
+           part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, gparam, gstart, sortedB);
+    LAUNCH(c, "mesh_nn_vertex_to_pixel_grid", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba<true>, V, pts, offsets, sil_pred,
+           part_ba, d_sil_pred, ind_ba, gparam, gstart, sortedA);
+  } else {
+    LAUNCH(c, "mesh_nn_pixel_to_vertex", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab<false>, V, pts, offsets, sil_pred,
+           part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, (const float *)nullptr, (const int *)nullptr,
+           (const float4 *)nullptr);
+    LAUNCH(c, "mesh_nn_vertex_to_pixel", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba<false>, V, pts, offsets, sil_pred, part_ba,
+           d_sil_pred, ind_ba, (const float *)nullptr, (const int *)nullptr, (const float4 *)nullptr);
+  }
   float denom = (float)(3 + V);
   LAUNCH(c, "mesh_finish", 1, 1024, 0, k_mesh_finish, B * MESH_AB_BLOCKS, part_ab, B * n_ba_blocks, part_ba, denom,
          loss);

@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -271,6 +272,7 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
   c->pitch = 3 * c->Vp;
   c->ksplit = 16;
   c->max_batch = std::max(max_batch, 1);
+  if (const char *e = getenv("SMPLB_L2_CHUNK")) c->l2_chunk = atoi(e);   // experiment knob, see DESIGN.md section 4
   // kinematic tree: parent index < child index (batch_lbs.py:130 walks joints in index order)
   c->tree.max_depth = 0;
   for (int j = 0; j < NJ; ++j) {
@@ -420,7 +422,7 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
   void *ptrs[] = {c->d_vt,       c->d_shapedirs, c->d_posedirs, c->d_W,        c->d_JR,       c->d_Dext,   c->d_J0,
                   c->d_Jdirs,    c->d_kcsr_off,  c->d_kcsr_idx, c->d_kcsr_val, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val,
                   c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_W16,      c->d_G,        c->d_cc,       c->d_G16,      c->d_Gt16,     c->d_Dt16_act, c->d_W16_act,  c->d_kcsr_slot, c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
-                  c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part};
+                  c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part, c->ws_grid};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 16; ++i) {
@@ -543,6 +545,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
   }
   if (!strcmp(key, "keep_verts")) {
     c->keep_verts = value;
+    return 0;
+  }
+  if (!strcmp(key, "mesh_grid")) {
+    c->use_mesh_grid = value;
     return 0;
   }
   if (!strcmp(key, "fold_warp")) {

@@ -132,6 +132,9 @@ struct smplb_ctx {
   float *ws_gp = nullptr;      // gradient-penalty partials
   size_t ws_gp_cap = 0;        // floats
   float *ws_mesh_part = nullptr;   // mesh-loss per-CTA partials
+  void *ws_grid = nullptr;         // uniform-grid search workspace (k_loss.cu)
+  size_t ws_grid_cap = 0;
+  int use_mesh_grid = 1;           // smplb_debug_set("mesh_grid", 0): brute-force scan (the reference's own algorithm)
   size_t ws_mesh_part_cap = 0;
   size_t ws_mesh_cap = 0;      // elements of ws_silpred / ws_dsil / ws_silcnt
   int saved_B = 0;

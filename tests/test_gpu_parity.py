@@ -404,3 +404,30 @@ def test_folded_keypoint_path_matches_per_vertex_path(smpl_full):
     finally:
         ctx.debug_set("fold", 1)
     assert rel_err(db1, db0) < 2e-5 and rel_err(dt1, dt0) < 2e-5
+
+
+def test_mesh_grid_search_equals_brute_force():
+    """The uniform-grid nearest-neighbour search must reproduce the reference's full scan
+    bit for bit: same indices (first index on ties), same loss, same gradient."""
+    rng = np.random.default_rng(77)
+    B, V = 6, 1500
+    seg = synthetic.make_silhouettes(B, seed=19, a_range=(10, 30), b_range=(20, 60))
+    pts3 = synthetic.silhouette_points(seg)
+    sp = (rng.normal(size=(B, V, 2)) * np.array([25.0, 45.0]) + 112.0).astype(np.float32)
+    sp[0, :200] = sp[0, 200:400]                       # exact duplicates: ties must pick the first index
+    sp[1] += 400.0                                     # a mesh projected far outside the image
+    sp[3, :, 0] = 100.0                                # degenerate: all vertices on one vertical line
+    ctx = ops._ctx_for(sp)
+    pts, offs = ops.silhouette_csr(pts3, B)
+    res = {}
+    for mode in (1, 0):
+        ctx.debug_set("mesh_grid", mode)
+        res[mode] = ops._mesh_call(ctx, pts, offs, sp, True, True)
+    ctx.debug_set("mesh_grid", 1)
+    (l1, g1, ab1, ba1), (l0, g0, ab0, ba0) = res[1], res[0]
+    assert np.array_equal(ab1, ab0) and np.array_equal(ba1, ba0)
+    assert l1[0] == l0[0]
+    assert np.array_equal(g1, g0)
+    # and both agree with the oracle's value
+    lo = onp.mesh_reprojection_loss(pts3.astype(np.float64), sp.astype(np.float64), B)
+    assert abs(l1[0] - lo) < TOL * lo
