@@ -368,17 +368,21 @@ __global__ void __launch_bounds__(MT) k_mesh_ab(int V, const float *__restrict__
 // in order.  Adds the L2 term ||B_b - A_nn|| (ops.py:92) and writes its gradient (unit vector).
 template <bool GRID>
 __global__ void __launch_bounds__(MT) k_mesh_ba(int V, const float *__restrict__ pts, const int *__restrict__ offsets,
-                                                const float *__restrict__ sil_pred, float *__restrict__ part,
+                                                const float *__restrict__ sil_pred, float *__restrict__ vdist,
                                                 float *__restrict__ d_sil, int *__restrict__ ind_ba,
                                                 const float *__restrict__ gparam, const int *__restrict__ gstart,
-                                                const float4 *__restrict__ sortedA) {
+                                                const float4 *__restrict__ sortedA, const float4 *__restrict__ sortedB) {
   __shared__ float4 s4[GRID ? 1 : MTILE];
-  __shared__ float red[MT];
   int i = blockIdx.y;
   int p0 = offsets[i], np = offsets[i + 1] - p0;
-  int b = blockIdx.x * MT + threadIdx.x;
-  bool ok = b < V;
+  int slot = blockIdx.x * MT + threadIdx.x;
+  bool ok = slot < V;
   const float *Bv = sil_pred + (size_t)i * V * 2;
+  // GRID: threads walk the vertices in their binned order, so the lanes of a warp query
+  // neighbouring positions (similar cells, similar trip counts); results go to the vertex's
+  // original index, and the per-image sum is taken in index order by k_mesh_rowsum.
+  int b = slot;
+  if (GRID && ok) b = __float_as_int(sortedB[(size_t)i * V + slot].w);
   float bx = 0.f, by = 0.f;
   if (ok) {
     bx = Bv[(size_t)b * 2 + 0];
@@ -427,8 +431,18 @@ __global__ void __launch_bounds__(MT) k_mesh_ba(int V, const float *__restrict__
     d_sil[((size_t)i * V + b) * 2 + 0] = gx;
     d_sil[((size_t)i * V + b) * 2 + 1] = gy;
   }
-  float bs = block_sum(dist, red);
-  if (threadIdx.x == 0) part[(size_t)i * gridDim.x + blockIdx.x] = bs;
+  if (ok) vdist[(size_t)i * V + b] = dist;
+}
+
+// Per-image sum of the vertex->pixel distances in vertex-index order (fixed order: the same
+// bits whichever order the search visited the vertices in).
+__global__ void __launch_bounds__(256) k_mesh_rowsum(int V, const float *__restrict__ vdist, float *__restrict__ part) {
+  __shared__ float red[256];
+  int i = blockIdx.x;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < V; k += 256) s += vdist[(size_t)i * V + k];
+  float tot = block_sum(s, red);
+  if (threadIdx.x == 0) part[i] = tot;
 }
 
 // loss = sum(partials) / (3 + V)  (ops.py:129-130: silhouette_gt.shape[1] + silhouette_pred.shape[1]);
@@ -563,6 +577,13 @@ int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *of
   int n_ba_blocks = cdiv(V, MT);
   float *part_ab = part_scratch;
   float *part_ba = part_scratch + (size_t)B * MESH_AB_BLOCKS;
+  if ((size_t)B * V > c->ws_vdist_cap) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->ws_vdist) CUDA_TRY(cudaFree(c->ws_vdist));
+    c->ws_vdist = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&c->ws_vdist, (size_t)B * V * 4));
+    c->ws_vdist_cap = (size_t)B * V;
+  }
   if (d_sil_pred) CUDA_TRY(cudaMemsetAsync(cnt_scratch, 0, (size_t)B * V * 2 * sizeof(int), c->cur));
   if (c->use_mesh_grid) {
     // grid workspace: per image and set 8 floats + 1025 ints, sorted copies of both point sets
@@ -583,17 +604,18 @@ int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *of
     LAUNCH(c, "mesh_nn_pixel_to_vertex_grid", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab<true>, V, pts, offsets, sil_pred,
            part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, gparam, gstart, sortedB);
     LAUNCH(c, "mesh_nn_vertex_to_pixel_grid", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba<true>, V, pts, offsets, sil_pred,
-           part_ba, d_sil_pred, ind_ba, gparam, gstart, sortedA);
+           c->ws_vdist, d_sil_pred, ind_ba, gparam, gstart, sortedA, sortedB);
   } else {
     LAUNCH(c, "mesh_nn_pixel_to_vertex", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab<false>, V, pts, offsets, sil_pred,
            part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, (const float *)nullptr, (const int *)nullptr,
            (const float4 *)nullptr);
-    LAUNCH(c, "mesh_nn_vertex_to_pixel", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba<false>, V, pts, offsets, sil_pred, part_ba,
-           d_sil_pred, ind_ba, (const float *)nullptr, (const int *)nullptr, (const float4 *)nullptr);
+    LAUNCH(c, "mesh_nn_vertex_to_pixel", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba<false>, V, pts, offsets, sil_pred,
+           c->ws_vdist, d_sil_pred, ind_ba, (const float *)nullptr, (const int *)nullptr, (const float4 *)nullptr,
+           (const float4 *)nullptr);
   }
+  LAUNCH(c, "mesh_rowsum", B, 256, 0, k_mesh_rowsum, V, c->ws_vdist, part_ba);
   float denom = (float)(3 + V);
-  LAUNCH(c, "mesh_finish", 1, 1024, 0, k_mesh_finish, B * MESH_AB_BLOCKS, part_ab, B * n_ba_blocks, part_ba, denom,
-         loss);
+  LAUNCH(c, "mesh_finish", 1, 1024, 0, k_mesh_finish, B * MESH_AB_BLOCKS, part_ab, B, part_ba, denom, loss);
   if (d_sil_pred) {
     size_t n = (size_t)B * V * 2;
     LAUNCH(c, "mesh_grad_finish", (unsigned)((n + 255) / 256), 256, 0, k_mesh_grad_finish, n, denom, cnt_scratch,

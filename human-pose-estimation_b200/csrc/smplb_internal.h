@@ -132,6 +132,8 @@ struct smplb_ctx {
   float *ws_gp = nullptr;      // gradient-penalty partials
   size_t ws_gp_cap = 0;        // floats
   float *ws_mesh_part = nullptr;   // mesh-loss per-CTA partials
+  float *ws_vdist = nullptr;       // [B][V] vertex->pixel distances (summed per image in index order)
+  size_t ws_vdist_cap = 0;
   void *ws_grid = nullptr;         // uniform-grid search workspace (k_loss.cu)
   size_t ws_grid_cap = 0;
   int use_mesh_grid = 1;           // smplb_debug_set("mesh_grid", 0): brute-force scan (the reference's own algorithm)
