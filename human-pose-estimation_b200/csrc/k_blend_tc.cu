@@ -30,7 +30,8 @@
 #define TC_KP 256          // padded K
 #define TC_KB 64           // K elements per 128-byte swizzle atom
 #define TC_NKB (TC_KP / TC_KB)
-#define TC_ASTAGES 2
+#define TC_ASTAGES 4         // ring stages of TC_SKB k-blocks each (32 KB): loads run 2 tiles ahead in half-tile steps
+#define TC_SKB 2
 #define TC_THREADS 320
 
 #define SM_B_OFF 0
@@ -42,18 +43,23 @@
 
 #include "tc_ptx.cuh"
 
+#ifndef BLEND_DIRECT_STORE
+#define BLEND_DIRECT_STORE 0
+#endif
+
 #define TC_IDESC umma_idesc_f16(TC_BM, TC_BN)
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_blend_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_d,
-               const __grid_constant__ CUtensorMap map_c, int n_mblk, int n_nblk, float inv_scale) {
+               const __grid_constant__ CUtensorMap map_c, int n_mblk, int n_nblk, float inv_scale, float *__restrict__ out,
+               int out_pitch, int n_rows) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + SM_BAR_OFF;
   // barrier slots (8 bytes each)
-  const uint32_t full_a = bar0 + 0, empty_a = bar0 + 16, full_b = bar0 + 32, empty_b = bar0 + 40;
-  const uint32_t tmem_full = bar0 + 48, tmem_empty = bar0 + 64;
-  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + SM_BAR_OFF + 96);
+  const uint32_t full_a = bar0 + 0, empty_a = bar0 + 32, full_b = bar0 + 64, empty_b = bar0 + 72;
+  const uint32_t tmem_full = bar0 + 80, tmem_empty = bar0 + 96;
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + SM_BAR_OFF + 120);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = n_mblk * n_nblk;
@@ -64,6 +70,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int i = 0; i < TC_ASTAGES; ++i) {
       mbar_init(full_a + 8 * i, 1);
       mbar_init(empty_a + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + 8 * i, 1);
       mbar_init(tmem_empty + 8 * i, 8);   // one arrival per epilogue warp
     }
@@ -72,7 +80,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_BAR_OFF + 96),
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_BAR_OFF + 120),
                  "n"(2 * TC_BN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -99,14 +107,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           ++x_loads;
           cur_m = m;
         }
-        mbar_wait(empty_a + 8 * stage, phase ^ 1);
-        mbar_expect_tx(full_a + 8 * stage, TC_NKB * TILE_KB_BYTES);
-        for (int kb = 0; kb < TC_NKB; ++kb)
-          tma_load_2d(sbase + SM_A_OFF + stage * (TC_NKB * TILE_KB_BYTES) + kb * TILE_KB_BYTES, &map_d, kb * TC_KB,
-                      n * TC_BN, full_a + 8 * stage);
-        if (++stage == TC_ASTAGES) {
-          stage = 0;
-          phase ^= 1;
+        for (int hs = 0; hs < TC_NKB / TC_SKB; ++hs) {
+          mbar_wait(empty_a + 8 * stage, phase ^ 1);
+          mbar_expect_tx(full_a + 8 * stage, TC_SKB * TILE_KB_BYTES);
+          for (int kk = 0; kk < TC_SKB; ++kk)
+            tma_load_2d(sbase + SM_A_OFF + stage * (TC_SKB * TILE_KB_BYTES) + kk * TILE_KB_BYTES, &map_d,
+                        (hs * TC_SKB + kk) * TC_KB, n * TC_BN, full_a + 8 * stage);
+          if (++stage == TC_ASTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -122,30 +132,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           cur_m = m;
         }
         mbar_wait(tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
-        mbar_wait(full_a + 8 * stage, phase);             // Dt16 tile landed
         tc_fence_after();
         uint32_t d_tmem = tmem_base + acc * TC_BN;
 #pragma unroll
-        for (int kb = 0; kb < TC_NKB; ++kb) {
-          // MMA "A" (M = samples) is the resident x16 tile, "B" (N = coordinates) the ring stage
-          uint32_t a_addr = sbase + SM_B_OFF + kb * TILE_KB_BYTES;
-          uint32_t b_addr = sbase + SM_A_OFF + stage * (TC_NKB * TILE_KB_BYTES) + kb * TILE_KB_BYTES;
+        for (int hs = 0; hs < TC_NKB / TC_SKB; ++hs) {
+          mbar_wait(full_a + 8 * stage, phase);           // this half of the Dt16 tile landed
+          tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < TC_KB / 16; ++k) {
-            // advance 16 fp16 = 32 B inside the 128 B swizzle atom
-            uint64_t ad = umma_desc_sw128(a_addr + k * 32);
-            uint64_t bd = umma_desc_sw128(b_addr + k * 32);
-            tc_mma_f16(d_tmem, ad, bd, TC_IDESC, (kb | k) != 0);
+          for (int kk = 0; kk < TC_SKB; ++kk) {
+            int kb = hs * TC_SKB + kk;
+            // MMA "A" (M = samples) is the resident x16 tile, "B" (N = coordinates) the ring stage
+            uint32_t a_addr = sbase + SM_B_OFF + kb * TILE_KB_BYTES;
+            uint32_t b_addr = sbase + SM_A_OFF + stage * (TC_SKB * TILE_KB_BYTES) + kk * TILE_KB_BYTES;
+#pragma unroll
+            for (int k = 0; k < TC_KB / 16; ++k) {
+              // advance 16 fp16 = 32 B inside the 128 B swizzle atom
+              uint64_t ad = umma_desc_sw128(a_addr + k * 32);
+              uint64_t bd = umma_desc_sw128(b_addr + k * 32);
+              tc_mma_f16(d_tmem, ad, bd, TC_IDESC, (kb | k) != 0);
+            }
+          }
+          tc_commit(empty_a + 8 * stage);    // ring stage reusable once these MMAs retire
+          if (++stage == TC_ASTAGES) {
+            stage = 0;
+            phase ^= 1;
           }
         }
-        tc_commit(empty_a + 8 * stage);      // ring stage reusable once these MMAs retire
         tc_commit(tmem_full + 8 * acc);      // accumulator ready for the epilogue
         bool last_of_m = (t + 1 == t1) || ((t + 1) / n_nblk != m);
         if (last_of_m) tc_commit(empty_b);
-        if (++stage == TC_ASTAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -191,12 +206,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                        : "memory");
         }
+#if BLEND_DIRECT_STORE
+        // experiment: coalesced st.global.cs from the staged chunk instead of a TMA store
+        __syncwarp();
+        {
+          int col0 = n * TC_BN + (2 * half + cc) * 32;
+          int row0 = m * TC_BM + 32 * q;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            int rr = it * 4 + (lane >> 3), ch16 = lane & 7;
+            uint32_t addr = stage_base + rr * 128 + ((ch16 ^ (rr & 7)) << 4);
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+            if (row0 + rr < n_rows && BLEND_DIRECT_STORE != 2) __stcs(reinterpret_cast<float4 *>(out + (size_t)(row0 + rr) * out_pitch + col0) + ch16, v);
+          }
+        }
+        __syncwarp();
+#else
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
           tma_store_2d(&map_c, stage_base, n * TC_BN + (2 * half + cc) * 32, m * TC_BM + 32 * q);
           tma_commit();
         }
+#endif
       }
       if (++acc == 2) {
         acc = 0;
@@ -332,7 +365,7 @@ int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed, bo
   int grid = total < c->num_sms ? total : c->num_sms;
   const CUtensorMap *md = (const CUtensorMap *)(act ? c->map_d_act : c->map_d);
   LAUNCH(c, act ? "blend_fwd_tc_active" : "blend_fwd_tc", grid, TC_THREADS, SM_TOTAL, k_blend_tc, map_x, *md, map_c, n_mblk,
-         n_nblk, c->tc_inv_scale);
+         n_nblk, c->tc_inv_scale, v_posed, pitch, B);
   return 0;
 }
 
