@@ -17,52 +17,53 @@
 //   warp 0   TMA producer (x16 tile per sample block, Dt16 tiles through a 2-deep ring)
 //   warp 1   tcgen05.mma issuer (one lane), TMEM allocator
 //   warps 2-9  epilogue: tcgen05.ld -> scale -> swizzled smem staging -> TMA store
-// Tile 128 (samples) x 128 (vertex coordinates); two TMEM accumulator stages so the MMAs of
-// tile i+1 overlap the epilogue of tile i.  The kernel is bound by its fp32 output stream.
+// Tile 256 (samples, two MMA sub-blocks) x 128 (vertex coordinates); two TMEM accumulator
+// stages so the MMAs of tile i+1 overlap the epilogue of tile i.  The kernel is bound by its
+// fp32 output stream and the L2 operand traffic that feeds it.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
 
 #include "smplb_internal.h"
 
-#define TC_BM 128
+#define TC_BM 128            // MMA M (one sub-block of samples)
+#define TC_MSUB 2            // sub-blocks per output tile: a CTA tile is 256 samples x 128 coordinates
 #define TC_BN 128
-#define TC_KP 256          // padded K
-#define TC_KB 64           // K elements per 128-byte swizzle atom
+#define TC_KP 256            // padded K
+#define TC_KB 64             // K elements per 128-byte swizzle atom
 #define TC_NKB (TC_KP / TC_KB)
-#define TC_ASTAGES 4         // ring stages of TC_SKB k-blocks each (32 KB): loads run 2 tiles ahead in half-tile steps
-#define TC_SKB 2
+#define TC_ASTAGES 4         // ring stages, one Dt16 k-block (16 KB) each
 #define TC_THREADS 320
 
-#define SM_B_OFF 0
-#define SM_A_OFF (64 * 1024)
-#define SM_C_OFF (192 * 1024)
-#define SM_BAR_OFF (224 * 1024)
+#define TILE_KB_BYTES (128 * 128)                       // one k-block of an operand tile: 128 rows x 128 B
+#define SM_X_OFF 0                                      // resident x16 tiles: TC_MSUB x 4 k-blocks = 128 KB
+#define SM_A_OFF (TC_MSUB * TC_NKB * TILE_KB_BYTES)     // Dt16 ring: 4 x 16 KB
+#define SM_C_OFF (SM_A_OFF + TC_ASTAGES * TILE_KB_BYTES)  // epilogue staging: 8 warps x 4 KB
+#define SM_BAR_OFF (SM_C_OFF + 8 * 4096)
 #define SM_TOTAL (SM_BAR_OFF + 128)
-#define TILE_KB_BYTES (128 * 128)   // one k-block of an operand tile: 128 rows x 128 B
 
 #include "tc_ptx.cuh"
 
-#ifndef BLEND_DIRECT_STORE
-#define BLEND_DIRECT_STORE 0
-#endif
-
 #define TC_IDESC umma_idesc_f16(TC_BM, TC_BN)
 
+// Both streaming kernels of the forward turned out to be bound by the L2 <-> SM fabric
+// (~8.3 TB/s of combined operand reads and output writes), not by HBM: with a 128-sample tile
+// every 64 KB of output costs a 64 KB Dt16 operand tile from L2.  A CTA therefore owns two
+// 128-sample sub-blocks (two resident x16 tiles, two accumulators) per Dt16 tile, halving
+// the operand traffic per output byte.
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_blend_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_d,
-               const __grid_constant__ CUtensorMap map_c, int n_mblk, int n_nblk, float inv_scale, float *__restrict__ out,
-               int out_pitch, int n_rows) {
+               const __grid_constant__ CUtensorMap map_c, int n_mblk, int n_nblk, float inv_scale) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + SM_BAR_OFF;
   // barrier slots (8 bytes each)
-  const uint32_t full_a = bar0 + 0, empty_a = bar0 + 32, full_b = bar0 + 64, empty_b = bar0 + 72;
+  const uint32_t full_a = bar0 + 0, empty_a = bar0 + 32, full_x = bar0 + 64, empty_x = bar0 + 72;
   const uint32_t tmem_full = bar0 + 80, tmem_empty = bar0 + 96;
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + SM_BAR_OFF + 120);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total = n_mblk * n_nblk;
+  const int total = n_mblk * n_nblk;          // n_mblk counts 256-sample super blocks
   const int t0 = (int)(((long long)blockIdx.x * total) / gridDim.x);
   const int t1 = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
 
@@ -75,13 +76,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(tmem_full + 8 * i, 1);
       mbar_init(tmem_empty + 8 * i, 8);   // one arrival per epilogue warp
     }
-    mbar_init(full_b, 1);
-    mbar_init(empty_b, 1);
+    mbar_init(full_x, 1);
+    mbar_init(empty_x, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_BAR_OFF + 120),
-                 "n"(2 * TC_BN)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_BAR_OFF + 120), "n"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -94,25 +94,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // =========================== TMA producer ===========================
     if (lane == 0) {
       // tiles are ordered sample-block major: consecutive tiles of a CTA write adjacent 512 B
-      // column ranges of the same 128 v_posed rows.  The x16 tile is loaded once per sample
-      // block; Dt16 tiles (10.6 MB in total, L2-resident) stream through a 2-deep ring.
+      // column ranges of the same 256 v_posed rows.  The two x16 tiles are loaded once per
+      // sample block; Dt16 k-blocks (10.6 MB in total, L2-resident) stream through the ring.
       int cur_m = -1, x_loads = 0, stage = 0, phase = 0;
       for (int t = t0; t < t1; ++t) {
         int m = t / n_nblk, n = t % n_nblk;
         if (m != cur_m) {
-          if (x_loads > 0) mbar_wait(empty_b, (x_loads - 1) & 1);   // MMAs of the previous sample block retired
-          mbar_expect_tx(full_b, TC_NKB * TILE_KB_BYTES);
-          for (int kb = 0; kb < TC_NKB; ++kb)
-            tma_load_2d(sbase + SM_B_OFF + kb * TILE_KB_BYTES, &map_x, kb * TC_KB, m * TC_BM, full_b);
+          if (x_loads > 0) mbar_wait(empty_x, (x_loads - 1) & 1);   // MMAs of the previous sample block retired
+          mbar_expect_tx(full_x, TC_MSUB * TC_NKB * TILE_KB_BYTES);
+          for (int u = 0; u < TC_MSUB; ++u)
+            for (int kb = 0; kb < TC_NKB; ++kb)
+              tma_load_2d(sbase + SM_X_OFF + (u * TC_NKB + kb) * TILE_KB_BYTES, &map_x, kb * TC_KB,
+                          (m * TC_MSUB + u) * TC_BM, full_x);
           ++x_loads;
           cur_m = m;
         }
-        for (int hs = 0; hs < TC_NKB / TC_SKB; ++hs) {
+        for (int kb = 0; kb < TC_NKB; ++kb) {
           mbar_wait(empty_a + 8 * stage, phase ^ 1);
-          mbar_expect_tx(full_a + 8 * stage, TC_SKB * TILE_KB_BYTES);
-          for (int kk = 0; kk < TC_SKB; ++kk)
-            tma_load_2d(sbase + SM_A_OFF + stage * (TC_SKB * TILE_KB_BYTES) + kk * TILE_KB_BYTES, &map_d,
-                        (hs * TC_SKB + kk) * TC_KB, n * TC_BN, full_a + 8 * stage);
+          mbar_expect_tx(full_a + 8 * stage, TILE_KB_BYTES);
+          tma_load_2d(sbase + SM_A_OFF + stage * TILE_KB_BYTES, &map_d, kb * TC_KB, n * TC_BN, full_a + 8 * stage);
           if (++stage == TC_ASTAGES) {
             stage = 0;
             phase ^= 1;
@@ -127,30 +127,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int t = t0; t < t1; ++t) {
         int m = t / n_nblk;
         if (m != cur_m) {
-          mbar_wait(full_b, x_loads & 1);
+          mbar_wait(full_x, x_loads & 1);
           ++x_loads;
           cur_m = m;
         }
-        mbar_wait(tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
+        mbar_wait(tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator pair
         tc_fence_after();
-        uint32_t d_tmem = tmem_base + acc * TC_BN;
 #pragma unroll
-        for (int hs = 0; hs < TC_NKB / TC_SKB; ++hs) {
-          mbar_wait(full_a + 8 * stage, phase);           // this half of the Dt16 tile landed
+        for (int kb = 0; kb < TC_NKB; ++kb) {
+          mbar_wait(full_a + 8 * stage, phase);           // Dt16 k-block landed
           tc_fence_after();
+          uint32_t b_addr = sbase + SM_A_OFF + stage * TILE_KB_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < TC_SKB; ++kk) {
-            int kb = hs * TC_SKB + kk;
-            // MMA "A" (M = samples) is the resident x16 tile, "B" (N = coordinates) the ring stage
-            uint32_t a_addr = sbase + SM_B_OFF + kb * TILE_KB_BYTES;
-            uint32_t b_addr = sbase + SM_A_OFF + stage * (TC_SKB * TILE_KB_BYTES) + kk * TILE_KB_BYTES;
+          for (int u = 0; u < TC_MSUB; ++u) {
+            // MMA "A" (M = samples) is a resident x16 tile, "B" (N = coordinates) the ring stage
+            uint32_t a_addr = sbase + SM_X_OFF + (u * TC_NKB + kb) * TILE_KB_BYTES;
+            uint32_t d_tmem = tmem_base + (acc * TC_MSUB + u) * TC_BN;
 #pragma unroll
-            for (int k = 0; k < TC_KB / 16; ++k) {
-              // advance 16 fp16 = 32 B inside the 128 B swizzle atom
-              uint64_t ad = umma_desc_sw128(a_addr + k * 32);
-              uint64_t bd = umma_desc_sw128(b_addr + k * 32);
-              tc_mma_f16(d_tmem, ad, bd, TC_IDESC, (kb | k) != 0);
-            }
+            for (int k = 0; k < TC_KB / 16; ++k)   // advance 16 fp16 = 32 B inside the 128 B swizzle atom
+              tc_mma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), TC_IDESC,
+                         (kb | k) != 0);
           }
           tc_commit(empty_a + 8 * stage);    // ring stage reusable once these MMAs retire
           if (++stage == TC_ASTAGES) {
@@ -158,9 +154,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             phase ^= 1;
           }
         }
-        tc_commit(tmem_full + 8 * acc);      // accumulator ready for the epilogue
+        tc_commit(tmem_full + 8 * acc);      // accumulators ready for the epilogue
         bool last_of_m = (t + 1 == t1) || ((t + 1) / n_nblk != m);
-        if (last_of_m) tc_commit(empty_b);
+        if (last_of_m) tc_commit(empty_x);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -169,67 +165,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else {
     // =========================== epilogue (warps 2..9) ===========================
-    // Two warps per TMEM lane quarter, each taking two of the tile's four 32-column chunks, so
-    // TMEM loads, shared-memory staging and TMA stores of different chunks overlap.
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;             // column chunks {2*half, 2*half+1}
+    // Warps 2-5 drain the first sub-block's accumulator, warps 6-9 the second; within each, warp
+    // (id % 4) owns TMEM lanes 32*(id%4).. (the only lanes it may access).
+    const int q = warp & 3;
+    const int u = (warp - 2) >> 2;
     const uint32_t stage_base = sbase + SM_C_OFF + (warp - 2) * 4096;
     int acc = 0, acc_phase = 0;
     for (int t = t0; t < t1; ++t) {
       int m = t / n_nblk, n = t % n_nblk;
       mbar_wait(tmem_full + 8 * acc, acc_phase);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + acc * TC_BN + (2 * half) * 32;
-      tc_ld_32x32(tbase, r0);
-      tc_ld_32x32(tbase + 32, r1);
-      tc_wait_ld();
-      // both chunks are in registers: hand the accumulator back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const uint32_t *r = cc == 0 ? r0 : r1;
-        // the staging buffer was read by this warp's previous TMA store
-        if (lane == 0) tma_wait_read<0>();
-        __syncwarp();
-        uint32_t row_addr = stage_base + lane * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 v;
-          v.x = __uint_as_float(r[4 * j + 0]) * inv_scale;
-          v.y = __uint_as_float(r[4 * j + 1]) * inv_scale;
-          v.z = __uint_as_float(r[4 * j + 2]) * inv_scale;
-          v.w = __uint_as_float(r[4 * j + 3]) * inv_scale;
-          uint32_t addr = row_addr + ((j ^ (lane & 7)) << 4);   // SWIZZLE_128B: 16B chunk ^= row % 8
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                       : "memory");
+      const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + (acc * TC_MSUB + u) * TC_BN;
+#pragma unroll 1
+      for (int pair = 0; pair < 2; ++pair) {
+        uint32_t r0[32], r1[32];
+        tc_ld_32x32(tbase + pair * 64, r0);
+        tc_ld_32x32(tbase + pair * 64 + 32, r1);
+        tc_wait_ld();
+        if (pair == 1) {
+          // all four chunks of this warp's rows are in registers: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
         }
-#if BLEND_DIRECT_STORE
-        // experiment: coalesced st.global.cs from the staged chunk instead of a TMA store
-        __syncwarp();
-        {
-          int col0 = n * TC_BN + (2 * half + cc) * 32;
-          int row0 = m * TC_BM + 32 * q;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            int rr = it * 4 + (lane >> 3), ch16 = lane & 7;
-            uint32_t addr = stage_base + rr * 128 + ((ch16 ^ (rr & 7)) << 4);
+        for (int cc = 0; cc < 2; ++cc) {
+          const uint32_t *r = cc == 0 ? r0 : r1;
+          if (lane == 0) tma_wait_read<0>();          // the staging buffer was read by this warp's previous store
+          __syncwarp();
+          uint32_t row_addr = stage_base + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
             float4 v;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-            if (row0 + rr < n_rows && BLEND_DIRECT_STORE != 2) __stcs(reinterpret_cast<float4 *>(out + (size_t)(row0 + rr) * out_pitch + col0) + ch16, v);
+            v.x = __uint_as_float(r[4 * j + 0]) * inv_scale;
+            v.y = __uint_as_float(r[4 * j + 1]) * inv_scale;
+            v.z = __uint_as_float(r[4 * j + 2]) * inv_scale;
+            v.w = __uint_as_float(r[4 * j + 3]) * inv_scale;
+            uint32_t addr = row_addr + ((j ^ (lane & 7)) << 4);   // SWIZZLE_128B: 16B chunk ^= row % 8
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                         : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_c, stage_base, n * TC_BN + (pair * 2 + cc) * 32, (m * TC_MSUB + u) * TC_BM + 32 * q);
+            tma_commit();
           }
         }
-        __syncwarp();
-#else
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&map_c, stage_base, n * TC_BN + (2 * half + cc) * 32, m * TC_BM + 32 * q);
-          tma_commit();
-        }
-#endif
       }
       if (++acc == 2) {
         acc = 0;
@@ -242,7 +224,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -360,12 +342,12 @@ int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed, bo
   TRY(make_map_2d(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)x16, TC_KP, (uint64_t)B, TC_KP * 2, TC_KB, TC_BM));
   TRY(make_map_2d(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)v_posed, (uint64_t)pitch, (uint64_t)B,
                   (uint64_t)pitch * 4, 32, 32));
-  int n_mblk = cdiv(B, TC_BM), n_nblk = pitch / TC_BN;
+  int n_mblk = cdiv(B, TC_BM * TC_MSUB), n_nblk = pitch / TC_BN;
   int total = n_mblk * n_nblk;
   int grid = total < c->num_sms ? total : c->num_sms;
   const CUtensorMap *md = (const CUtensorMap *)(act ? c->map_d_act : c->map_d);
   LAUNCH(c, act ? "blend_fwd_tc_active" : "blend_fwd_tc", grid, TC_THREADS, SM_TOTAL, k_blend_tc, map_x, *md, map_c, n_mblk,
-         n_nblk, c->tc_inv_scale, v_posed, pitch, B);
+         n_nblk, c->tc_inv_scale);
   return 0;
 }
 
