@@ -62,6 +62,10 @@ SIGNATURES = {
     "smplb_gradient_penalty": [_P, _I, _P, _P, _P, _P, _P, _P, _I],
     "smplb_gradient_penalty_from_sums": [_P, _L, _P, _P, _I],
     "smplb_gradient_penalty_backward": [_P, _I, _L, _P, _P, _P, _P, _P, _I],
+    "smplb_silhouette_csr": [_P, _I, _I, _I, _P, _P, _I, _P, _I],
+    "smplb_kcs": [_P, _I, _I, _P, _P, _P, _I],
+    "smplb_kcs_backward": [_P, _I, _I, _P, _P, _P, _P, _I],
+    "smplb_interpolate": [_P, _I, _I, _P, _P, _P, _P, _I],
     "smplb_step": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I],
     "smplb_comm_unique_id": [_P],
     "smplb_comm_init": [_P, _I, _I, _P],

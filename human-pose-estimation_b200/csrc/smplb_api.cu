@@ -984,6 +984,63 @@ extern "C" int smplb_gradient_penalty_backward(smplb_ctx *c, int M, int64_t M_to
   return st.finish();
 }
 
+// ------------------------------------------------------------------- SURVEY section 8f rows
+extern "C" int smplb_silhouette_csr(smplb_ctx *c, int B, int H, int W, const float *seg, float *points_xy, int cap,
+                                    int32_t *offsets, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(B < 1 || H < 1 || W < 1 || cap < 0 || !seg || !offsets || (cap > 0 && !points_xy), SMPLB_EINVAL,
+         "B, H, W >= 1 and non-null seg, offsets (and points_xy when cap > 0) required");
+  TRY(ensure_ws(c, B));
+  Stager st(c, mem);
+  const float *ds = st.in(seg, (size_t)B * H * W);
+  float *dp = st.out(points_xy, (size_t)cap * 2);
+  int32_t *dof = st.out(offsets, (size_t)B + 1);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  if (!dp) dp = c->ws_scal;
+  TRY(launch_silhouette_csr(c, B, H, W, ds, dp, cap, dof, c->ws_cnt));
+  return st.finish();
+}
+
+extern "C" int smplb_kcs(smplb_ctx *c, int N, int K, const float *joints, const float *Cm, float *kcs, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(N < 1 || K < 14 || !joints || !Cm || !kcs, SMPLB_EINVAL, "N >= 1, K >= 14 and non-null pointers required");
+  Stager st(c, mem);
+  const float *dj = st.in(joints, (size_t)N * K * 3), *dc = st.in(Cm, (size_t)14 * 13);
+  float *dk = st.out(kcs, (size_t)N * 169);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_kcs(c, N, K, dj, dc, dk));
+  return st.finish();
+}
+
+extern "C" int smplb_kcs_backward(smplb_ctx *c, int N, int K, const float *joints, const float *Cm, const float *d_kcs,
+                                  float *d_joints, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(N < 1 || K < 14 || !joints || !Cm || !d_kcs || !d_joints, SMPLB_EINVAL,
+         "N >= 1, K >= 14 and non-null pointers required");
+  Stager st(c, mem);
+  const float *dj = st.in(joints, (size_t)N * K * 3), *dc = st.in(Cm, (size_t)14 * 13), *dk = st.in(d_kcs, (size_t)N * 169);
+  float *o = st.out(d_joints, (size_t)N * K * 3);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_kcs_bwd(c, N, K, dj, dc, dk, o));
+  return st.finish();
+}
+
+extern "C" int smplb_interpolate(smplb_ctx *c, int N, int row, const float *fake, const float *real, const float *alpha,
+                                 float *out, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(N < 1 || row < 1 || !fake || !real || !alpha || !out, SMPLB_EINVAL, "N, row >= 1 and non-null pointers required");
+  Stager st(c, mem);
+  const float *df = st.in(fake, (size_t)N * row), *dr = st.in(real, (size_t)N * row), *da = st.in(alpha, (size_t)N);
+  float *o = st.out(out, (size_t)N * row);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_interp(c, (size_t)N * row, row, df, dr, da, o));
+  return st.finish();
+}
+
 // ---------------------------------------------------------------------------------- fused step
 extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *theta, const float *cam,
                           const float *kp_gt, const float *points_xy, const int32_t *offsets, int P, float w_kp,

@@ -248,6 +248,12 @@ int launch_proj(smplb_ctx *c, int B, int N, const float *X, const float *cam, in
 int launch_proj_bwd(smplb_ctx *c, int B, int N, const float *X, const float *cam, const float *d_out, int pixel,
                     float im_w, float im_h, float gscale, const long long *den, int accumulate_cam, float *d_X,
                     float *d_cam);
+// k_extra.cu
+int launch_silhouette_csr(smplb_ctx *c, int B, int H, int W, const float *seg, float *points, int cap, int *offsets,
+                          int *counts_scratch);
+int launch_kcs(smplb_ctx *c, int N, int K, const float *joints, const float *Cm, float *kcs);
+int launch_kcs_bwd(smplb_ctx *c, int N, int K, const float *joints, const float *Cm, const float *dK, float *d_joints);
+int launch_interp(smplb_ctx *c, size_t total, int row, const float *fake, const float *real, const float *alpha, float *out);
 // k_loss.cu
 int launch_kp_loss(smplb_ctx *c, int B, int K, const float *kp_gt, const float *kp_pred, float *dkp, float *part,
                    int *cnt);

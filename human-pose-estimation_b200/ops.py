@@ -70,6 +70,22 @@ def silhouette_csr(silhouette_gt, batch_size):
     return pts, offsets
 
 
+def silhouette_csr_device(seg, cap=None):
+    """On-device version of silhouette_csr for a dense mask: seg [B,H,W] or [B,H,W,1] (numpy or
+    DeviceArray) -> (points_xy [cap,2], offsets [B+1]) of the same kind.  `cap` bounds the
+    number of points kept (default B*H*W)."""
+    ctx = _ctx_for(seg)
+    a = runtime.Args(ctx)
+    shp = tuple(seg.shape)
+    B, H, W = int(shp[0]), int(shp[1]), int(shp[2])
+    cap = B * H * W if cap is None else int(cap)
+    ps = a.inp(seg, (B, H, W))
+    pts, pp = a.out((cap, 2))
+    offs, po = a.out((B + 1,), dtype=np.int32)
+    check(lib().smplb_silhouette_csr(ctx.handle, B, H, W, ps, pp, cap, po, a.mem))
+    return pts, offs
+
+
 def _mesh_call(ctx, pts, offsets, sil_pred, want_grad, want_idx):
     a = runtime.Args(ctx)
     N, V = int(sil_pred.shape[0]), int(sil_pred.shape[1])

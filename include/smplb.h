@@ -190,6 +190,23 @@ int smplb_gradient_penalty_from_sums(smplb_ctx *ctx, int64_t M_total, const floa
 int smplb_gradient_penalty_backward(smplb_ctx *ctx, int M, int64_t M_total, const float *col_sums, float *d_g0,
                                     float *d_g1, float *d_g2, float *d_g3, int mem);
 
+/* ---- neighbours of the path ------------------------------------------- *
+ * tf.cast(tf.where(seg > 0)[:, :3], float32) (src/trainer.py:291,443) as an on-device ordered
+ * compaction into the CSR form smplb_mesh_reproj_loss / smplb_step take: seg [B,H,W] (NHWC with
+ * C = 1), points_xy [cap,2] receives (x = col, y = row) in row-major order per image, offsets
+ * [B+1]; points beyond cap are dropped (offsets still report the true counts).          */
+int smplb_silhouette_csr(smplb_ctx *ctx, int B, int H, int W, const float *seg, float *points_xy, int cap,
+                         int32_t *offsets, int mem);
+/* get_kcs(joints, C_matrix) (src/models.py:123-139): joints [N,K,3] (first 14 used), C [14,13]
+ * -> kcs [N,13,13]; and its backward d_kcs [N,13,13] -> d_joints [N,K,3].             */
+int smplb_kcs(smplb_ctx *ctx, int N, int K, const float *joints, const float *C, float *kcs, int mem);
+int smplb_kcs_backward(smplb_ctx *ctx, int N, int K, const float *joints, const float *C, const float *d_kcs,
+                       float *d_joints, int mem);
+/* Critic-input interpolation fake + alpha * (real - fake), alpha [N] per row of length `row`
+ * (src/trainer.py:551-557).                                                           */
+int smplb_interpolate(smplb_ctx *ctx, int N, int row, const float *fake, const float *real, const float *alpha,
+                      float *out, int mem);
+
 /* ---- the benchmarked fused call: what one generator stage of Trainer.train_step does
  * with SMPL, projection and losses (src/trainer.py:404-450) plus its backward
  * (src/trainer.py:502).

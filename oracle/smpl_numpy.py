@@ -365,3 +365,32 @@ def gradient_penalty_backward(gradients):
         n = np.sqrt(np.sum(m * m))
         out.append(np.broadcast_to(-2.0 * (1.0 - n) * m / (n * g.shape[0]), g.shape).astype(g.dtype))
     return out
+
+
+# --------------------------------------------------------------------------
+# src/models.py (SURVEY.md section 8f neighbours of the path)
+# --------------------------------------------------------------------------
+def precompute_C_matrix(num_joints=14):
+    """models.py:97-118."""
+    num_bones = num_joints - 1
+    C = np.zeros([num_joints, num_bones])
+    C[np.arange(num_bones), np.arange(num_bones)] = 1
+    C[np.array([1, 2, 8, 9, 3, 4, 7, 8, 12, 12, 9, 10, 13]), np.arange(num_bones)] = -1
+    return C
+
+
+def get_kcs(joints, C_matrix, num_joints=14):
+    """models.py:123-139 -- B = joints[:, :14]^T C per sample, KCS = B^T B (the reference
+    forms an N x 13 x 13 x N tensor and takes its diagonal; same numbers)."""
+    j = joints[:, :num_joints, :]
+    Bm = np.einsum("njc,ja->nca", j, C_matrix)
+    return np.einsum("nca,ncb->nab", Bm, Bm)
+
+
+def get_kcs_backward(joints, C_matrix, d_kcs, num_joints=14):
+    j = joints[:, :num_joints, :]
+    Bm = np.einsum("njc,ja->nca", j, C_matrix)
+    dB = np.einsum("nab,ncb->nca", d_kcs + d_kcs.transpose(0, 2, 1), Bm)
+    out = np.zeros_like(joints)
+    out[:, :num_joints, :] = np.einsum("ja,nca->njc", C_matrix, dB)
+    return out

@@ -239,6 +239,26 @@ def print(*a, **k):
     builtins.print(*[v.item() if isinstance(v, torch.Tensor) and v.numel() == 1 else v for v in a])
 
 
+def tensordot(a, b, axes):
+    return torch.tensordot(_t(a), _t(b), dims=axes).as_subclass(Tensor)
+
+
+def transpose(x, perm=None):
+    x = _t(x)
+    if perm is None:
+        perm = list(reversed(range(x.dim())))
+    return x.permute(*perm)
+
+
+class _Linalg:
+    @staticmethod
+    def diag_part(x):
+        return torch.diagonal(_t(x), dim1=-2, dim2=-1)
+
+
+linalg = _Linalg()
+
+
 class _Math:
     @staticmethod
     def divide(a, b):

@@ -431,3 +431,30 @@ def test_mesh_grid_search_equals_brute_force():
     # and both agree with the oracle's value
     lo = onp.mesh_reprojection_loss(pts3.astype(np.float64), sp.astype(np.float64), B)
     assert abs(l1[0] - lo) < TOL * lo
+
+
+def test_section_8f_rows():
+    """Neighbours of the path: on-device silhouette extraction, KCS forward/backward,
+    critic-input interpolation."""
+    from hpe_b200 import models
+    B = 5
+    seg = synthetic.make_silhouettes(B, seed=23, a_range=(8, 20), b_range=(12, 40))
+    pts_h, offs_h = ops.silhouette_csr(synthetic.silhouette_points(seg), B)
+    pts_d, offs_d = ops.silhouette_csr_device(seg)
+    assert np.array_equal(offs_d, offs_h)                           # integer work: bit-exact
+    assert np.array_equal(pts_d[:offs_h[-1]], pts_h)                # same points, same (row-major) order
+    pts_c, offs_c = ops.silhouette_csr_device(seg, cap=100)         # capacity-limited: true counts, truncated list
+    assert np.array_equal(offs_c, offs_h) and np.array_equal(pts_c, pts_h[:100])
+    rng = np.random.default_rng(5)
+    joints = rng.normal(size=(9, 19, 3)).astype(np.float32)
+    C = models.precompute_C_matrix()
+    assert np.array_equal(C, onp.precompute_C_matrix().astype(np.float32))
+    k = models.get_kcs(joints, C)
+    assert k.shape == (9, 13, 13) and rel_err(k, onp.get_kcs(joints.astype(np.float64), C.astype(np.float64))) < 1e-5
+    up = rng.normal(size=(9, 13, 13)).astype(np.float32)
+    dj = models.get_kcs_backward(joints, C, up)
+    dj_o = onp.get_kcs_backward(joints.astype(np.float64), C.astype(np.float64), up.astype(np.float64))
+    assert rel_err(dj, dj_o) < 1e-5 and not dj[:, 14:].any()
+    fake, real = rng.normal(size=(9, 23, 3, 3)).astype(np.float32), rng.normal(size=(9, 23, 3, 3)).astype(np.float32)
+    alpha = rng.uniform(size=9).astype(np.float32)
+    assert rel_err(models.interpolate(fake, real, alpha), fake + alpha[:, None, None, None] * (real - fake)) < 1e-6

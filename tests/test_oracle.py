@@ -148,3 +148,30 @@ def test_oracle_matches_live_reference(small_model):
     assert rel_err(onp.batch_rodrigues(inp["theta"].reshape(-1, 3)), ref.np(ref.batch_lbs.batch_rodrigues(th))) < 1e-14
     assert rel_err(onp.batch_skew(inp["theta"].reshape(-1, 3)), ref.np(ref.batch_lbs.batch_skew(th))) < 1e-14
     assert rel_err(onp.batch_lrotmin(inp["theta"]), ref.np(ref.batch_lbs.batch_lrotmin(ref.tensor(inp["theta"])))) < 1e-14
+
+
+@pytest.mark.skipif(not run_reference.available(), reason="reference checkout not mounted (GPU box)")
+def test_kcs_oracle_matches_reference_source():
+    """get_kcs / precompute_C_matrix of src/models.py executed from the reference's own source
+    text (the module itself imports keras, so the two functions are lifted with ast)."""
+    import ast
+    import os
+    import warnings
+    warnings.filterwarnings("ignore")
+    ref = run_reference.Reference(float64=True)
+    src = open(os.path.join(run_reference.REFERENCE_ROOT, "src", "models.py")).read()
+    tree = ast.parse(src)
+    ns = {"tf": ref.tf, "np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("get_kcs", "precompute_C_matrix"):
+            exec(compile(ast.Module([node], []), "models.py", "exec"), ns)
+    C_ref = ref.np(ns["precompute_C_matrix"]())
+    assert np.array_equal(C_ref, onp.precompute_C_matrix())
+    rng = np.random.default_rng(4)
+    joints = rng.normal(size=(5, 19, 3))
+    jt = ref.tensor(joints, True)
+    k_ref = ns["get_kcs"](jt, ref.tf.constant(C_ref, ref.dtype))
+    assert rel_err(onp.get_kcs(joints, C_ref), ref.np(k_ref)) < 1e-13
+    up = rng.normal(size=(5, 13, 13))
+    g = ref.torch.autograd.grad((k_ref * ref.tensor(up)).sum(), [jt])[0].numpy()
+    assert rel_err(onp.get_kcs_backward(joints, C_ref, up), g) < 1e-12
