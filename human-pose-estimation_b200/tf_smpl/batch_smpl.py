@@ -91,6 +91,17 @@ class SMPL(object):
             return verts, joints, Rs
         return joints
 
+    def forward_joints_rotations(self, beta, theta):
+        """joints and Rs without materialising verts (what the critic's "real" stream and the
+        mocap preprocessing of data_loader.py:139-143 consume)."""
+        a = runtime.Args(self.ctx)
+        N = int(beta.shape[0])
+        pb, pt = a.inp(beta, (N, self.num_betas)), a.inp(theta, (N, 72))
+        joints, pj = a.out((N, self.num_keypoints, 3))
+        Rs, pR = a.out((N, 24, 3, 3))
+        check(lib().smplb_smpl_forward(self.ctx.handle, N, pb, pt, None, pj, pR, None, a.mem))
+        return joints, Rs
+
     # -- backward (TF autodiff in the reference, src/trainer.py:383,502) ----
     def backward(self, d_verts=None, d_joints=None, d_Rs=None, batch=None):
         """Gradients of the last call w.r.t. (beta, theta) for upstream gradients on

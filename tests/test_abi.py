@@ -52,6 +52,17 @@ def test_product_never_imports_oracle():
                 assert "import torch" not in txt, "%s imports torch" % f
 
 
+def test_tf_adapter_is_import_guarded():
+    from hpe_b200 import tf_adapter
+    try:
+        import tensorflow  # noqa: F401
+        pytest.skip("TensorFlow is installed")
+    except ImportError:
+        pass
+    with pytest.raises(ImportError):
+        tf_adapter.make_tf_smpl(object())
+
+
 def test_bad_joint_type_raises():
     from hpe_b200.tf_smpl.batch_smpl import load_model_arrays
     with pytest.raises(ValueError):

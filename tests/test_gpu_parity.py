@@ -458,3 +458,18 @@ def test_section_8f_rows():
     fake, real = rng.normal(size=(9, 23, 3, 3)).astype(np.float32), rng.normal(size=(9, 23, 3, 3)).astype(np.float32)
     alpha = rng.uniform(size=9).astype(np.float32)
     assert rel_err(models.interpolate(fake, real, alpha), fake + alpha[:, None, None, None] * (real - fake)) < 1e-6
+
+
+def test_mocap_preprocessing_batched(smpl_full, full_model):
+    """data_loader.py:139-143 maps SMPL over the mocap table one pose at a time; here the table
+    is one batched call and must give what per-example calls give."""
+    from hpe_b200 import data_loader
+    inp = synthetic.make_inputs(300, seed=606)
+    joints, shape, rots = data_loader.preprocess_poses(smpl_full, inp["theta"], inp["beta"], chunk=128)
+    assert joints.shape == (300, 19, 3) and rots.shape == (300, 24, 3, 3) and shape.shape == (300, 10)
+    for i in (0, 1, 131, 299):
+        v, j, R = smpl_full(inp["beta"][i:i + 1], inp["theta"][i], get_skin=True)     # the reference's per-example call
+        assert rel_err(joints[i], j[0]) < 1e-5 and np.array_equal(rots[i], R[0])
+    o = onp.SMPL(full_model, dtype=np.float64)
+    _, j64, R64 = o(inp["beta"][:4].astype(np.float64), inp["theta"][:4].astype(np.float64), get_skin=True)
+    assert rel_err(joints[:4], j64) < TOL and rel_err(rots[:4], R64) < TOL
