@@ -11,8 +11,8 @@
 //   columns  24..47   W_hi   x   A_lo
 //   columns  48..71   W_lo   x   A_hi          (72..127 zero; 5 MMAs of K = 16 are issued)
 // T never leaves the SM: the epilogue threads (one per vertex = TMEM lane) read it with
-// tcgen05.ld, apply it to v_posed and write verts through a shared-memory transpose so both
-// global streams are fully coalesced.  The kernel is bound by those two streams.
+// tcgen05.ld, apply it to v_posed (staged by TMA) and write verts.  The kernel is bound by those
+// two streams.
 //
 // Persistent, warp-specialised: warp 0 TMA producer of the MMA operands (W16 tile per vertex
 // tile, A16 chunk per tile), warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue, warp 10 TMA
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
       for (int g2 = 0; g2 < 2; ++g2) {
         const int sg = 2 * half + g2;
         uint32_t r[48];                           // T of 4 samples: 48 fp32 columns
-#pragma unroll
-        for (int i = 0; i < 12; ++i) tc_ld_32x4(trow + sg * 48 + i * 4, r + 4 * i);
+        tc_ld_32x32(trow + sg * 48, r);
+        tc_ld_32x16(trow + sg * 48 + 32, r + 32);
         float p[4][3];
 #pragma unroll
         for (int si = 0; si < 4; ++si) {
@@ -212,30 +212,17 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
                              fmaf(__uint_as_float(T[4 * rr + 1]), p[si][1],
                                   fmaf(__uint_as_float(T[4 * rr + 2]), p[si][2], __uint_as_float(T[4 * rr + 3]))));
         }
-        // Transpose [vertex][xyz] in place: the 96 floats this warp owns per sample in the v_posed
-        // tile are reused as staging (every lane has its p in registers by now).  Float i of the
-        // warp's 96 lives at segment i / 32, lane slot i % 32: conflict-free both ways.
-        __syncwarp();
-#pragma unroll
-        for (int si = 0; si < 4; ++si) {
-          float *base = ptile + (sg * 4 + si) * ST_VT;
-#pragma unroll
-          for (int rr = 0; rr < 3; ++rr) {
-            int i = 3 * lane + rr;
-            base[(i >> 5) * (ST_S * ST_VT) + (i & 31)] = o[si][rr];
-          }
-        }
-        __syncwarp();
+        // verts[b][v][xyz]: three strided scalar stores per sample.  The same LSU wavefronts as a
+        // shared-memory transpose followed by coalesced stores, with a third of the instructions
+        // (measured 134 -> 126 us); L2 merges the partial sectors.
 #pragma unroll
         for (int si = 0; si < 4; ++si) {
           int b = ch * ST_S + sg * 4 + si;
-          if (b >= B) continue;                   // warp-uniform
-          const float *base = ptile + (sg * 4 + si) * ST_VT + lane;
-          float *dst = verts + ((size_t)b * V + v0) * 3 + lane;
-          float x0 = base[0], x1 = base[ST_S * ST_VT], x2 = base[2 * ST_S * ST_VT];
-          if (lane < nflt) __stcs(dst, x0);
-          if (lane + 32 < nflt) __stcs(dst + 32, x1);
-          if (lane + 64 < nflt) __stcs(dst + 64, x2);
+          if (b >= B || 3 * lane >= nflt) continue;
+          float *dst = verts + ((size_t)b * V + v0 + lane) * 3;
+          __stcs(dst, o[si][0]);
+          __stcs(dst + 1, o[si][1]);
+          __stcs(dst + 2, o[si][2]);
         }
       }
       __syncwarp();
