@@ -27,7 +27,7 @@
 #include "smplb_internal.h"
 
 #define TC_BM 128            // MMA M (one sub-block of samples)
-#define TC_MSUB 2            // sub-blocks per output tile: a CTA tile is 256 samples x 128 coordinates
+#define TC_MSUB 1            // sub-blocks per output tile: a CTA tile is 256 samples x 128 coordinates
 #define TC_BN 128
 #define TC_KP 256            // padded K
 #define TC_KB 64             // K elements per 128-byte swizzle atom
@@ -165,25 +165,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else {
     // =========================== epilogue (warps 2..9) ===========================
-    // Warps 2-5 drain the first sub-block's accumulator, warps 6-9 the second; within each, warp
-    // (id % 4) owns TMEM lanes 32*(id%4).. (the only lanes it may access).
+    // Warp (id % 4) owns TMEM lanes 32*(id%4).. (the only lanes it may access).  With one
+    // sub-block the two warps of a lane quarter split the tile's four 32-column chunks; with two
+    // sub-blocks each takes one sub-block.
     const int q = warp & 3;
-    const int u = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;
+    const int u = TC_MSUB == 2 ? half : 0;
+    const int chunk0 = TC_MSUB == 2 ? 0 : 2 * half;
+    constexpr int NPAIR = TC_MSUB == 2 ? 2 : 1;     // pairs of 32-column chunks this warp drains per tile
     const uint32_t stage_base = sbase + SM_C_OFF + (warp - 2) * 4096;
     int acc = 0, acc_phase = 0;
     for (int t = t0; t < t1; ++t) {
       int m = t / n_nblk, n = t % n_nblk;
       mbar_wait(tmem_full + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + (acc * TC_MSUB + u) * TC_BN;
+      const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + (acc * TC_MSUB + u) * TC_BN + chunk0 * 32;
 #pragma unroll 1
-      for (int pair = 0; pair < 2; ++pair) {
+      for (int pair = 0; pair < NPAIR; ++pair) {
         uint32_t r0[32], r1[32];
         tc_ld_32x32(tbase + pair * 64, r0);
         tc_ld_32x32(tbase + pair * 64 + 32, r1);
         tc_wait_ld();
-        if (pair == 1) {
-          // all four chunks of this warp's rows are in registers: hand the accumulator back
+        if (pair == NPAIR - 1) {
+          // all of this warp's share of the accumulator is in registers: hand it back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&map_c, stage_base, n * TC_BN + (pair * 2 + cc) * 32, (m * TC_MSUB + u) * TC_BM + 32 * q);
+            tma_store_2d(&map_c, stage_base, n * TC_BN + (chunk0 + pair * 2 + cc) * 32, (m * TC_MSUB + u) * TC_BM + 32 * q);
             tma_commit();
           }
         }
