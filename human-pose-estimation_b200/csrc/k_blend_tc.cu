@@ -371,17 +371,17 @@ int compact_tc_init(smplb_ctx *c) {
   c->compact_ok = false;
   if (!c->tc_ok || !c->skin_tc_ok || c->n_act >= c->V || c->n_act == 0) return 0;
   CUDA_TRY(cudaMalloc((void **)&c->d_Dt16_act, (size_t)c->pitch_act * TC_KP * sizeof(__half)));
-  CUDA_TRY(cudaMalloc((void **)&c->d_W16_act, (size_t)c->Vpa * 128 * sizeof(__half)));
+  CUDA_TRY(cudaMalloc((void **)&c->d_W16_act, (size_t)c->Vpa * 64 * sizeof(__half)));
   k_gather_rows16<<<c->pitch_act, 128, 0, c->stream>>>(c->n_act, c->Vpa, c->Vp, 3, TC_KP, c->d_act_idx,
                                                       (const __half *)c->d_Dt16, (__half *)c->d_Dt16_act);
-  k_gather_rows16<<<c->Vpa, 128, 0, c->stream>>>(c->n_act, c->Vpa, c->Vp, 1, 128, c->d_act_idx,
+  k_gather_rows16<<<c->Vpa, 64, 0, c->stream>>>(c->n_act, c->Vpa, c->Vp, 1, 64, c->d_act_idx,
                                                 (const __half *)c->d_W16, (__half *)c->d_W16_act);
   c->launches += 2;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   TRY(make_map_2d((CUtensorMap *)c->map_d_act, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c->d_Dt16_act, TC_KP,
                   (uint64_t)c->pitch_act, TC_KP * 2, TC_KB, TC_BN));
-  TRY(make_map_2d((CUtensorMap *)c->map_w_act, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c->d_W16_act, 128, (uint64_t)c->Vpa,
-                  128 * 2, 64, 128));
+  TRY(make_map_2d((CUtensorMap *)c->map_w_act, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c->d_W16_act, 64, (uint64_t)c->Vpa,
+                  64 * 2, 64, 128));
   c->compact_ok = true;
   return 0;
 }

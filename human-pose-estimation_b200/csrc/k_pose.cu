@@ -219,17 +219,18 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
       for (int cc = 0; cc < 3; ++cc) Jtr[((size_t)b * NJ + j) * 3 + cc] = G[9 + cc];
     }
     if (A16) {
-      // fp16 split operand of the tcgen05 skinning GEMM (k_skin_tc.cu): row (b, e = 4r + d),
-      // columns j | 24 + j | 48 + j = A_hi | A_lo | A_hi  (pairs with W_hi | W_hi | W_lo)
-      __half *rowbase = A16 + (size_t)b * 12 * 128;
+      // fp16 split operand of the tcgen05 skinning GEMM (k_skin_tc.cu): row (b, e = 4r + d), one
+      // 64-column swizzle atom laid out in 16-column windows (see the window table there):
+      //   [A_hi 0..15] [A_hi 16..23 | A_lo 16..23] [A_lo 0..15] [0]
+      __half *rowbase = A16 + (size_t)b * 12 * 64;
+      const int col_lo = j < 16 ? 32 + j : j + 8;
 #pragma unroll
       for (int e = 0; e < 12; ++e) {
         float val = a[e];
         __half hi = __float2half_rn(val);
         __half lo = __float2half_rn(val - __half2float(hi));
-        rowbase[e * 128 + j] = hi;
-        rowbase[e * 128 + 24 + j] = lo;
-        rowbase[e * 128 + 48 + j] = hi;
+        rowbase[e * 64 + j] = hi;
+        rowbase[e * 64 + col_lo] = lo;
       }
     }
   }

@@ -7,9 +7,16 @@
 // than moving the kernel's bytes -- so T runs as a tcgen05 GEMM: M = 128 vertices (TMEM lanes),
 // N = 12 * 16 samples, K = 72 -> 80.  fp16 operands are split so the product keeps fp32-grade
 // accuracy (a single fp16/tf32 rounding of W would move vertices by ~0.5 mm, 5x the tolerance):
-//   columns   0..23   W_hi   x   A_hi
-//   columns  24..47   W_hi   x   A_lo
-//   columns  48..71   W_lo   x   A_hi          (72..127 zero; 5 MMAs of K = 16 are issued)
+//   T = W_hi x A_hi + W_hi x A_lo + W_lo x A_hi.
+// Both operands are ONE 64-column (128 B) swizzle atom per row, organised in four 16-column
+// windows so that five K = 16 MMAs, each pairing a window of W16 with a window of A16, produce
+// exactly those 72 products (16 B-aligned window starts are all the descriptor needs):
+//   window      0             1                          2              3
+//   W16     W_hi[0:16]   W_hi[16:24] W_hi[16:24]     W_lo[0:16]    W_lo[16:24] 0
+//   A16     A_hi[0:16]   A_hi[16:24] A_lo[16:24]     A_lo[0:16]    0
+//   MMAs    (W0,A0) (W1,A1) (W0,A2) (W2,A0) (W3,A1)
+// Halving the operand rows (they were two atoms) cut the L2 -> SM traffic of a tile from 80 KB
+// to 64 KB, which is what this kernel is bound by once HBM keeps up.
 // T never leaves the SM: the epilogue threads (one per vertex = TMEM lane) read it with
 // tcgen05.ld, apply it to v_posed (staged by TMA) and write verts.  The kernel is bound by those
 // two streams.
@@ -27,13 +34,12 @@
 #define ST_VT 128                 // vertices per tile (MMA M)
 #define ST_S 16                   // samples per tile
 #define ST_N (12 * ST_S)          // MMA N = 192
-#define ST_KP 128                 // padded K in shared memory (two 64-wide swizzle atoms)
+#define ST_KP 64                  // operand row: one 64-wide swizzle atom
 #define ST_ASTAGES 2
-#define ST_PSTAGES 3
+#define ST_PSTAGES 4
 #define ST_THREADS 352
-#define ST_W_BYTES (2 * ST_VT * 128)      // 32 KB: two k-blocks of 128 rows x 128 B
-#define ST_A_KB_BYTES (ST_N * 128)        // 24 KB: one k-block of the A16 chunk
-#define ST_A_BYTES (2 * ST_A_KB_BYTES)    // 48 KB
+#define ST_W_BYTES (ST_VT * 128)          // 16 KB: 128 rows x 128 B
+#define ST_A_BYTES (ST_N * 128)           // 24 KB: the A16 chunk of 16 samples
 #define ST_SM_A 0                                            // resident A16 chunk (reloaded when the sample chunk changes)
 #define ST_SM_W (ST_A_BYTES)                                 // W16 tile ring
 #define ST_P_BYTES (3 * ST_S * ST_VT * 4)                    // 24 KB: v_posed tile [xyz][16 samples][128 vertices]
@@ -96,16 +102,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
         if (ch != cur_ch) {
           if (a_loads > 0) mbar_wait(empty_w, (a_loads - 1) & 1);
           mbar_expect_tx(full_w, ST_A_BYTES);
-          for (int kb = 0; kb < 2; ++kb)
-            tma_load_2d(sbase + ST_SM_A + kb * ST_A_KB_BYTES, &map_a, kb * 64, ch * ST_N, full_w);
+          tma_load_2d(sbase + ST_SM_A, &map_a, 0, ch * ST_N, full_w);
           ++a_loads;
           cur_ch = ch;
         }
         mbar_wait(empty_a + 8 * stage, phase ^ 1);
         mbar_expect_tx(full_a + 8 * stage, ST_W_BYTES);
-        for (int kb = 0; kb < 2; ++kb)
-          tma_load_2d(sbase + ST_SM_W + stage * ST_W_BYTES + kb * (ST_VT * 128), &map_w, kb * 64, vt * ST_VT,
-                      full_a + 8 * stage);
+        tma_load_2d(sbase + ST_SM_W + stage * ST_W_BYTES, &map_w, 0, vt * ST_VT, full_a + 8 * stage);
         if (++stage == ST_ASTAGES) {
           stage = 0;
           phase ^= 1;
@@ -129,11 +132,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
         tc_fence_after();
         uint32_t d_tmem = tmem_base + acc * 256;
         uint32_t w_addr = sbase + ST_SM_W + stage * ST_W_BYTES, a_addr = sbase + ST_SM_A;
-        // K = 80: four 16-wide steps in the first swizzle atom, one in the second
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + k * 32), umma_desc_sw128(a_addr + k * 32), idesc, k != 0);
-        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + ST_VT * 128), umma_desc_sw128(a_addr + ST_A_KB_BYTES), idesc, 1);
+        // five K = 16 steps, (W window, A window) as in the table at the top
+        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 0 * 32), umma_desc_sw128(a_addr + 0 * 32), idesc, 0);
+        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 1 * 32), umma_desc_sw128(a_addr + 1 * 32), idesc, 1);
+        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 0 * 32), umma_desc_sw128(a_addr + 2 * 32), idesc, 1);
+        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 2 * 32), umma_desc_sw128(a_addr + 0 * 32), idesc, 1);
+        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 3 * 32), umma_desc_sw128(a_addr + 1 * 32), idesc, 1);
         tc_commit(empty_a + 8 * stage);
         tc_commit(tmem_full + 8 * acc);
         bool last_of_ch = (t + 1 == t1) || ((t + 1) / n_vt != ch);
@@ -245,16 +249,19 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
   }
 }
 
-// W16[v][k]: W_hi | W_hi | W_lo | 0 (row pitch 128 halves); rows >= V are zero.
+// W16[v][64]: the window layout at the top of this file; rows >= V are zero.
 __global__ void k_build_w16(int V, int Vp, const float *__restrict__ W, __half *__restrict__ W16) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Vp * 128) return;
-  int v = i / 128, k = i % 128;
+  if (i >= Vp * 64) return;
+  int v = i / 64, k = i % 64;
   float out = 0.f;
-  if (v < V && k < 72) {
-    float w = W[(size_t)v * NJ + (k % 24)];
+  if (v < V && k < 56) {
+    // joint and part (hi / lo) held by column k
+    int j = k < 24 ? k : (k < 32 ? k - 8 : (k < 48 ? k - 32 : k - 32));
+    bool lo = k >= 32;
+    float w = W[(size_t)v * NJ + j];
     float hi = __half2float(__float2half_rn(w));
-    out = (k < 48) ? hi : (w - hi);
+    out = lo ? (w - hi) : hi;
   }
   W16[i] = __float2half_rn(out);
 }
@@ -286,8 +293,8 @@ static int make_map_f16(CUtensorMap *map, void *ptr, uint64_t inner, uint64_t ou
 
 int skin_tc_init(smplb_ctx *c) {
   c->skin_tc_ok = false;
-  CUDA_TRY(cudaMalloc((void **)&c->d_W16, (size_t)c->Vp * 128 * sizeof(__half)));
-  k_build_w16<<<cdiv(c->Vp * 128, 256), 256, 0, c->stream>>>(c->V, c->Vp, c->d_W, (__half *)c->d_W16);
+  CUDA_TRY(cudaMalloc((void **)&c->d_W16, (size_t)c->Vp * 64 * sizeof(__half)));
+  k_build_w16<<<cdiv(c->Vp * 64, 256), 256, 0, c->stream>>>(c->V, c->Vp, c->d_W, (__half *)c->d_W16);
   c->launches++;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaFuncSetAttribute(k_skin_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SM_TOTAL));

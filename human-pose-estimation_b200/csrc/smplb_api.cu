@@ -214,8 +214,8 @@ static int ensure_ws(smplb_ctx *c, int B) {
     WS_ALLOC(ws_rowscale, nb);
     WS_ALLOC(ws_x16b, nb * 352);
   }
-  WS_ALLOC(ws_A16, nb * 12 * 64);   // 12 rows x 128 halves per sample; columns 72..127 stay zero
-  CUDA_TRY(cudaMemsetAsync(c->ws_A16, 0, nb * 12 * 64 * 4, c->stream));
+  WS_ALLOC(ws_A16, nb * 12 * 32);   // 12 rows x 64 halves per sample; columns 48..63 stay zero
+  CUDA_TRY(cudaMemsetAsync(c->ws_A16, 0, nb * 12 * 32 * 4, c->stream));
   WS_ALLOC(ws_Rs, nb * NJ * 9);
   WS_ALLOC(ws_J, nb * NJ * 3);
   WS_ALLOC(ws_A, nb * NJ * 12);
@@ -662,7 +662,7 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
     for (int b0 = 0; b0 < B; b0 += chunk) {
       int nb = std::min(chunk, B - b0);
       TRY(launch_blend_fwd_tc(c, nb, (const char *)c->ws_x16 + (size_t)b0 * 512, c->ws_vposed, false));
-      TRY(launch_skin_fwd_tc(c, nb, (const char *)c->ws_A16 + (size_t)b0 * 12 * 256, c->ws_vposed,
+      TRY(launch_skin_fwd_tc(c, nb, (const char *)c->ws_A16 + (size_t)b0 * 12 * 128, c->ws_vposed,
                              vout + (size_t)b0 * c->V3, false));
     }
   } else if (full) {

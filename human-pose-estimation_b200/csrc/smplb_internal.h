@@ -64,7 +64,7 @@ struct smplb_ctx {
   // compact keypoint path: the same blend / skinning kernels run on the active vertices only, so
   // joints, the keypoint loss and its backward never touch the 6890-vertex tensors
   void *d_Dt16_act = nullptr;      // [3*Vpa][256] fp16: rows of Dt16 gathered
-  void *d_W16_act = nullptr;       // [Vpa][128] fp16
+  void *d_W16_act = nullptr;       // [Vpa][64] fp16
   alignas(64) unsigned char map_d_act[128];
   alignas(64) unsigned char map_w_act[128];
   int *d_kcsr_slot = nullptr;      // kcsr_idx re-indexed to active slots
@@ -101,9 +101,9 @@ struct smplb_ctx {
   // ---- tcgen05 skinning path (k_skin_tc.cu)
   bool skin_tc_ok = false;
   int use_skin_tc = 1;         // smplb_debug_set("skin_tc", 0) selects the FP32 CUDA-core skinning kernel
-  void *d_W16 = nullptr;       // [Vp][128] fp16: W_hi | W_hi | W_lo | 0
+  void *d_W16 = nullptr;       // [Vp][64] fp16, 16-column windows (k_skin_tc.cu)
   alignas(64) unsigned char map_w[128];   // CUtensorMap of W16
-  void *ws_A16 = nullptr;      // [B*12][128] fp16: A_hi | A_lo | A_hi | 0, row (b, 4r+d)
+  void *ws_A16 = nullptr;      // [B*12][64] fp16, row (b, 4r+d), 16-column windows (k_skin_tc.cu)
   // ---- workspace, sized for max_batch (grown on demand)
   int ws_batch = 0;
   float *ws_x = nullptr;       // [B][KX]

@@ -1,0 +1,192 @@
+// Micro-benchmarks behind the fused blend+skin design:
+//   1. tcgen05.ld throughput per SM (how fast the epilogue can drain TMEM),
+//   2. tcgen05.mma issue rate at small N with the A operand in TMEM (TS mode) and in shared
+//      memory (SS mode).
+// Operand contents are whatever the memories hold: only the timing is read.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tmem_rate tmem_rate.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../human-pose-estimation_b200/csrc/tc_ptx.cuh"
+
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// mode 0: tcgen05.ld x32 from `nwarps` warps; mode 1: x16
+__global__ void __launch_bounds__(256, 1) k_ld(int iters, int mode, long long *out) {
+  __shared__ uint32_t tptr;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tptr)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tptr + ((uint32_t)(32 * (warp & 3)) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    uint32_t r[32];
+    if (mode == 0) {
+      tc_ld_32x32(tbase + ((i * 32) & 255) + (warp >> 2) * 256, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc ^= r[j];
+    } else {
+      tc_ld_32x16(tbase + ((i * 16) & 255) + (warp >> 2) * 256, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc ^= r[j];
+    }
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  if (acc == 0x12345678u) out[1000] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tptr), "n"(512) : "memory");
+  }
+}
+
+// iters MMAs of shape 128 x N x 16, A from TMEM (ts = 1) or shared memory (ts = 0)
+template <int N>
+__global__ void __launch_bounds__(128, 1) k_mma(int iters, int ts, int nacc, long long *out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tptr;
+  __shared__ __align__(8) unsigned long long bar;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;  // 1.0h
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tptr)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tptr;
+  if (warp == 0) {
+    // the whole warp runs the loop (warp-uniform operands stay in uniform registers); one elected
+    // lane issues, as CUTLASS does
+    const uint32_t sb = smem_u32(smem);
+    constexpr uint32_t idesc = umma_idesc_f16(128, N);
+    const uint64_t bd0 = umma_desc_sw128(sb + 16384);
+    const uint64_t ad0 = umma_desc_sw128(sb);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        uint32_t d = tbase + 128 + (nacc == 1 ? 0 : (u % 2) * N) + (nacc > 2 ? (u / 2 % 2) * 2 * N : 0);
+        uint64_t bdesc = bd0 + 2 * (u & 3);
+        if (elect_one()) {
+          if (ts)
+            tc_mma_f16_ts(d, tbase + u * 8, bdesc, idesc, 1);
+          else
+            tc_mma_f16(d, ad0 + 2 * (u & 3), bdesc, idesc, 1);
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) tc_commit(smem_u32(&bar));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "n"(512) : "memory");
+  }
+}
+
+template <int N>
+static void run_mma(long long *d_out, int ts, int nacc = 2) {
+  long long h[148];
+  const int iters = 4000;
+  cudaFuncSetAttribute(k_mma<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int rep = 0; rep < 2; ++rep) {
+    k_mma<N><<<148, 128, 64 * 1024>>>(iters, ts, nacc, d_out);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("mma N=%d ts=%d: %s\n", N, ts, cudaGetErrorString(e));
+      return;
+    }
+  }
+  cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+  long long mx = 0;
+  for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+  printf("mma 128x%dx16 %s nacc=%d: %.1f clk/instr (floor %d)\n", N, ts ? "TS" : "SS", nacc, (double)mx / iters, N / 2);
+}
+
+int main() {
+  long long *d_out;
+  cudaMalloc(&d_out, 2048 * sizeof(long long));
+  long long h[148];
+  for (int mode = 0; mode < 2; ++mode)
+    for (int threads = 128; threads <= 256; threads += 128) {
+      const int iters = 4000;
+      for (int rep = 0; rep < 2; ++rep) k_ld<<<148, threads>>>(iters, mode, d_out);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) {
+        printf("ld: %s\n", cudaGetErrorString(e));
+        return 1;
+      }
+      cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+      long long mx = 0;
+      for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+      double bytes = (double)iters * (threads / 32) * 32 * (mode == 0 ? 32 : 16) * 4;
+      printf("tcgen05.ld x%d, %d warps: %.1f clk/iter, %.1f B/clk/SM\n", mode == 0 ? 32 : 16, threads / 32, (double)mx / iters,
+             bytes / mx);
+    }
+  for (int nacc = 1; nacc <= 4; nacc *= 2) {
+    run_mma<16>(d_out, 1, nacc);
+    run_mma<16>(d_out, 0, nacc);
+  }
+  for (int nacc = 1; nacc <= 4; nacc *= 2) {
+    run_mma<48>(d_out, 1, nacc);
+    run_mma<48>(d_out, 0, nacc);
+  }
+  for (int nacc = 1; nacc <= 2; nacc *= 2) {
+    run_mma<96>(d_out, 1, nacc);
+    run_mma<96>(d_out, 0, nacc);
+    run_mma<192>(d_out, 1, nacc);
+    run_mma<192>(d_out, 0, nacc);
+  }
+  run_mma<128>(d_out, 0, 1);
+  run_mma<128>(d_out, 0, 2);
+  run_mma<64>(d_out, 0, 2);
+  run_mma<64>(d_out, 1, 2);
+  return 0;
+}
