@@ -407,6 +407,7 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
   if ((rc = blend_tc_init(c))) return fail(rc);
   if ((rc = skin_tc_init(c))) return fail(rc);
   if ((rc = compact_tc_init(c))) return fail(rc);
+  if ((rc = body_tc_init(c))) return fail(rc);
   if ((rc = fold_init(c))) return fail(rc);
   if ((rc = ensure_ws(c, c->max_batch))) return fail(rc);
   *out = c;
@@ -567,6 +568,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->l2_chunk = value;
     return 0;
   }
+  if (!strcmp(key, "fused")) {
+    c->use_fused = value;
+    return 0;
+  }
   if (!strcmp(key, "skin_tc")) {
     c->use_skin_tc = value;
     return 0;
@@ -623,7 +628,7 @@ static int join_verts(smplb_ctx *c) {
 
 static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float *theta, float *verts, float *joints,
                             float *Rs, float *Jtr, const float *cam, const float *kp_gt, float *kp_pred,
-                            bool need_verts) {
+                            bool need_verts, bool want_vposed = false) {
   TRY(ensure_ws(c, B));
   CUDA_TRY(cudaMemcpyAsync(c->ws_beta, beta, (size_t)B * c->NB * 4, cudaMemcpyDeviceToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->ws_theta, theta, (size_t)B * 72 * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -649,6 +654,10 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   // trip.  The dense backward rebuilds v_posed when it needs it (saved_full = false).
   int chunk = c->l2_chunk;
   bool chunked = full && tc && stc && chunk > 0 && B > chunk;
+  // One kernel for blend + skinning when nothing downstream is known to need v_posed (the dense
+  // backward rebuilds it on demand, saved_full = false); the caller can ask for the two-kernel
+  // path, which keeps v_posed, through want_vposed.
+  bool fused = full && tc && stc && c->body_tc_ok && c->use_fused && !chunked && !want_vposed;
   // the fold GEMM needs TMEM and ~160 KB of shared memory, which the persistent blend / skinning
   // CTAs would deny it: issue it before forking so only the light per-body kernels overlap them
   if (fold) TRY(launch_fold_gemm_u(c, B, c->ws_x16b));
@@ -658,7 +667,9 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
     CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
     c->cur = c->stream2;
   }
-  if (full && chunked) {
+  if (fused) {
+    TRY(launch_body_fwd_tc(c, B, c->ws_x16, c->ws_A16, vout));
+  } else if (full && chunked) {
     for (int b0 = 0; b0 < B; b0 += chunk) {
       int nb = std::min(chunk, B - b0);
       TRY(launch_blend_fwd_tc(c, nb, (const char *)c->ws_x16 + (size_t)b0 * 512, c->ws_vposed, false));
@@ -671,7 +682,7 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
     if (stc) TRY(launch_skin_fwd_tc(c, B, c->ws_A16, c->ws_vposed, vout, false));
     else TRY(launch_skin_fwd(c, B, c->ws_A, c->ws_vposed, vout));
   }
-  c->saved_full = full && !chunked;
+  c->saved_full = full && !chunked && !fused;
   if (overlap) {
     cudaError_t e1 = cudaEventRecord(c->ev_join, c->stream2);
     c->cur = c->stream;
@@ -1071,7 +1082,7 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
 
   float *jbuf = ojoints ? ojoints : c->ws_joints;
   TRY(smpl_forward_dev(c, B, dbeta, dtheta, overts, jbuf, oRs, nullptr, dcam, dkpgt, okp ? okp : c->ws_kp,
-                       overts != nullptr || have_mesh));
+                       overts != nullptr || have_mesh, /*want_vposed=*/have_mesh && bwd));
   const float *vbuf = c->saved_verts;
   bool comm = c->nccl_comm && c->nranks > 1;
   if (!have_mesh && !comm) {

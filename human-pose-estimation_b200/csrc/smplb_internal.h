@@ -104,6 +104,9 @@ struct smplb_ctx {
   void *d_W16 = nullptr;       // [Vp][64] fp16, 16-column windows (k_skin_tc.cu)
   alignas(64) unsigned char map_w[128];   // CUtensorMap of W16
   void *ws_A16 = nullptr;      // [B*12][64] fp16, row (b, 4r+d), 16-column windows (k_skin_tc.cu)
+  // ---- fused blend + skinning (k_body_tc.cu): verts without the v_posed round trip
+  bool body_tc_ok = false;
+  int use_fused = 1;           // smplb_debug_set("fused", 0) selects the two-kernel path (which saves v_posed)
   // ---- workspace, sized for max_batch (grown on demand)
   int ws_batch = 0;
   float *ws_x = nullptr;       // [B][KX]
@@ -237,6 +240,9 @@ int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long l
 int skin_tc_init(smplb_ctx *c);
 int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts, bool act);
 int compact_tc_init(smplb_ctx *c);
+// k_body_tc.cu
+int body_tc_init(smplb_ctx *c);
+int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts);
 // k_skin.cu
 int launch_skin_fwd(smplb_ctx *c, int B, const float *A, const float *v_posed, float *verts);
 int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, const float *kp_gt, float *joints,

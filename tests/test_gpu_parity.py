@@ -369,6 +369,43 @@ def test_tcgen05_skinning_matches_fp32_kernel(smpl_full):
     assert rel_err(v1, v0) < 5e-6 and rel_err(j1, j0) < 5e-6
 
 
+def test_fused_blend_skinning_matches_two_kernel_path(smpl_full, full_model):
+    """k_body_tc (blend + skinning in one kernel, v_posed stays in TMEM) against k_blend_tc +
+    k_skin_tc: the same fp16 operands and fp32 accumulation, so the two may differ only by fp32
+    summation order; and against the fp64 oracle at the stated tolerance.  Batch sizes straddle
+    the 96-sample super-tile and the 8-sample skinning tile (ragged tails)."""
+    ctx = smpl_full.ctx
+    o = onp.SMPL(full_model, dtype=np.float64)
+    for B in (1, 7, 96, 203):
+        inp = synthetic.make_inputs(B, seed=500 + B)
+        try:
+            ctx.debug_set("fused", 0)
+            v0, j0, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
+        finally:
+            ctx.debug_set("fused", 1)
+        v1, j1, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
+        assert np.isfinite(v1).all()
+        assert rel_err(v1, v0) < 2e-6, B
+        assert np.array_equal(j1, j0)
+        n = min(B, 4)
+        v, _, _ = o(inp["beta"][:n].astype(np.float64), inp["theta"][:n].astype(np.float64), get_skin=True)
+        assert rel_err(v1[:n], v) < TOL
+    # the dense backward after a fused forward rebuilds v_posed on demand
+    inp = synthetic.make_inputs(33, seed=77)
+    rng = np.random.default_rng(5)
+    d_verts = rng.standard_normal((33, full_model["v_template"].shape[0], 3)).astype(np.float32)
+    smpl_full(inp["beta"], inp["theta"], get_skin=True)
+    g1 = smpl_full.backward(d_verts=d_verts)
+    try:
+        ctx.debug_set("fused", 0)
+        smpl_full(inp["beta"], inp["theta"], get_skin=True)
+        g0 = smpl_full.backward(d_verts=d_verts)
+    finally:
+        ctx.debug_set("fused", 1)
+    for a, b in zip(g1, g0):
+        assert rel_err(a, b) < 2e-6
+
+
 def test_folded_keypoint_path_matches_per_vertex_path(smpl_full):
     """joints / kp loss / gradients from the folded formulation (G x, no vertices) against the
     per-vertex keypoint path; both are checked against the oracle elsewhere, this pins them to
