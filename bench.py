@@ -61,6 +61,8 @@ def kernel_work(name, B):
         "fold_bwd_du_dA": ("hbm", B * (1368 * 4 + 1152 + K * 12 + 1152 + 3 * 1408 * 2)),
         "blend_fwd_sgemm": ("tensor", 2.0 * B * 218 * 3 * V),
         "blend_fwd_tc": ("hbm", B * (vb + 512) + 2 * 256 * 3 * V),
+        # fused blend + skinning: verts out, x16 (512 B) + A16 (1536 B) rows in, Dt16 + W16 once
+        "body_fwd_tc": ("hbm", B * (vb + 512 + 1536) + 2 * 256 * 3 * V + 2 * 64 * V),
         "skin_fwd": ("hbm", B * (2 * vb + 1152) + 24 * 4 * V),
         "skin_fwd_tc": ("hbm", B * (2 * vb + 3072) + 2 * 128 * V),
         "skin_bwd_active": ("hbm", B * (1152 + K * 12 + 4 * 1152 + 2 * 608 * 12)),
@@ -373,7 +375,7 @@ def main():
             "config": {"workload": "SMPL fwd+bwd (beta/theta/cam) + kp reprojection loss, B=%d per GPU, V=6890, K=19, "
                                    "dense skinning weights (BASELINE config 2)" % B,
                        "global_batch": world * B, "parallelism": "batch-sharded x%d" % world, "contexts_in_flight_per_gpu": NE,
-                       "l2": "per-step working set (verts + v_posed + dp, ~1.0 GB) exceeds the 126 MB L2; inputs rotate "
+                       "l2": "per-step working set (verts, 340 MB per context) exceeds the 126 MB L2; inputs rotate "
                              "over %d buffer sets" % NSET,
                        "timing": "value: CUDA events around the K steps, which alternate between two contexts of the GPU "
                                  "(each overlaps its 6890-vertex kernels with its keypoint path on a second stream); "

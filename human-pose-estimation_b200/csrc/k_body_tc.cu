@@ -18,61 +18,72 @@
 // shapes are chosen to keep the instruction count per sample low under the 512-column TMEM
 // budget: 3 * NS (P) + TBUF * 12 * ST (T) <= 512.
 //
-// Persistent, warp-specialised: warp 0 TMA producer of the blend operands, warp 1 MMA issuer and
-// TMEM allocator, warps 2-9 epilogue (two per TMEM lane quarter, each half of a tile's samples),
-// warp 10 TMA producer of the skinning operands.
+// Persistent, warp-specialised: warp 0 TMA producer of the blend operands, warp 1 blend MMA issuer
+// and TMEM allocator, warp 2 TMA producer of the skinning operands, warp 3 skinning MMA issuer,
+// warps 4.. epilogue (one set of 8
+// warps per T stage; two warps per TMEM lane quarter, each half of a tile's samples).
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdio.h>
 
 #include "smplb_internal.h"
 #include "tc_ptx.cuh"
 
-#ifndef FB_NS
-#define FB_NS 96                      // samples per super-tile (blend MMA N)
+#ifdef FB_TIMING
+#define TCLK() clock64()
+#define TADD(acc, t) acc += clock64() - (t)
+#else
+#define TCLK() 0ll
+#define TADD(acc, t)
 #endif
-#ifndef FB_ST
-#define FB_ST 8                       // samples per skinning MMA
-#endif
-#ifndef FB_TBUF
-#define FB_TBUF 2                     // T accumulator stages
+#ifndef FB_ABLATE
+#define FB_ABLATE 0   // tuning builds: 1 = epilogue only hand-shakes (MMA-side time), 2 = no MMAs (epilogue-side time), 3 = no stores
 #endif
 #define FB_VT 128                     // vertices per super-tile (MMA M)
-#define FB_TN (12 * FB_ST)            // skinning MMA N
-#define FB_NT (FB_NS / FB_ST)         // skinning tiles per super-tile
-#define FB_DSTAGES 4
-#define FB_ASTAGES 3
-#define FB_THREADS 352
-#define FB_X_KB_BYTES (FB_NS * 128)                 // one k-block of the x16 tile
-#define FB_X_BYTES (4 * FB_X_KB_BYTES)
-#define FB_D_BYTES (FB_VT * 128)                    // one Dt16 k-block of one plane: 16 KB
-#define FB_W_BYTES (FB_VT * 128)                    // W16 tile: 16 KB
-#define FB_A_BYTES (FB_TN * 128)                    // A16 rows of ST samples
-#define FB_SM_X 0
-#define FB_SM_D (FB_SM_X + FB_X_BYTES)
-#define FB_SM_W (FB_SM_D + FB_DSTAGES * FB_D_BYTES)
-#define FB_SM_A (FB_SM_W + 2 * FB_W_BYTES)
-#define FB_SM_BAR (FB_SM_A + FB_ASTAGES * FB_A_BYTES)
-#define FB_SM_TOTAL (FB_SM_BAR + 256)
-#define FB_TCOL (3 * FB_NS)                         // first TMEM column of the T stages
+#define FB_D_BYTES (FB_VT * 128)      // one Dt16 k-block of one plane: 16 KB
+#define FB_W_BYTES (FB_VT * 128)      // W16 tile: 16 KB
 
-static_assert(FB_NS % 16 == 0 && FB_NS % FB_ST == 0 && FB_ST % 8 == 0, "tile shape");
-static_assert(3 * FB_NS + FB_TBUF * FB_TN <= 512, "TMEM budget");
-static_assert(FB_X_KB_BYTES % 1024 == 0 && FB_A_BYTES % 1024 == 0, "swizzle atoms need 1024 B alignment");
-static_assert(FB_SM_TOTAL <= 227 * 1024, "shared memory budget");
+// NS samples per super-tile (blend MMA N), ST samples per skinning MMA, TBUF T accumulator stages.
+template <int NS_, int ST_, int TBUF_, int DSTAGES_ = 4, int ASTAGES_ = 3, int PRE_ = 0>
+struct BodyCfg {
+  static constexpr int NS = NS_, ST = ST_, TBUF = TBUF_, DSTAGES = DSTAGES_, ASTAGES = ASTAGES_, PRE = PRE_;
+  static constexpr int TN = 12 * ST;            // skinning MMA N
+  static constexpr int NT = NS / ST;            // skinning tiles per super-tile
+  static constexpr int X_KB_BYTES = NS * 128;   // one k-block of the x16 tile
+  static constexpr int X_BYTES = 4 * X_KB_BYTES;
+  static constexpr int A_BYTES = TN * 128;      // A16 rows of ST samples
+  static constexpr int SM_X = 0;
+  static constexpr int SM_D = SM_X + X_BYTES;
+  static constexpr int SM_W = SM_D + DSTAGES * FB_D_BYTES;
+  static constexpr int SM_A = SM_W + 2 * FB_W_BYTES;
+  static constexpr int SM_BAR = SM_A + ASTAGES * A_BYTES;
+  static constexpr int SM_TOTAL = SM_BAR + 256;
+  static constexpr int TCOL = 3 * NS;           // first TMEM column of the T stages
+  // warps: 0 blend-operand producer, 1 blend MMA issuer, 2 skinning-operand producer, 3 skinning MMA issuer,
+  // 4..11 epilogue.  PRE = skinning tiles whose v_posed the epilogue fetches early (see there)
+  static constexpr int THREADS = 32 * 12;
+  static_assert(NT % TBUF == 0 && PRE < NT, "tile counts");
+  static_assert(NS % 16 == 0 && NS % ST == 0 && ST % 8 == 0, "tile shape");
+  static_assert(3 * NS + TBUF * TN <= 512, "TMEM budget");
+  static_assert(X_KB_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "swizzle atoms need 1024 B alignment");
+  static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+  static_assert(DSTAGES <= 4 && ASTAGES <= 4 && TBUF <= 2, "barrier slots");
+};
 
-__global__ void __launch_bounds__(FB_THREADS, 1)
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
     k_body_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_d,
               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_a, int B, int V, int Vp,
               int n_vt, int n_m, float inv_scale, float *__restrict__ verts) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar0 = sbase + FB_SM_BAR;
+  const uint32_t bar0 = sbase + C::SM_BAR;
   const uint32_t full_x = bar0 + 0, empty_x = bar0 + 8, p_full = bar0 + 16, p_empty = bar0 + 24;
-  const uint32_t full_d = bar0 + 32, empty_d = bar0 + 64;     // FB_DSTAGES (<= 4) each
+  const uint32_t full_d = bar0 + 32, empty_d = bar0 + 64;     // C::DSTAGES (<= 4) each
   const uint32_t full_w = bar0 + 96, empty_w = bar0 + 112;    // 2 each
-  const uint32_t full_a = bar0 + 128, empty_a = bar0 + 160;   // FB_ASTAGES (<= 4) each
-  const uint32_t t_full = bar0 + 192, t_empty = bar0 + 208;   // FB_TBUF (<= 2) each
-  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + FB_SM_BAR + 224);
+  const uint32_t full_a = bar0 + 128, empty_a = bar0 + 160;   // C::ASTAGES (<= 4) each
+  const uint32_t t_full = bar0 + 192, t_empty = bar0 + 208;   // C::TBUF (<= 2) each
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + C::SM_BAR + 224);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = n_vt * n_m;
@@ -84,7 +95,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     mbar_init(empty_x, 1);
     mbar_init(p_full, 1);
     mbar_init(p_empty, 8);                 // one arrival per epilogue warp
-    for (int i = 0; i < FB_DSTAGES; ++i) {
+    for (int i = 0; i < C::DSTAGES; ++i) {
       mbar_init(full_d + 8 * i, 1);
       mbar_init(empty_d + 8 * i, 1);
     }
@@ -92,18 +103,18 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       mbar_init(full_w + 8 * i, 1);
       mbar_init(empty_w + 8 * i, 1);
     }
-    for (int i = 0; i < FB_ASTAGES; ++i) {
+    for (int i = 0; i < C::ASTAGES; ++i) {
       mbar_init(full_a + 8 * i, 1);
       mbar_init(empty_a + 8 * i, 1);
     }
-    for (int i = 0; i < FB_TBUF; ++i) {
+    for (int i = 0; i < C::TBUF; ++i) {
       mbar_init(t_full + 8 * i, 1);
       mbar_init(t_empty + 8 * i, 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + FB_SM_BAR + 224), "n"(512)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::SM_BAR + 224), "n"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -123,8 +134,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         const int m = t / n_vt, vt = t % n_vt;
         if (m != cur_m) {
           if (x_loads > 0) mbar_wait(empty_x, (x_loads - 1) & 1);
-          mbar_expect_tx(full_x, FB_X_BYTES);
-          for (int kb = 0; kb < 4; ++kb) tma_load_2d(sbase + FB_SM_X + kb * FB_X_KB_BYTES, &map_x, kb * 64, m * FB_NS, full_x);
+          mbar_expect_tx(full_x, C::X_BYTES);
+          for (int kb = 0; kb < 4; ++kb) tma_load_2d(sbase + C::SM_X + kb * C::X_KB_BYTES, &map_x, kb * 64, m * C::NS, full_x);
           ++x_loads;
           cur_m = m;
         }
@@ -132,15 +143,15 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(empty_d + 8 * stage, phase ^ 1);
             mbar_expect_tx(full_d + 8 * stage, FB_D_BYTES);
-            tma_load_2d(sbase + FB_SM_D + stage * FB_D_BYTES, &map_d, kb * 64, cc * Vp + vt * FB_VT, full_d + 8 * stage);
-            if (++stage == FB_DSTAGES) {
+            tma_load_2d(sbase + C::SM_D + stage * FB_D_BYTES, &map_d, kb * 64, cc * Vp + vt * FB_VT, full_d + 8 * stage);
+            if (++stage == C::DSTAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 2) {
     // =========================== skinning operand producer ===========================
     if (lane == 0) {
       int wbuf = 0, wphase = 0, stage = 0, phase = 0;
@@ -148,16 +159,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         const int m = t / n_vt, vt = t % n_vt;
         mbar_wait(empty_w + 8 * wbuf, wphase ^ 1);
         mbar_expect_tx(full_w + 8 * wbuf, FB_W_BYTES);
-        tma_load_2d(sbase + FB_SM_W + wbuf * FB_W_BYTES, &map_w, 0, vt * FB_VT, full_w + 8 * wbuf);
+        tma_load_2d(sbase + C::SM_W + wbuf * FB_W_BYTES, &map_w, 0, vt * FB_VT, full_w + 8 * wbuf);
         if (++wbuf == 2) {
           wbuf = 0;
           wphase ^= 1;
         }
-        for (int st = 0; st < FB_NT; ++st) {
+        for (int st = 0; st < C::NT; ++st) {
           mbar_wait(empty_a + 8 * stage, phase ^ 1);
-          mbar_expect_tx(full_a + 8 * stage, FB_A_BYTES);
-          tma_load_2d(sbase + FB_SM_A + stage * FB_A_BYTES, &map_a, 0, (m * FB_NS + st * FB_ST) * 12, full_a + 8 * stage);
-          if (++stage == FB_ASTAGES) {
+          mbar_expect_tx(full_a + 8 * stage, C::A_BYTES);
+          tma_load_2d(sbase + C::SM_A + stage * C::A_BYTES, &map_a, 0, (m * C::NS + st * C::ST) * 12, full_a + 8 * stage);
+          if (++stage == C::ASTAGES) {
             stage = 0;
             phase ^= 1;
           }
@@ -165,12 +176,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc_p = umma_idesc_f16(FB_VT, FB_NS);
-      constexpr uint32_t idesc_t = umma_idesc_f16(FB_VT, FB_TN);
-      int cur_m = -1, x_loads = 0, dstage = 0, dphase = 0, wbuf = 0, wphase = 0, astage = 0, aphase = 0;
-      int tb = 0, tphase = 0, n_tiles = 0;
+    // =========================== blend MMA issuer ===========================
+    // All 32 lanes run the loop and wait on the barriers; the elected lane issues (see elect_one).
+    // The two contractions have their own issuing warps (1: blend, 3: skinning): a warp's loop
+    // bookkeeping (~200 clk per group of MMAs) does not overlap its own issue stalls, so one warp
+    // doing both kept the tensor pipe idle half of the time.
+    {
+      constexpr uint32_t idesc_p = umma_idesc_f16(FB_VT, C::NS);
+      const uint64_t desc_d0 = umma_desc_sw128(sbase + C::SM_D), desc_x0 = umma_desc_sw128(sbase + C::SM_X);
+      int cur_m = -1, x_loads = 0, dstage = 0, dphase = 0, n_tiles = 0;
+      [[maybe_unused]] long long w_pe = 0, w_fd = 0, w_tot = TCLK(), tq;
       for (int t = t0; t < t1; ++t, ++n_tiles) {
         const int m = t / n_vt;
         if (m != cur_m) {
@@ -178,102 +193,161 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
           ++x_loads;
           cur_m = m;
         }
-        // ---- blend: P = Dt16 tile x x16 tile^T, three coordinate planes
+        // P = Dt16 tile x x16 tile^T, three coordinate planes
+        tq = TCLK();
         mbar_wait(p_empty, (n_tiles & 1) ^ 1);       // the epilogue has read the previous P
+        TADD(w_pe, tq);
         tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < 3; ++cc) {
-          const uint32_t d_tmem = tmem_base + cc * FB_NS;
+          const uint32_t d_tmem = tmem_base + cc * C::NS;
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
+            tq = TCLK();
             mbar_wait(full_d + 8 * dstage, dphase);
+            TADD(w_fd, tq);
             tc_fence_after();
-            const uint32_t a_addr = sbase + FB_SM_D + dstage * FB_D_BYTES;
-            const uint32_t b_addr = sbase + FB_SM_X + kb * FB_X_KB_BYTES;
+            const uint64_t a_desc = umma_desc_add(desc_d0, dstage * FB_D_BYTES);
+            const uint64_t b_desc = umma_desc_add(desc_x0, kb * C::X_KB_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (kb == 3 && k == 3) continue;        // K = 240: the last 16 columns are zero padding
-              tc_mma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc_p, (kb | k) != 0);
+              for (int k = 0; k < 4; ++k) {
+                if (kb == 3 && k == 3) continue;      // K = 240: the last 16 columns are zero padding
+                if (FB_ABLATE != 2) tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_p, (kb | k) != 0);
+              }
+              tc_commit(empty_d + 8 * dstage);
             }
-            tc_commit(empty_d + 8 * dstage);
-            if (++dstage == FB_DSTAGES) {
+            __syncwarp();
+            if (++dstage == C::DSTAGES) {
               dstage = 0;
               dphase ^= 1;
             }
           }
         }
-        tc_commit(p_full);
         const bool last_of_m = (t + 1 == t1) || ((t + 1) / n_vt != m);
-        if (last_of_m) tc_commit(empty_x);
-        // ---- skinning transforms, ST samples at a time
+        if (elect_one()) {
+          tc_commit(p_full);
+          if (last_of_m) tc_commit(empty_x);
+        }
+        __syncwarp();
+      }
+#ifdef FB_TIMING
+      if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+        printf("cta %d blend MMA warp: total %lld, wait p_empty %lld, full_d %lld (tiles %d)\n", blockIdx.x, clock64() - w_tot,
+               w_pe, w_fd, t1 - t0);
+#endif
+    }
+  } else if (warp == 3) {
+    // =========================== skinning MMA issuer ===========================
+    {
+      constexpr uint32_t idesc_t = umma_idesc_f16(FB_VT, C::TN);
+      const uint64_t desc_w0 = umma_desc_sw128(sbase + C::SM_W), desc_a0 = umma_desc_sw128(sbase + C::SM_A);
+      int wbuf = 0, wphase = 0, astage = 0, aphase = 0, tb = 0, tphase = 0;
+      [[maybe_unused]] long long w_te = 0, w_fa = 0, w_tot = TCLK(), tq;
+      for (int t = t0; t < t1; ++t) {
         mbar_wait(full_w + 8 * wbuf, wphase);
-        const uint32_t w_addr = sbase + FB_SM_W + wbuf * FB_W_BYTES;
+        const uint64_t w_desc = umma_desc_add(desc_w0, wbuf * FB_W_BYTES);
 #pragma unroll 1
-        for (int st = 0; st < FB_NT; ++st) {
+        for (int st = 0; st < C::NT; ++st) {
+          tq = TCLK();
           mbar_wait(t_empty + 8 * tb, tphase ^ 1);
+          TADD(w_te, tq);
+          tq = TCLK();
           mbar_wait(full_a + 8 * astage, aphase);
+          TADD(w_fa, tq);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + FB_TCOL + tb * FB_TN;
-          const uint32_t a_addr = sbase + FB_SM_A + astage * FB_A_BYTES;
-          // (W window, A window) pairs of the table in k_skin_tc.cu
-          tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 0 * 32), umma_desc_sw128(a_addr + 0 * 32), idesc_t, 0);
-          tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 1 * 32), umma_desc_sw128(a_addr + 1 * 32), idesc_t, 1);
-          tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 0 * 32), umma_desc_sw128(a_addr + 2 * 32), idesc_t, 1);
-          tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 2 * 32), umma_desc_sw128(a_addr + 0 * 32), idesc_t, 1);
-          tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 3 * 32), umma_desc_sw128(a_addr + 1 * 32), idesc_t, 1);
-          tc_commit(empty_a + 8 * astage);
-          tc_commit(t_full + 8 * tb);
-          if (++astage == FB_ASTAGES) {
+          const uint32_t d_tmem = tmem_base + C::TCOL + tb * C::TN;
+          const uint64_t a_desc = umma_desc_add(desc_a0, astage * C::A_BYTES);
+          if (elect_one()) {
+            // (W window, A window) pairs of the table in k_skin_tc.cu; a window is 32 B = 2 units
+            if (FB_ABLATE != 2) {
+              tc_mma_f16(d_tmem, w_desc + 0, a_desc + 0, idesc_t, 0);
+              tc_mma_f16(d_tmem, w_desc + 2, a_desc + 2, idesc_t, 1);
+              tc_mma_f16(d_tmem, w_desc + 0, a_desc + 4, idesc_t, 1);
+              tc_mma_f16(d_tmem, w_desc + 4, a_desc + 0, idesc_t, 1);
+              tc_mma_f16(d_tmem, w_desc + 6, a_desc + 2, idesc_t, 1);
+            }
+            tc_commit(empty_a + 8 * astage);
+            tc_commit(t_full + 8 * tb);
+          }
+          __syncwarp();
+          if (++astage == C::ASTAGES) {
             astage = 0;
             aphase ^= 1;
           }
-          if (++tb == FB_TBUF) {
+          if (++tb == C::TBUF) {
             tb = 0;
             tphase ^= 1;
           }
         }
-        tc_commit(empty_w + 8 * wbuf);
+        if (elect_one()) tc_commit(empty_w + 8 * wbuf);
+        __syncwarp();
         if (++wbuf == 2) {
           wbuf = 0;
           wphase ^= 1;
         }
       }
+#ifdef FB_TIMING
+      if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+        printf("cta %d skin MMA warp: total %lld, wait t_empty %lld, full_a %lld\n", blockIdx.x, clock64() - w_tot, w_te, w_fa);
+#endif
     }
-  } else {
-    // =========================== epilogue (warps 2..9) ===========================
-    // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31); each takes
+  } else if (warp >= 4) {
+    // =========================== epilogue (warps 4..11) ===========================
+    // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31), each taking
     // half of a skinning tile's samples.  Thread = vertex: T (12 columns per sample) and the three
     // coordinates of v_posed come out of TMEM; nothing passes through shared memory.
+    // P has a single TMEM stage, so the blend of the next super-tile cannot start before the
+    // last read of this one: the v_posed values of the last PRE tiles are therefore fetched into
+    // registers early and P is handed back PRE tiles before the super-tile ends, which hides most
+    // of the blend behind the remaining skinning tiles.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int HS = FB_ST / 2;                 // samples per warp per tile
+    const int half = ((warp - 4) >> 2) & 1;
+    constexpr int HS = C::ST / 2;                 // samples per warp per tile
+    constexpr int G = HS / 4;                     // groups of 4 samples per warp per tile
+    constexpr int PRE = C::PRE;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
     int tb = 0, tphase = 0, n_tiles = 0;
+    [[maybe_unused]] long long w_pf = 0, w_tf = 0, w_ld = 0, w_tot = TCLK(), tq;
     for (int t = t0; t < t1; ++t, ++n_tiles) {
       const int m = t / n_vt, vt = t % n_vt;
       const int v0 = vt * FB_VT + 32 * q;
       const bool v_ok = v0 + lane < V;
-      const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
-      mbar_wait(p_full, n_tiles & 1);
-#pragma unroll 1
-      for (int st = 0; st < FB_NT; ++st) {
-        mbar_wait(t_full + 8 * tb, tphase);
+      float *const vbase = verts + ((size_t)(m * C::NS) * V + v0 + lane) * 3;
+      const int b_left = B - m * C::NS;           // samples of this super-tile inside the batch
+
+      // one skinning tile; p_in == nullptr: v_posed comes from TMEM (P), else from registers
+      auto do_tile = [&](int st, const uint32_t(*p_in)[3][4], bool release_p) {
+        const uint32_t my_full = t_full + 8 * tb, my_empty = t_empty + 8 * tb;
+        const uint32_t tcol0 = lane_base + C::TCOL + tb * C::TN + half * HS * 12;
+        tq = TCLK();
+        mbar_wait(my_full, tphase);
+        TADD(w_tf, tq);
         tc_fence_after();
-        const int s_loc = st * FB_ST + half * HS;   // first sample (within the super-tile) of this warp
+        const int s_loc = st * C::ST + half * HS;   // first sample (within the super-tile) of this warp
 #pragma unroll
-        for (int g = 0; g < HS / 4; ++g) {
+        for (int g = 0; g < G; ++g) {
           uint32_t r[48], pc[3][4];
-          const uint32_t tcol = lane_base + FB_TCOL + tb * FB_TN + (half * HS + 4 * g) * 12;
-          tc_ld_32x32(tcol, r);
-          tc_ld_32x16(tcol + 32, r + 32);
+          tc_ld_32x32(tcol0 + g * 48, r);
+          tc_ld_32x16(tcol0 + g * 48 + 32, r + 32);
+          if (p_in == nullptr) {
 #pragma unroll
-          for (int cc = 0; cc < 3; ++cc) tc_ld_32x4(lane_base + cc * FB_NS + s_loc + 4 * g, pc[cc]);
+            for (int cc = 0; cc < 3; ++cc) tc_ld_32x4(lane_base + cc * C::NS + s_loc + 4 * g, pc[cc]);
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+              for (int si = 0; si < 4; ++si) pc[cc][si] = p_in[g][cc][si];
+          }
+          tq = TCLK();
           tc_wait_ld();
-          if (g == HS / 4 - 1) {
+          TADD(w_ld, tq);
+          if (g == G - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              mbar_arrive(t_empty + 8 * tb);
-              if (st == FB_NT - 1) mbar_arrive(p_empty);   // last read of this super-tile's P
+              mbar_arrive(my_empty);
+              if (release_p) mbar_arrive(p_empty);   // this warp's last read of the super-tile's P
             }
           }
 #pragma unroll
@@ -287,21 +361,49 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
               o[rr] = fmaf(__uint_as_float(T[4 * rr]), px,
                            fmaf(__uint_as_float(T[4 * rr + 1]), py,
                                 fmaf(__uint_as_float(T[4 * rr + 2]), pz, __uint_as_float(T[4 * rr + 3]))));
-            const int b = m * FB_NS + s_loc + 4 * g + si;
-            if (b < B && v_ok) {
-              float *dst = verts + ((size_t)b * V + v0 + lane) * 3;
+            const int sl = s_loc + 4 * g + si;
+            if (FB_ABLATE != 3 && sl < b_left && v_ok) {
+              float *dst = vbase + sl * (V * 3);
               __stcs(dst, o[0]);
               __stcs(dst + 1, o[1]);
               __stcs(dst + 2, o[2]);
             }
           }
         }
-        if (++tb == FB_TBUF) {
+        if (++tb == C::TBUF) {
           tb = 0;
           tphase ^= 1;
         }
+      };
+
+      tq = TCLK();
+      mbar_wait(p_full, n_tiles & 1);
+      TADD(w_pf, tq);
+      tc_fence_after();
+#pragma unroll 1
+      for (int st = 0; st < C::NT - PRE; ++st) do_tile(st, nullptr, PRE == 0 && st == C::NT - 1);
+      if (PRE > 0) {
+        uint32_t pre[PRE > 0 ? PRE : 1][G][3][4];
+#pragma unroll
+        for (int i = 0; i < PRE; ++i)
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+              tc_ld_32x4(lane_base + cc * C::NS + (C::NT - PRE + i) * C::ST + half * HS + 4 * g, pre[i][g][cc]);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_empty);
+#pragma unroll
+        for (int i = 0; i < PRE; ++i) do_tile(C::NT - PRE + i, pre[i], false);
       }
     }
+#ifdef FB_TIMING
+    if (lane == 0 && (warp == 4 || warp == 9) && (blockIdx.x == 0 || blockIdx.x == 77))
+      printf("cta %d epilogue warp %d: total %lld, wait p_full %lld, t_full %lld, tmem ld %lld\n", blockIdx.x, warp,
+             clock64() - w_tot, w_pf, w_tf, w_ld);
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -337,24 +439,40 @@ static int make_map_rows16(CUtensorMap *map, const void *ptr, uint64_t row_halve
 }
 
 // Needs the operands of both tensor-core kernels (Dt16 + its scale, W16).
+using BodyA = BodyCfg<96, 8, 2, 4, 3, 4>;   // default: double-buffered T, v_posed of the last 4 tiles fetched early
+using BodyB = BodyCfg<96, 8, 2, 4, 3, 0>;   // no early fetch (the blend is exposed)
+using BodyC = BodyCfg<96, 16, 1, 4, 2, 0>;  // N = 192 skinning MMAs, single T stage
+
 int body_tc_init(smplb_ctx *c) {
   c->body_tc_ok = false;
   if (!c->tc_ok || !c->skin_tc_ok) return 0;
-  CUDA_TRY(cudaFuncSetAttribute(k_body_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SM_TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyA>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyA::SM_TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyB>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyB::SM_TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyC::SM_TOTAL));
   c->body_tc_ok = true;
   return 0;
 }
 
-// verts [B][V][3] from the operand rows pose_fwd wrote (x16 [B][256], A16 [12 B][64]).
-int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts) {
-  RET_IF(!c->body_tc_ok, SMPLB_ESTATE, "fused tcgen05 blend+skinning path is not initialised");
+template <class C>
+static int launch_body_cfg(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts) {
   alignas(64) CUtensorMap map_x, map_a;
-  TRY(make_map_rows16(&map_x, x16, 256, (uint64_t)B, FB_NS));
-  TRY(make_map_rows16(&map_a, A16, 64, (uint64_t)B * 12, FB_TN));
-  const int n_vt = c->Vp / FB_VT, n_m = cdiv(B, FB_NS);
+  TRY(make_map_rows16(&map_x, x16, 256, (uint64_t)B, C::NS));
+  TRY(make_map_rows16(&map_a, A16, 64, (uint64_t)B * 12, C::TN));
+  const int n_vt = c->Vp / FB_VT, n_m = cdiv(B, C::NS);
   const int total = n_vt * n_m;
   const int grid = total < c->num_sms ? total : c->num_sms;
-  LAUNCH(c, "body_fwd_tc", grid, FB_THREADS, FB_SM_TOTAL, k_body_tc, map_x, *(const CUtensorMap *)c->map_d,
+  LAUNCH(c, "body_fwd_tc", grid, C::THREADS, C::SM_TOTAL, k_body_tc<C>, map_x, *(const CUtensorMap *)c->map_d,
          *(const CUtensorMap *)c->map_w, map_a, B, c->V, c->Vp, n_vt, n_m, c->tc_inv_scale, verts);
   return 0;
+}
+
+// verts [B][V][3] from the operand rows pose_fwd wrote (x16 [B][256], A16 [12 B][64]).
+// smplb_debug_set("fused", 2 | 3) selects the alternative configurations (tuning / validation).
+int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts) {
+  RET_IF(!c->body_tc_ok, SMPLB_ESTATE, "fused tcgen05 blend+skinning path is not initialised");
+  switch (c->use_fused) {
+    case 2: return launch_body_cfg<BodyB>(c, B, x16, A16, verts);
+    case 3: return launch_body_cfg<BodyC>(c, B, x16, A16, verts);
+    default: return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
+  }
 }

@@ -51,6 +51,21 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One lane of a fully active warp (the lowest).  The MMA issuer warps run their loops with all 32
+// lanes and issue under this predicate: inside an `if (lane == 0)` region the compiler treats
+// every operand as divergent and wraps each tcgen05.mma in ~17 instructions of vector->uniform
+// register moves and an election loop (~100 clk per MMA); warp-uniform code issues one in ~40 clk.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate; one thread issues for the CTA.
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -89,6 +104,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+
+// The same descriptor for a warp-uniform base address; k-steps and ring stages advance it by
+// (bytes >> 4) with a plain add (the 14-bit address field cannot carry for valid addresses).
+__device__ __forceinline__ uint64_t umma_desc_add(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
 
 // Instruction descriptor for kind::f16 with fp16 A/B (K-major both) and fp32 D:
 // bits 4-5 = 1 (D fp32), N >> 3 at bit 17, M >> 4 at bit 24.
