@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--engines", type=int, default=2, help="contexts in flight per GPU")
+    ap.add_argument("--fused", type=int, default=-1, help="tuning: smplb_debug_set('fused', n) on every context")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -235,6 +236,9 @@ def main():
     engines = [SMPL(model, device=local, max_batch=B) for _ in range(NE)]
     smpl = engines[0]
     ctx = smpl.ctx
+    if args.fused >= 0:
+        for e in engines:
+            e.ctx.debug_set("fused", args.fused)
     if world > 1:
         for e in engines:
             uid = [runtime.Context.comm_unique_id() if rank == 0 else None]

@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // all 32 lanes run the loop, the elected lane issues (tc_ptx.cuh: elect_one)
+    {
+      const uint64_t desc_x0 = umma_desc_sw128(sbase + SM_X_OFF), desc_a0 = umma_desc_sw128(sbase + SM_A_OFF);
       int cur_m = -1, x_loads = 0, stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int t = t0; t < t1; ++t) {
         int m = t / n_nblk;
@@ -137,26 +139,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int kb = 0; kb < TC_NKB; ++kb) {
           mbar_wait(full_a + 8 * stage, phase);           // Dt16 k-block landed
           tc_fence_after();
-          uint32_t b_addr = sbase + SM_A_OFF + stage * TILE_KB_BYTES;
+          const uint64_t b_desc = umma_desc_add(desc_a0, stage * TILE_KB_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int u = 0; u < TC_MSUB; ++u) {
-            // MMA "A" (M = samples) is a resident x16 tile, "B" (N = coordinates) the ring stage
-            uint32_t a_addr = sbase + SM_X_OFF + (u * TC_NKB + kb) * TILE_KB_BYTES;
-            uint32_t d_tmem = tmem_base + (acc * TC_MSUB + u) * TC_BN;
+            for (int u = 0; u < TC_MSUB; ++u) {
+              // MMA "A" (M = samples) is a resident x16 tile, "B" (N = coordinates) the ring stage
+              const uint64_t a_desc = umma_desc_add(desc_x0, (u * TC_NKB + kb) * TILE_KB_BYTES);
+              const uint32_t d_tmem = tmem_base + (acc * TC_MSUB + u) * TC_BN;
 #pragma unroll
-            for (int k = 0; k < TC_KB / 16; ++k)   // advance 16 fp16 = 32 B inside the 128 B swizzle atom
-              tc_mma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), TC_IDESC,
-                         (kb | k) != 0);
+              for (int k = 0; k < TC_KB / 16; ++k)   // advance 16 fp16 = 32 B inside the 128 B swizzle atom
+                tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, TC_IDESC, (kb | k) != 0);
+            }
+            tc_commit(empty_a + 8 * stage);    // ring stage reusable once these MMAs retire
           }
-          tc_commit(empty_a + 8 * stage);    // ring stage reusable once these MMAs retire
+          __syncwarp();
           if (++stage == TC_ASTAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(tmem_full + 8 * acc);      // accumulators ready for the epilogue
-        bool last_of_m = (t + 1 == t1) || ((t + 1) / n_nblk != m);
-        if (last_of_m) tc_commit(empty_x);
+        const bool last_of_m = (t + 1 == t1) || ((t + 1) / n_nblk != m);
+        if (elect_one()) {
+          tc_commit(tmem_full + 8 * acc);      // accumulators ready for the epilogue
+          if (last_of_m) tc_commit(empty_x);
+        }
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

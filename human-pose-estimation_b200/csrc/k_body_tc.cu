@@ -18,6 +18,14 @@
 // shapes are chosen to keep the instruction count per sample low under the 512-column TMEM
 // budget: 3 * NS (P) + TBUF * 12 * ST (T) <= 512.
 //
+// What bounds it (tools/fused_timing.py builds, profiles/r01/v7_*): shared-memory bandwidth.  An
+// SS-mode MMA with N = 96 reads 4 KB of "A" and 3 KB of "B" per K-step, 56 clk at 128 B/clk -- already
+// longer than its 48 clk on the tensor pipe -- and every operand byte also enters shared memory
+// through TMA: ~1.1 MB of shared-memory traffic per super-tile, ~8.5 k clk of the ~13 k it takes.
+// Tried and measured slower or equal: a second set of epilogue warps, a software-pipelined
+// (two register sets) epilogue, N = 192 skinning MMAs with a single T stage, plain instead of
+// evict-first stores (+5 %).
+//
 // Persistent, warp-specialised: warp 0 TMA producer of the blend operands, warp 1 blend MMA issuer
 // and TMEM allocator, warp 2 TMA producer of the skinning operands, warp 3 skinning MMA issuer,
 // warps 4.. epilogue (one set of 8

@@ -79,8 +79,10 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // all 32 lanes run the loop, the elected lane issues (tc_ptx.cuh: elect_one)
+    {
       constexpr uint32_t idesc = umma_idesc_f16(G_BM, G_BN);
+      const uint64_t desc0 = umma_desc_sw128(sbase);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         int z = t / (n_nblk * n_mblk);
@@ -91,18 +93,20 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full + 8 * stage, phase);
           tc_fence_after();
-          uint32_t a_addr = sbase + stage * G_STAGE_BYTES, b_addr = a_addr + G_KB_BYTES;
+          const uint64_t a_desc = umma_desc_add(desc0, stage * G_STAGE_BYTES), b_desc = umma_desc_add(a_desc, G_KB_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < G_KB / 16; ++k)
-            tc_mma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                       (kb != kb0) || (k != 0));
-          tc_commit(empty + 8 * stage);
+            for (int k = 0; k < G_KB / 16; ++k) tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0) || (k != 0));
+            tc_commit(empty + 8 * stage);
+          }
+          __syncwarp();
           if (++stage == G_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(tmem_full + 8 * acc);
+        if (elect_one()) tc_commit(tmem_full + 8 * acc);
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

@@ -45,30 +45,40 @@ __global__ void k_kp_loss(int B, int K, const float *__restrict__ kp_gt, const f
   cnt[b] = tc;
 }
 
-// Sum of the per-body partials: one block, fixed order.
-__global__ void __launch_bounds__(1024) k_reduce_kp(int B, const float *__restrict__ part, const int *__restrict__ cnt,
-                                                    float *__restrict__ abs_sum, long long *__restrict__ num_present,
-                                                    float *__restrict__ cnt_as_float) {
-  __shared__ float red[1024];
-  __shared__ long long redc[1024];
-  int t = threadIdx.x;
+// Sum of the per-body partials: one block, fixed order.  256 threads (8 K registers), so the
+// block can be placed on an SM that a persistent tensor-core CTA occupies: a 1024-thread block
+// could not, and while it waited at the head of the queue it held back every later launch of
+// every stream (tools/timeline.py showed the whole keypoint path stalling ~95 us on it).
+#define RK_THREADS 256
+__device__ __forceinline__ void reduce_kp_block(int B, const float *__restrict__ part, const int *__restrict__ cnt,
+                                                float *red, long long *redc) {
+  const int t = threadIdx.x;
   float s = 0.f;
   long long c = 0;
-  for (int i = t; i < B; i += 1024) {
+  for (int i = t; i < B; i += RK_THREADS) {
     s += part[i];
     c += cnt[i];
   }
   red[t] = s;
   redc[t] = c;
   __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
+  for (int o = RK_THREADS / 2; o > 0; o >>= 1) {
     if (t < o) {
       red[t] += red[t + o];
       redc[t] += redc[t + o];
     }
     __syncthreads();
   }
-  if (t == 0) {
+}
+
+__global__ void __launch_bounds__(RK_THREADS) k_reduce_kp(int B, const float *__restrict__ part,
+                                                          const int *__restrict__ cnt, float *__restrict__ abs_sum,
+                                                          long long *__restrict__ num_present,
+                                                          float *__restrict__ cnt_as_float) {
+  __shared__ float red[RK_THREADS];
+  __shared__ long long redc[RK_THREADS];
+  reduce_kp_block(B, part, cnt, red, redc);
+  if (threadIdx.x == 0) {
     *abs_sum = red[0];
     *num_present = redc[0];
     if (cnt_as_float) *cnt_as_float = (float)redc[0];   // exact below 2^24; the all-reduced form
@@ -77,30 +87,14 @@ __global__ void __launch_bounds__(1024) k_reduce_kp(int B, const float *__restri
 
 // Single-GPU, keypoint-loss-only steps: reduce and finalize in one launch (no all-reduce or
 // mesh term has to come in between).
-__global__ void __launch_bounds__(1024) k_reduce_finalize(int B, const float *__restrict__ part,
-                                                          const int *__restrict__ cnt, float w_kp, long long count_override,
-                                                          float *__restrict__ scal, long long *__restrict__ kp_cnt,
-                                                          float *__restrict__ out) {
-  __shared__ float red[1024];
-  __shared__ long long redc[1024];
-  int t = threadIdx.x;
-  float s = 0.f;
-  long long c = 0;
-  for (int i = t; i < B; i += 1024) {
-    s += part[i];
-    c += cnt[i];
-  }
-  red[t] = s;
-  redc[t] = c;
-  __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if (t < o) {
-      red[t] += red[t + o];
-      redc[t] += redc[t + o];
-    }
-    __syncthreads();
-  }
-  if (t == 0) {
+__global__ void __launch_bounds__(RK_THREADS) k_reduce_finalize(int B, const float *__restrict__ part,
+                                                                const int *__restrict__ cnt, float w_kp,
+                                                                long long count_override, float *__restrict__ scal,
+                                                                long long *__restrict__ kp_cnt, float *__restrict__ out) {
+  __shared__ float red[RK_THREADS];
+  __shared__ long long redc[RK_THREADS];
+  reduce_kp_block(B, part, cnt, red, redc);
+  if (threadIdx.x == 0) {
     long long den = count_override > 0 ? count_override : redc[0];
     float kp = den > 0 ? red[0] / (float)den : 0.0f;
     scal[0] = red[0];
@@ -553,7 +547,7 @@ int launch_kp_loss(smplb_ctx *c, int B, int K, const float *kp_gt, const float *
 
 int launch_reduce_kp(smplb_ctx *c, int B, const float *part, const int *cnt, float *abs_sum, long long *num_present,
                      float *cnt_as_float) {
-  LAUNCH(c, "reduce_kp", 1, 1024, 0, k_reduce_kp, B, part, cnt, abs_sum, num_present, cnt_as_float);
+  LAUNCH(c, "reduce_kp", 1, RK_THREADS, 0, k_reduce_kp, B, part, cnt, abs_sum, num_present, cnt_as_float);
   return 0;
 }
 
@@ -566,7 +560,7 @@ int launch_finalize_loss(smplb_ctx *c, float w_kp, float w_mesh, long long count
 
 int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long long count_override, float *loss_parts) {
   (void)w_mesh;
-  LAUNCH(c, "reduce_finalize_kp", 1, 1024, 0, k_reduce_finalize, B, c->ws_part, c->ws_cnt, w_kp, count_override, c->ws_scal,
+  LAUNCH(c, "reduce_finalize_kp", 1, RK_THREADS, 0, k_reduce_finalize, B, c->ws_part, c->ws_cnt, w_kp, count_override, c->ws_scal,
          c->ws_cnt64, loss_parts);
   return 0;
 }

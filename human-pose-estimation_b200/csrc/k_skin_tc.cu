@@ -117,8 +117,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // all 32 lanes run the loop, the elected lane issues (tc_ptx.cuh: elect_one)
+    {
       constexpr uint32_t idesc = umma_idesc_f16(ST_VT, ST_N);
+      const uint64_t desc_w0 = umma_desc_sw128(sbase + ST_SM_W), a_desc = umma_desc_sw128(sbase + ST_SM_A);
       int cur_ch = -1, a_loads = 0, stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int t = t0; t < t1; ++t) {
         int ch = t / n_vt;
@@ -130,18 +132,21 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
         mbar_wait(tmem_empty + 8 * acc, acc_phase ^ 1);
         mbar_wait(full_a + 8 * stage, phase);
         tc_fence_after();
-        uint32_t d_tmem = tmem_base + acc * 256;
-        uint32_t w_addr = sbase + ST_SM_W + stage * ST_W_BYTES, a_addr = sbase + ST_SM_A;
-        // five K = 16 steps, (W window, A window) as in the table at the top
-        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 0 * 32), umma_desc_sw128(a_addr + 0 * 32), idesc, 0);
-        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 1 * 32), umma_desc_sw128(a_addr + 1 * 32), idesc, 1);
-        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 0 * 32), umma_desc_sw128(a_addr + 2 * 32), idesc, 1);
-        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 2 * 32), umma_desc_sw128(a_addr + 0 * 32), idesc, 1);
-        tc_mma_f16(d_tmem, umma_desc_sw128(w_addr + 3 * 32), umma_desc_sw128(a_addr + 1 * 32), idesc, 1);
-        tc_commit(empty_a + 8 * stage);
-        tc_commit(tmem_full + 8 * acc);
-        bool last_of_ch = (t + 1 == t1) || ((t + 1) / n_vt != ch);
-        if (last_of_ch) tc_commit(empty_w);
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint64_t w_desc = umma_desc_add(desc_w0, stage * ST_W_BYTES);
+        const bool last_of_ch = (t + 1 == t1) || ((t + 1) / n_vt != ch);
+        if (elect_one()) {
+          // five K = 16 steps, (W window, A window) as in the table at the top; a window is 32 B = 2 units
+          tc_mma_f16(d_tmem, w_desc + 0, a_desc + 0, idesc, 0);
+          tc_mma_f16(d_tmem, w_desc + 2, a_desc + 2, idesc, 1);
+          tc_mma_f16(d_tmem, w_desc + 0, a_desc + 4, idesc, 1);
+          tc_mma_f16(d_tmem, w_desc + 4, a_desc + 0, idesc, 1);
+          tc_mma_f16(d_tmem, w_desc + 6, a_desc + 2, idesc, 1);
+          tc_commit(empty_a + 8 * stage);
+          tc_commit(tmem_full + 8 * acc);
+          if (last_of_ch) tc_commit(empty_w);
+        }
+        __syncwarp();
         if (++stage == ST_ASTAGES) {
           stage = 0;
           phase ^= 1;

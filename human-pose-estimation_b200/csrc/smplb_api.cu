@@ -583,16 +583,44 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
   smplb_set_error("unknown debug key %s", key);
   return SMPLB_EINVAL;
 }
+// on = 1: per-kernel times (everything on one stream, so the events bracket one kernel each);
+// on = 2: timeline trace -- the streams keep overlapping and smplb_profile_read returns one
+// "name start_ms end_ms" line per launch, relative to a process-wide reference event, so the traces
+// of several contexts of a device can be laid side by side (tools/timeline.py).
+static cudaEvent_t g_trace_ref = nullptr;
 extern "C" int smplb_profile_enable(smplb_ctx *c, int on) {
   RET_IF(!c, SMPLB_EINVAL, "null context");
   c->profile = on != 0;
-  c->profile_serial = on != 0;   // per-kernel events are only meaningful without stream overlap
+  c->profile_serial = on == 1;   // per-kernel events are only meaningful without stream overlap
+  c->profile_trace = on == 2;
+  if (on == 2 && !g_trace_ref) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventCreate(&g_trace_ref));
+    CUDA_TRY(cudaEventRecord(g_trace_ref, c->stream));
+  }
   return 0;
 }
 extern "C" int smplb_profile_read(smplb_ctx *c, char *buf, size_t buflen) {
   CHECK_CTX(c);
   RET_IF(!buf || buflen == 0, SMPLB_EINVAL, "null buffer");
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (c->stream2) CUDA_TRY(cudaStreamSynchronize(c->stream2));
+  if (c->profile_trace && g_trace_ref) {
+    std::string s;
+    char line[256];
+    for (auto &r : c->prof) {
+      float t0 = 0.f, t1 = 0.f;
+      cudaEventElapsedTime(&t0, g_trace_ref, r.e0);
+      cudaEventElapsedTime(&t1, g_trace_ref, r.e1);
+      snprintf(line, sizeof(line), "%s %.6f %.6f\n", r.name, t0, t1);
+      s += line;
+      c->event_pool.push_back(r.e0);
+      c->event_pool.push_back(r.e1);
+    }
+    c->prof.clear();
+    snprintf(buf, buflen, "%s", s.c_str());
+    return 0;
+  }
   std::map<std::string, std::pair<double, int>> acc;
   std::vector<std::string> order;
   for (auto &r : c->prof) {

@@ -151,6 +151,7 @@ struct smplb_ctx {
   int64_t launches = 0;
   bool profile = false;
   bool profile_serial = false;
+  bool profile_trace = false;      // smplb_profile_enable(ctx, 2): per-launch timeline instead of per-kernel sums
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
   // NCCL (dlopen'ed)

@@ -132,7 +132,19 @@ class Context(object):
         check(lib().smplb_debug_set(self.handle, key.encode(), int(value)))
 
     def profile(self, on):
-        check(lib().smplb_profile_enable(self.handle, 1 if on else 0))
+        """True / 1: per-kernel times (streams serialised); 2: timeline trace (profile_trace)."""
+        check(lib().smplb_profile_enable(self.handle, int(on)))
+
+    def profile_trace(self):
+        """[(name, start_ms, end_ms)] of every launch since profile(2), relative to a
+        process-wide reference event (comparable across the contexts of a device)."""
+        buf = C.create_string_buffer(1 << 20)
+        check(lib().smplb_profile_read(self.handle, buf, len(buf)))
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, t0, t1 = line.split()
+            out.append((name, float(t0), float(t1)))
+        return out
 
     def profile_read(self):
         buf = C.create_string_buffer(1 << 16)

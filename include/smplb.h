@@ -102,8 +102,8 @@ int smplb_timer_elapsed_ms(smplb_ctx *ctx, int slot, float *ms); /* synchronises
 int smplb_launch_count(smplb_ctx *ctx, int64_t *count);
 /* Per-kernel accumulated device time, measured with events around every launch when
  * enabled (debug/bench breakdown only; serialises nothing but adds event overhead). */
-int smplb_profile_enable(smplb_ctx *ctx, int on);
-int smplb_profile_read(smplb_ctx *ctx, char *buf, size_t buflen); /* "name ms count\n" lines; resets */
+int smplb_profile_enable(smplb_ctx *ctx, int on);   /* 1: per-kernel times (serialised streams); 2: timeline trace */
+int smplb_profile_read(smplb_ctx *ctx, char *buf, size_t buflen); /* "name ms count\n" lines (mode 2: "name start_ms end_ms" per launch); resets */
 /* Test hook: key "blend_tc" = 0 routes the blend contraction through the FP32 CUDA-core GEMM
  * that cross-checks the tcgen05 kernel (default 1); "skin_tc", "fold", "compact_bwd",
  * "overlap" likewise select cross-check paths; "keep_verts" see smplb_last_verts. */
