@@ -366,6 +366,140 @@ __global__ void __launch_bounds__(32 * FW_WARPS)
   }
 }
 
+// One generator step in one kernel (smplb_step with the keypoint loss only): forward (joints,
+// projection, loss partials) and backward (du, dA, d_cam) of the folded keypoint path read U and A
+// once.  The loss gradient is formed for a unit upstream scale -- the global 1 / num_present is
+// not known before the batch-wide reduction (and, across GPUs, the all-reduce) -- and
+// k_pose_bwd applies gscale / num_present to its outputs and to d_cam (everything in between is
+// linear), so the reduction runs beside the backward GEMM instead of in front of it.
+__global__ void __launch_bounds__(32 * FW_WARPS)
+    k_fold_step_w(int B, int K, int ldu, int nup, const float *__restrict__ U, const float *__restrict__ cc,
+                  const float *__restrict__ A, const float *__restrict__ cam, const float *__restrict__ kp_gt,
+                  float *__restrict__ joints, float *__restrict__ kp_pred, float *__restrict__ part,
+                  int *__restrict__ cnt, float *__restrict__ d_cam, float *__restrict__ dA, __half *__restrict__ du16,
+                  float *__restrict__ rowscale) {
+  __shared__ __align__(16) float sA[FW_WARPS][NJ * 12];
+  __shared__ float sdj[FW_WARPS][MAXK * 3];
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int b = blockIdx.x * FW_WARPS + w;
+  if (b >= B) return;
+  for (int i = lane; i < NJ * 12; i += 32) sA[w][i] = A[(size_t)b * NJ * 12 + i];
+  __syncwarp();
+  const float *Ub = U + (size_t)b * ldu;
+  const float s = cam[b * 3 + 0], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
+  // ---- forward, lane k owns keypoint k (k_fold_fwd_w)
+  float l = 0.f, gx = 0.f, gy = 0.f, as = 0.f;
+  int cn = 0;
+  if (lane < K) {
+    const float *u = Ub + (size_t)lane * NJ * 3;
+    const float *c = cc + lane * NJ;
+    float x = 0.f, y = 0.f, z = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < NJ; ++j) {
+      float u0 = u[3 * j], u1 = u[3 * j + 1], u2 = u[3 * j + 2], cj = c[j];
+      const float4 *a = reinterpret_cast<const float4 *>(sA[w] + j * 12);
+      float4 r0 = a[0], r1 = a[1], r2 = a[2];
+      x += fmaf(r0.x, u0, fmaf(r0.y, u1, fmaf(r0.z, u2, r0.w * cj)));
+      y += fmaf(r1.x, u0, fmaf(r1.y, u1, fmaf(r1.z, u2, r1.w * cj)));
+      z += fmaf(r2.x, u0, fmaf(r2.y, u1, fmaf(r2.z, u2, r2.w * cj)));
+    }
+    size_t bk = (size_t)b * K + lane;
+    joints[bk * 3 + 0] = x;
+    joints[bk * 3 + 1] = y;
+    joints[bk * 3 + 2] = z;
+    float px = s * (x + tx), py = s * (y + ty);
+    if (kp_pred) {
+      kp_pred[bk * 2 + 0] = px;
+      kp_pred[bk * 2 + 1] = py;
+    }
+    float gtx = kp_gt[bk * 3 + 0], gty = kp_gt[bk * 3 + 1], vis = kp_gt[bk * 3 + 2];
+    float dx = px - gtx, dy = py - gty;
+    l = vis * fabsf(dx) + vis * fabsf(dy);
+    cn = (vis != 0.0f) ? 2 : 0;
+    gx = vis * (float)((dx > 0.f) - (dx < 0.f));   // d loss / d kp_pred for a unit scale
+    gy = vis * (float)((dy > 0.f) - (dy < 0.f));
+    as = gx * (x + tx) + gy * (y + ty);
+    sdj[w][lane * 3 + 0] = s * gx;
+    sdj[w][lane * 3 + 1] = s * gy;
+    sdj[w][lane * 3 + 2] = 0.0f;
+  }
+  {
+    // fixed-order sums over the keypoints (every lane adds k = 0, 1, ... in turn)
+    float tl = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    int tc = 0;
+    for (int q = 0; q < K; ++q) {
+      tl += __shfl_sync(FULL, l, q);
+      tc += __shfl_sync(FULL, cn, q);
+      c0 += __shfl_sync(FULL, as, q);
+      c1 += __shfl_sync(FULL, gx, q);
+      c2 += __shfl_sync(FULL, gy, q);
+    }
+    if (lane == 0) {
+      part[b] = tl;
+      cnt[b] = tc;
+      d_cam[b * 3 + 0] = c0;          // unscaled; k_pose_bwd multiplies by gscale / num_present
+      d_cam[b * 3 + 1] = s * c1;
+      d_cam[b * 3 + 2] = s * c2;
+    }
+  }
+  __syncwarp();
+  // ---- backward, lane j owns joint j (k_fold_bwd_w): du_kj = A_R_j^T dj_k, dA_j = sum_k dj_k (x) [u_kj ; c_kj]
+  int j = lane < NJ ? lane : NJ - 1;
+  const float *a = sA[w] + j * 12;
+  float ar[9] = {a[0], a[1], a[2], a[4], a[5], a[6], a[8], a[9], a[10]};
+  const float *u = Ub + (size_t)j * 3;
+  float acc[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) acc[e] = 0.f;
+  float m = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float g0 = sdj[w][3 * k], g1 = sdj[w][3 * k + 1], g2 = sdj[w][3 * k + 2];
+    float du0 = ar[0] * g0 + ar[3] * g1 + ar[6] * g2;
+    float du1 = ar[1] * g0 + ar[4] * g1 + ar[7] * g2;
+    float du2 = ar[2] * g0 + ar[5] * g1 + ar[8] * g2;
+    m = fmaxf(m, fmaxf(fabsf(du0), fmaxf(fabsf(du1), fabsf(du2))));
+    const float *uk = u + (size_t)k * NJ * 3;
+    float u4[4] = {uk[0], uk[1], uk[2], cc[k * NJ + j]};
+    float gg[3] = {g0, g1, g2};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int d = 0; d < 4; ++d) acc[4 * r + d] = fmaf(gg[r], u4[d], acc[4 * r + d]);
+  }
+  if (lane >= NJ) m = 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  // power-of-two scale that brings max |du| to [1, 2): exact to apply and to undo
+  int e = 0;
+  float inv = 1.0f, sc2 = 1.0f;
+  if (m > 0.f && isfinite(m)) {
+    frexpf(m, &e);
+    inv = ldexpf(1.0f, 1 - e);
+    sc2 = ldexpf(1.0f, e - 1);
+  }
+  if (lane == 0) rowscale[b] = sc2;
+  if (lane < NJ) {
+    float *o = dA + ((size_t)b * NJ + j) * 12;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) o[q] = acc[q];
+    __half *row = du16 + (size_t)b * (3 * nup);
+    for (int k = 0; k < K; ++k) {
+      float g0 = sdj[w][3 * k], g1 = sdj[w][3 * k + 1], g2 = sdj[w][3 * k + 2];
+      float d3[3] = {(ar[0] * g0 + ar[3] * g1 + ar[6] * g2) * inv, (ar[1] * g0 + ar[4] * g1 + ar[7] * g2) * inv,
+                     (ar[2] * g0 + ar[5] * g1 + ar[8] * g2) * inv};
+      int n = (k * NJ + j) * 3;
+#pragma unroll
+      for (int cI = 0; cI < 3; ++cI) {
+        __half hi = __float2half_rn(d3[cI]);
+        __half lo = __float2half_rn(d3[cI] - __half2float(hi));
+        row[n + cI] = hi;
+        row[nup + n + cI] = lo;
+        row[2 * nup + n + cI] = hi;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------- host
 int tc_make_map(void *map, int is_f32, void *ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                 uint32_t box_inner, uint32_t box_outer);
@@ -454,6 +588,18 @@ int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, 
     LAUNCH(c, "fold_bwd_du_dA_cta", B, 32 * c->K, 0, k_fold_bwd, B, c->K, c->fold_nup, c->fold_nup, c->ws_U, c->d_cc, A,
            d_joints, dA_part, (__half *)c->ws_du16, c->ws_rowscale);
   }
+  TRY(launch_gemm_tc(c, "fold_gemm_dx", B, KX, 3 * c->fold_nup, c->ws_du16, c->map_g2, dx_part, KX, ksplit,
+                     c->fold_inv_scale));
+  return 0;
+}
+
+// Forward + backward of the folded keypoint path in one kernel, then dx = du G (see k_fold_step_w:
+// all gradients are for a unit loss scale; launch_pose_bwd applies gscale / num_present).
+int launch_fold_step(smplb_ctx *c, int B, const float *A, const float *cam, const float *kp_gt, float *joints,
+                     float *kp_pred, float *part, int *cnt, float *d_cam, float *dA_part, float *dx_part, int ksplit) {
+  RET_IF(!c->fold_ok, SMPLB_ESTATE, "folded keypoint path is not initialised");
+  LAUNCH(c, "fold_step_fwd_bwd", cdiv(B, FW_WARPS), 32 * FW_WARPS, 0, k_fold_step_w, B, c->K, c->fold_nup, c->fold_nup, c->ws_U,
+         c->d_cc, A, cam, kp_gt, joints, kp_pred, part, cnt, d_cam, dA_part, (__half *)c->ws_du16, c->ws_rowscale);
   TRY(launch_gemm_tc(c, "fold_gemm_dx", B, KX, 3 * c->fold_nup, c->ws_du16, c->map_g2, dx_part, KX, ksplit,
                      c->fold_inv_scale));
   return 0;

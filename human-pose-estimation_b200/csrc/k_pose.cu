@@ -251,12 +251,21 @@ __global__ void __launch_bounds__(32 * PB_WARPS)
                const float *__restrict__ Jin, const float *__restrict__ A, const float *__restrict__ dA_part,
                int n_dA_parts, const float *__restrict__ dx_part, int ksplit, int dx_rows,
                const float *__restrict__ rowscale, const float *__restrict__ d_Rs,
-               const float *__restrict__ Jdirs, float *__restrict__ d_beta, float *__restrict__ d_theta) {
+               const float *__restrict__ Jdirs, float *__restrict__ d_beta, float *__restrict__ d_theta,
+               const long long *__restrict__ den, float gscale, float *__restrict__ d_cam) {
   __shared__ PoseBwdSmem sm[PB_WARPS];
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int b = blockIdx.x * PB_WARPS + w;
   if (b >= B) return;
   PoseBwdSmem &S = sm[w];
+  // Deferred loss scale (k_fold_step_w): dA, dx and d_cam arrive for a unit upstream scale and
+  // everything below is linear in them, so gscale / num_present is applied to the outputs.
+  float osc = 1.0f;
+  if (den) {
+    long long dv = *den;
+    osc = dv > 0 ? gscale / (float)dv : 0.0f;
+    if (d_cam && lane < 3) d_cam[(size_t)b * 3 + lane] *= osc;
+  }
   if (lane < NJ) {
     int j = lane;
     float dA[12];
@@ -339,9 +348,9 @@ __global__ void __launch_bounds__(32 * PB_WARPS)
     const float *th = theta + (size_t)b * 72 + 3 * j;
     float dth[3];
     rodrigues_bwd(th[0], th[1], th[2], G, dth);
-    d_theta[(size_t)b * 72 + 3 * j + 0] = dth[0];
-    d_theta[(size_t)b * 72 + 3 * j + 1] = dth[1];
-    d_theta[(size_t)b * 72 + 3 * j + 2] = dth[2];
+    d_theta[(size_t)b * 72 + 3 * j + 0] = dth[0] * osc;
+    d_theta[(size_t)b * 72 + 3 * j + 1] = dth[1] * osc;
+    d_theta[(size_t)b * 72 + 3 * j + 2] = dth[2] * osc;
   }
   if (lane < NB) {
     // d beta = Jdirs^T dJ + (dp . shapedirs^T), the latter from the blend backward GEMM
@@ -349,7 +358,7 @@ __global__ void __launch_bounds__(32 * PB_WARPS)
     for (int ks = 0; ks < ksplit; ++ks) acc += dx_part[((size_t)ks * dx_rows + b) * KX + NPF + lane];
     if (rowscale) acc *= rowscale[b];
     for (int jc = 0; jc < NJ * 3; ++jc) acc = fmaf(Jdirs[(size_t)jc * NB + lane], S.dJ[jc / 3][jc % 3], acc);
-    d_beta[(size_t)b * NB + lane] = acc;
+    d_beta[(size_t)b * NB + lane] = acc * osc;
   }
 }
 
@@ -437,9 +446,10 @@ int launch_pose_fwd(smplb_ctx *c, int B, const float *beta, const float *theta, 
 
 int launch_pose_bwd(smplb_ctx *c, int B, const float *theta, const float *Rs, const float *J, const float *A,
                     const float *dA_part, int n_dA_parts, const float *dx_part, int ksplit, int dx_rows,
-                    const float *rowscale, const float *d_Rs, float *d_beta, float *d_theta) {
+                    const float *rowscale, const float *d_Rs, float *d_beta, float *d_theta, const long long *den,
+                    float gscale, float *d_cam) {
   LAUNCH(c, "pose_bwd", cdiv(B, PB_WARPS), 32 * PB_WARPS, 0, k_pose_bwd, B, c->NB, c->tree, theta, Rs, J, A, dA_part,
-         n_dA_parts, dx_part, ksplit, dx_rows, rowscale, d_Rs, c->d_Jdirs, d_beta, d_theta);
+         n_dA_parts, dx_part, ksplit, dx_rows, rowscale, d_Rs, c->d_Jdirs, d_beta, d_theta, den, gscale, d_cam);
   return 0;
 }
 

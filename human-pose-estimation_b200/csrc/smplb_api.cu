@@ -568,6 +568,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->l2_chunk = value;
     return 0;
   }
+  if (!strcmp(key, "fold_step")) {
+    c->use_fold_step = value;
+    return 0;
+  }
   if (!strcmp(key, "fused")) {
     c->use_fused = value;
     return 0;
@@ -656,7 +660,7 @@ static int join_verts(smplb_ctx *c) {
 
 static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float *theta, float *verts, float *joints,
                             float *Rs, float *Jtr, const float *cam, const float *kp_gt, float *kp_pred,
-                            bool need_verts, bool want_vposed = false) {
+                            bool need_verts, bool want_vposed = false, float *step_d_cam = nullptr) {
   TRY(ensure_ws(c, B));
   CUDA_TRY(cudaMemcpyAsync(c->ws_beta, beta, (size_t)B * c->NB * 4, cudaMemcpyDeviceToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->ws_theta, theta, (size_t)B * 72 * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -723,7 +727,13 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   c->saved_verts = vout;
   float *jout = joints ? joints : c->ws_joints;
   c->saved_fold = fold;
-  if (fold) {
+  c->saved_fold_step = false;
+  if (fold && step_d_cam && cam && kp_gt && c->fold_warp_kernels && c->use_fold_step) {
+    // smplb_step with the keypoint loss only: forward and backward of the folded path in one
+    // kernel + the dx GEMM; gradients for a unit loss scale (k_pose_bwd applies w_kp / num_present)
+    TRY(launch_fold_step(c, B, c->ws_A, cam, kp_gt, jout, kp_pred, c->ws_part, c->ws_cnt, step_d_cam, c->ws_dA, c->ws_dx, 2));
+    c->saved_fold_step = true;
+  } else if (fold) {
     // joints from x and A alone (k_fold.cu): one small GEMM + a per-body contraction
     TRY(launch_fold_fwd(c, B, c->ws_x16b, c->ws_A, cam, kp_gt, jout, kp_pred, kp_gt ? c->ws_dkp : nullptr,
                         kp_gt ? c->ws_part : nullptr, kp_gt ? c->ws_cnt : nullptr));
@@ -1110,7 +1120,8 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
 
   float *jbuf = ojoints ? ojoints : c->ws_joints;
   TRY(smpl_forward_dev(c, B, dbeta, dtheta, overts, jbuf, oRs, nullptr, dcam, dkpgt, okp ? okp : c->ws_kp,
-                       overts != nullptr || have_mesh, /*want_vposed=*/have_mesh && bwd));
+                       overts != nullptr || have_mesh, /*want_vposed=*/have_mesh && bwd,
+                       /*step_d_cam=*/(bwd && !have_mesh) ? odc : nullptr));
   const float *vbuf = c->saved_verts;
   bool comm = c->nccl_comm && c->nranks > 1;
   if (!have_mesh && !comm) {
@@ -1130,7 +1141,13 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
     }
     TRY(launch_finalize_loss(c, w_kp, w_mesh, (long long)kp_count_override, have_mesh ? 1 : 0, oloss));
   }
-  if (bwd) {
+  if (bwd && c->saved_fold_step) {
+    // the forward ran k_fold_step_w + the dx GEMM; the loss reduction above supplied num_present
+    RET_IF(c->saved_B != B, SMPLB_ESTATE, "internal: forward state lost");
+    int rows = cdiv(B, 128) * 128;
+    TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, 1, c->ws_dx, 2, rows, c->ws_rowscale, nullptr,
+                        odb, odt, c->ws_cnt64, w_kp, odc));
+  } else if (bwd) {
     if (!have_mesh && c->saved_fold && c->fold_warp_kernels) {
       // keypoint-only backward: d kp loss -> d joints, d cam, du, dA in one kernel, then the GEMM
       RET_IF(c->saved_B != B, SMPLB_ESTATE, "internal: forward state lost");

@@ -89,6 +89,8 @@ struct smplb_ctx {
   float *ws_rowscale = nullptr;    // [B]
   void *ws_x16b = nullptr;         // [B][704] fp16: x_hi | x_hi | x_lo | 0
   bool saved_fold = false;
+  bool saved_fold_step = false;    // the forward already ran the fused keypoint forward + backward (k_fold_step_w)
+  int use_fold_step = 1;           // smplb_debug_set("fold_step", 0): separate forward / backward kernels
   int fold_warp_kernels = 1;       // smplb_debug_set("fold_warp", 0): CTA-per-body reference kernels
   // ---- tcgen05 blend path (k_blend_tc.cu)
   bool tc_ok = false;          // operands built, tensor map encoded
@@ -217,7 +219,8 @@ int launch_pose_fwd(smplb_ctx *c, int B, const float *beta, const float *theta, 
                     float *Jtr, float *x, void *x16, void *A16, void *x16b);
 int launch_pose_bwd(smplb_ctx *c, int B, const float *theta, const float *Rs, const float *J, const float *A,
                     const float *dA_part, int n_dA_parts, const float *dx_part, int ksplit, int dx_rows,
-                    const float *rowscale, const float *d_Rs, float *d_beta, float *d_theta);
+                    const float *rowscale, const float *d_Rs, float *d_beta, float *d_theta,
+                    const long long *den = nullptr, float gscale = 1.0f, float *d_cam = nullptr);
 int launch_rodrigues(smplb_ctx *c, int N, const float *theta, float *R);
 int launch_global_rigid(smplb_ctx *c, int B, const float *Rs, const float *Js, float *new_J, float *A44);
 int launch_skew(smplb_ctx *c, int N, const float *vec, float *out);
@@ -236,6 +239,8 @@ int launch_fold_fwd(smplb_ctx *c, int B, const void *x16b, const float *A, const
 int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, const float *dkp, const float *joints,
                     const float *cam, float gscale, const long long *den, float *d_cam, float *dA_part, float *dx_part,
                     int ksplit);
+int launch_fold_step(smplb_ctx *c, int B, const float *A, const float *cam, const float *kp_gt, float *joints,
+                     float *kp_pred, float *part, int *cnt, float *d_cam, float *dA_part, float *dx_part, int ksplit);
 int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long long count_override, float *loss_parts);
 // k_skin_tc.cu
 int skin_tc_init(smplb_ctx *c);

@@ -406,6 +406,29 @@ def test_fused_blend_skinning_matches_two_kernel_path(smpl_full, full_model):
         assert rel_err(a, b) < 2e-6
 
 
+def test_fused_keypoint_forward_backward_matches_separate_kernels(smpl_full):
+    """k_fold_step_w (forward + backward of the folded keypoint path in one kernel, gradients formed
+    for a unit loss scale and scaled by w_kp / num_present in k_pose_bwd) against the separate
+    kernels, including the all-invisible sample, a count override (the multi-GPU shard case) and a
+    non-default loss weight."""
+    inp = synthetic.make_inputs(150, seed=2024)
+    ctx = smpl_full.ctx
+    for kw in ({}, {"kp_count_override": 12345}, {"w_kp": 7.5}):
+        a = {k: np.array(v) for k, v in smpl_full.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"], **kw).items()}
+        try:
+            ctx.debug_set("fold_step", 0)
+            b = {k: np.array(v) for k, v in smpl_full.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"], **kw).items()}
+        finally:
+            ctx.debug_set("fold_step", 1)
+        for k in ("joints", "kp_pred", "verts", "Rs"):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a["loss_parts"][:2], b["loss_parts"][:2])
+        assert abs(a["loss_parts"][3] - b["loss_parts"][3]) <= 1e-6 * abs(b["loss_parts"][3])
+        for k in ("d_beta", "d_theta", "d_cam"):
+            assert rel_err(a[k], b[k]) < 2e-6, (k, kw)
+        assert not a["d_theta"][1].any() and not a["d_cam"][1].any()     # sample 1 has no visible keypoint
+
+
 def test_folded_keypoint_path_matches_per_vertex_path(smpl_full):
     """joints / kp loss / gradients from the folded formulation (G x, no vertices) against the
     per-vertex keypoint path; both are checked against the oracle elsewhere, this pins them to
