@@ -372,26 +372,40 @@ __global__ void __launch_bounds__(32 * FW_WARPS)
 // not known before the batch-wide reduction (and, across GPUs, the all-reduce) -- and
 // k_pose_bwd applies gscale / num_present to its outputs and to d_cam (everything in between is
 // linear), so the reduction runs beside the backward GEMM instead of in front of it.
-__global__ void __launch_bounds__(32 * FW_WARPS)
+#define FS_WARPS 4
+#define FS_MAXU 1536   // floats of one U row staged per warp (3 * 24 * K rounded up to 128; K <= 21)
+__global__ void __launch_bounds__(32 * FS_WARPS)
     k_fold_step_w(int B, int K, int ldu, int nup, const float *__restrict__ U, const float *__restrict__ cc,
                   const float *__restrict__ A, const float *__restrict__ cam, const float *__restrict__ kp_gt,
                   float *__restrict__ joints, float *__restrict__ kp_pred, float *__restrict__ part,
                   int *__restrict__ cnt, float *__restrict__ d_cam, float *__restrict__ dA, __half *__restrict__ du16,
                   float *__restrict__ rowscale) {
-  __shared__ __align__(16) float sA[FW_WARPS][NJ * 12];
-  __shared__ float sdj[FW_WARPS][MAXK * 3];
+  __shared__ __align__(16) float sU[FS_WARPS][FS_MAXU];
+  __shared__ __align__(16) float sA[FS_WARPS][NJ * 12];
+  __shared__ float sdj[FS_WARPS][MAXK * 3];
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int b = blockIdx.x * FW_WARPS + w;
+  int b = blockIdx.x * FS_WARPS + w;
   if (b >= B) return;
-  for (int i = lane; i < NJ * 12; i += 32) sA[w][i] = A[(size_t)b * NJ * 12 + i];
+  // The kernel is a chain of dependent global loads if U is read where it is used (one latency per
+  // joint / keypoint iteration): stage the body's U row (5.5 KB) and A with independent vector
+  // loads first, then both phases run out of shared memory.
+  {
+    const float4 *src = reinterpret_cast<const float4 *>(U + (size_t)b * ldu);
+    float4 *dst = reinterpret_cast<float4 *>(sU[w]);
+    const int n4 = (K * NJ * 3 + 3) / 4;
+    for (int i = lane; i < n4; i += 32) dst[i] = src[i];
+    const float4 *asrc = reinterpret_cast<const float4 *>(A + (size_t)b * NJ * 12);
+    float4 *adst = reinterpret_cast<float4 *>(sA[w]);
+    for (int i = lane; i < NJ * 3; i += 32) adst[i] = asrc[i];
+  }
   __syncwarp();
-  const float *Ub = U + (size_t)b * ldu;
+  const float *Ub = sU[w];
   const float s = cam[b * 3 + 0], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
   // ---- forward, lane k owns keypoint k (k_fold_fwd_w)
   float l = 0.f, gx = 0.f, gy = 0.f, as = 0.f;
   int cn = 0;
   if (lane < K) {
-    const float *u = Ub + (size_t)lane * NJ * 3;
+    const float *u = Ub + lane * NJ * 3;
     const float *c = cc + lane * NJ;
     float x = 0.f, y = 0.f, z = 0.f;
 #pragma unroll 4
@@ -447,18 +461,19 @@ __global__ void __launch_bounds__(32 * FW_WARPS)
   int j = lane < NJ ? lane : NJ - 1;
   const float *a = sA[w] + j * 12;
   float ar[9] = {a[0], a[1], a[2], a[4], a[5], a[6], a[8], a[9], a[10]};
-  const float *u = Ub + (size_t)j * 3;
+  const float *u = Ub + j * 3;
   float acc[12];
 #pragma unroll
   for (int e = 0; e < 12; ++e) acc[e] = 0.f;
   float m = 0.f;
+#pragma unroll 4
   for (int k = 0; k < K; ++k) {
     float g0 = sdj[w][3 * k], g1 = sdj[w][3 * k + 1], g2 = sdj[w][3 * k + 2];
     float du0 = ar[0] * g0 + ar[3] * g1 + ar[6] * g2;
     float du1 = ar[1] * g0 + ar[4] * g1 + ar[7] * g2;
     float du2 = ar[2] * g0 + ar[5] * g1 + ar[8] * g2;
     m = fmaxf(m, fmaxf(fabsf(du0), fmaxf(fabsf(du1), fabsf(du2))));
-    const float *uk = u + (size_t)k * NJ * 3;
+    const float *uk = u + k * NJ * 3;
     float u4[4] = {uk[0], uk[1], uk[2], cc[k * NJ + j]};
     float gg[3] = {g0, g1, g2};
 #pragma unroll
@@ -482,20 +497,32 @@ __global__ void __launch_bounds__(32 * FW_WARPS)
     float *o = dA + ((size_t)b * NJ + j) * 12;
 #pragma unroll
     for (int q = 0; q < 12; ++q) o[q] = acc[q];
-    __half *row = du16 + (size_t)b * (3 * nup);
+  }
+  // du16 row = hi | lo | hi (three blocks of nup halves): stage the fp32 values in the U buffer
+  // (no longer needed) and write the row with coalesced 4-byte stores instead of 2-byte
+  // stores 144 B apart
+  __syncwarp();
+  if (lane < NJ) {
     for (int k = 0; k < K; ++k) {
       float g0 = sdj[w][3 * k], g1 = sdj[w][3 * k + 1], g2 = sdj[w][3 * k + 2];
-      float d3[3] = {(ar[0] * g0 + ar[3] * g1 + ar[6] * g2) * inv, (ar[1] * g0 + ar[4] * g1 + ar[7] * g2) * inv,
-                     (ar[2] * g0 + ar[5] * g1 + ar[8] * g2) * inv};
       int n = (k * NJ + j) * 3;
-#pragma unroll
-      for (int cI = 0; cI < 3; ++cI) {
-        __half hi = __float2half_rn(d3[cI]);
-        __half lo = __float2half_rn(d3[cI] - __half2float(hi));
-        row[n + cI] = hi;
-        row[nup + n + cI] = lo;
-        row[2 * nup + n + cI] = hi;
-      }
+      sU[w][n + 0] = (ar[0] * g0 + ar[3] * g1 + ar[6] * g2) * inv;
+      sU[w][n + 1] = (ar[1] * g0 + ar[4] * g1 + ar[7] * g2) * inv;
+      sU[w][n + 2] = (ar[2] * g0 + ar[5] * g1 + ar[8] * g2) * inv;
+    }
+  }
+  __syncwarp();
+  {
+    __half2 *row = reinterpret_cast<__half2 *>(du16 + (size_t)b * (3 * nup));
+    const int nu = K * NJ * 3, half_nup = nup / 2;
+    for (int i = lane; i < half_nup; i += 32) {
+      float v0 = 2 * i < nu ? sU[w][2 * i] : 0.f, v1 = 2 * i + 1 < nu ? sU[w][2 * i + 1] : 0.f;
+      __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+      __half2 hi = __halves2half2(h0, h1);
+      __half2 lo = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+      row[i] = hi;
+      row[half_nup + i] = lo;
+      row[2 * half_nup + i] = hi;
     }
   }
 }
@@ -598,7 +625,8 @@ int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, 
 int launch_fold_step(smplb_ctx *c, int B, const float *A, const float *cam, const float *kp_gt, float *joints,
                      float *kp_pred, float *part, int *cnt, float *d_cam, float *dA_part, float *dx_part, int ksplit) {
   RET_IF(!c->fold_ok, SMPLB_ESTATE, "folded keypoint path is not initialised");
-  LAUNCH(c, "fold_step_fwd_bwd", cdiv(B, FW_WARPS), 32 * FW_WARPS, 0, k_fold_step_w, B, c->K, c->fold_nup, c->fold_nup, c->ws_U,
+  RET_IF(c->K * NJ * 3 > FS_MAXU, SMPLB_EINVAL, "too many keypoints for k_fold_step_w");
+  LAUNCH(c, "fold_step_fwd_bwd", cdiv(B, FS_WARPS), 32 * FS_WARPS, 0, k_fold_step_w, B, c->K, c->fold_nup, c->fold_nup, c->ws_U,
          c->d_cc, A, cam, kp_gt, joints, kp_pred, part, cnt, d_cam, dA_part, (__half *)c->ws_du16, c->ws_rowscale);
   TRY(launch_gemm_tc(c, "fold_gemm_dx", B, KX, 3 * c->fold_nup, c->ws_du16, c->map_g2, dx_part, KX, ksplit,
                      c->fold_inv_scale));

@@ -728,7 +728,7 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   float *jout = joints ? joints : c->ws_joints;
   c->saved_fold = fold;
   c->saved_fold_step = false;
-  if (fold && step_d_cam && cam && kp_gt && c->fold_warp_kernels && c->use_fold_step) {
+  if (fold && step_d_cam && cam && kp_gt && c->fold_warp_kernels && c->use_fold_step && c->K * NJ * 3 <= 1536) {
     // smplb_step with the keypoint loss only: forward and backward of the folded path in one
     // kernel + the dx GEMM; gradients for a unit loss scale (k_pose_bwd applies w_kp / num_present)
     TRY(launch_fold_step(c, B, c->ws_A, cam, kp_gt, jout, kp_pred, c->ws_part, c->ws_cnt, step_d_cam, c->ws_dA, c->ws_dx, 2));
