@@ -102,6 +102,25 @@ __device__ __forceinline__ void chain_fwd(const Tree &tree, int lane, const floa
   }
 }
 
+struct __align__(16) PoseFwdSmem {
+  float Rs[NJ * 9], J[NJ * 3], A[NJ * 12], Jtr[NJ * 3];
+  __half x16[256], A16[12 * 64], x16b[704];
+};
+
+// bytes (a multiple of 16) from shared to global memory with 16-byte stores; dst may be null
+__device__ __forceinline__ void copy_out16(int lane, void *dst, const void *src, int bytes) {
+  if (!dst) return;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) != 0) {   // a caller's oddly aligned buffer: 4-byte stores
+    const uint32_t *s1 = reinterpret_cast<const uint32_t *>(src);
+    uint32_t *d1 = reinterpret_cast<uint32_t *>(dst);
+    for (int i = lane; i < bytes / 4; i += 32) d1[i] = s1[i];
+    return;
+  }
+  const float4 *s4 = reinterpret_cast<const float4 *>(src);
+  float4 *d4 = reinterpret_cast<float4 *>(dst);
+  for (int i = lane; i < bytes / 16; i += 32) d4[i] = s4[i];
+}
+
 // One warp per body: theta -> Rs, pose_feature; beta -> J (folded regression
 // J = J0 + Jdirs beta, exact algebra for batch_smpl.py:110-118); chain -> A, J_transformed.
 // Also writes the blend GEMM operand row x = [pose_feature | beta | 1 | 0 ...].
@@ -112,9 +131,14 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
                                                   float *__restrict__ Jtr, float *__restrict__ x,
                                                   __half *__restrict__ x16, __half *__restrict__ A16,
                                                   __half *__restrict__ x16b) {
+  // Every output row of a body is staged in shared memory and written out with 16-byte stores:
+  // the 2- and 4-byte stores scattered over ~6 KB per body that this kernel used to issue cost 5x
+  // the DRAM write traffic of the data (partial sectors) and kept the LSU queues full (ncu).
+  __shared__ PoseFwdSmem sm[4];
   int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (b >= B) return;
+  PoseFwdSmem &S = sm[threadIdx.x >> 5];
   int j = lane < NJ ? lane : NJ - 1;
   bool act = lane < NJ;
   const float *th = theta + (size_t)b * 72 + 3 * j;
@@ -129,14 +153,10 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
     J[cc] = acc;
   }
   if (act) {
-    if (Rs) {
 #pragma unroll
-      for (int e = 0; e < 9; ++e) Rs[((size_t)b * NJ + j) * 9 + e] = R[e];
-    }
-    if (Jout) {
+    for (int e = 0; e < 9; ++e) S.Rs[j * 9 + e] = R[e];
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc) Jout[((size_t)b * NJ + j) * 3 + cc] = J[cc];
-    }
+    for (int cc = 0; cc < 3; ++cc) S.J[j * 3 + cc] = J[cc];
     if (x && j >= 1) {
       // pose_feature index (j-1)*9 + 3r + c (batch_smpl.py:126-127)
 #pragma unroll
@@ -146,7 +166,7 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
   if (x16) {
     // fp16 operand row of the tcgen05 blend GEMM (K map in k_blend_tc.cu): pose_feature,
     // beta_hi, beta_hi, beta_lo, three 1s (v_template hi/mid/lo), zero padding to 256.
-    __half *xr = x16 + (size_t)b * 256;
+    __half *xr = S.x16;
     if (act && j >= 1) {
 #pragma unroll
       for (int e = 0; e < 9; ++e)
@@ -170,7 +190,7 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
   if (x16b) {
     // operand row of the folded keypoint GEMM (k_fold.cu): x = [pose_feature | beta | 1 | 0..]
     // (224 wide) as x_hi | x_hi | x_lo | 0 (704 halves)
-    __half *xr = x16b + (size_t)b * 704;
+    __half *xr = S.x16b;
     if (act && j >= 1) {
 #pragma unroll
       for (int e = 0; e < 9; ++e) {
@@ -206,7 +226,7 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
   chain_fwd(tree, lane, R, J, G);
   if (act) {
     // A_j = [Rg | tg - Rg J_j]  (batch_lbs.py:146-150), J_transformed = tg (:140)
-    float *a = A + ((size_t)b * NJ + j) * 12;
+    float *a = S.A + j * 12;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       a[4 * r + 0] = G[3 * r + 0];
@@ -214,15 +234,13 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
       a[4 * r + 2] = G[3 * r + 2];
       a[4 * r + 3] = G[9 + r] - (G[3 * r + 0] * J[0] + G[3 * r + 1] * J[1] + G[3 * r + 2] * J[2]);
     }
-    if (Jtr) {
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc) Jtr[((size_t)b * NJ + j) * 3 + cc] = G[9 + cc];
-    }
+    for (int cc = 0; cc < 3; ++cc) S.Jtr[j * 3 + cc] = G[9 + cc];
     if (A16) {
       // fp16 split operand of the tcgen05 skinning GEMM (k_skin_tc.cu): row (b, e = 4r + d), one
       // 64-column swizzle atom laid out in 16-column windows (see the window table there):
       //   [A_hi 0..15] [A_hi 16..23 | A_lo 16..23] [A_lo 0..15] [0]
-      __half *rowbase = A16 + (size_t)b * 12 * 64;
+      __half *rowbase = S.A16;
       const int col_lo = j < 16 ? 32 + j : j + 8;
 #pragma unroll
       for (int e = 0; e < 12; ++e) {
@@ -234,6 +252,18 @@ __global__ void __launch_bounds__(128) k_pose_fwd(int B, int NB, Tree tree, cons
       }
     }
   }
+  if (A16) {
+    // zero padding columns 48..63 of the 12 operand rows
+    for (int i = lane; i < 12 * 16; i += 32) S.A16[(i / 16) * 64 + 48 + (i % 16)] = __float2half_rn(0.f);
+  }
+  __syncwarp();
+  copy_out16(lane, Rs ? Rs + (size_t)b * NJ * 9 : nullptr, S.Rs, NJ * 9 * 4);
+  copy_out16(lane, Jout ? Jout + (size_t)b * NJ * 3 : nullptr, S.J, NJ * 3 * 4);
+  copy_out16(lane, A + (size_t)b * NJ * 12, S.A, NJ * 12 * 4);
+  copy_out16(lane, Jtr ? Jtr + (size_t)b * NJ * 3 : nullptr, S.Jtr, NJ * 3 * 4);
+  copy_out16(lane, x16 ? x16 + (size_t)b * 256 : nullptr, S.x16, 256 * 2);
+  copy_out16(lane, A16 ? A16 + (size_t)b * 12 * 64 : nullptr, S.A16, 12 * 64 * 2);
+  copy_out16(lane, x16b ? x16b + (size_t)b * 704 : nullptr, S.x16b, 704 * 2);
 }
 
 // Backward of the per-body stage.  One warp per body; the reverse chain walks joints 23..1
