@@ -18,13 +18,16 @@
 // shapes are chosen to keep the instruction count per sample low under the 512-column TMEM
 // budget: 3 * NS (P) + TBUF * 12 * ST (T) <= 512.
 //
-// What bounds it (tools/fused_timing.py builds, profiles/r01/v7_*): shared-memory bandwidth.  An
-// SS-mode MMA with N = 96 reads 4 KB of "A" and 3 KB of "B" per K-step, 56 clk at 128 B/clk -- already
-// longer than its 48 clk on the tensor pipe -- and every operand byte also enters shared memory
-// through TMA: ~1.1 MB of shared-memory traffic per super-tile, ~8.5 k clk of the ~13 k it takes.
-// Tried and measured slower or equal: a second set of epilogue warps, a software-pipelined
-// (two register sets) epilogue, N = 192 skinning MMAs with a single T stage, plain instead of
-// evict-first stores (+5 %).
+// What bounds it (tools/fused_timing.py builds, profiles/r01/v7_*): the hand-shake chain of a
+// skinning tile -- T stage released -> issuer wakes -> 5 MMAs through the tensor pipe -> commit ->
+// epilogue wakes -> tcgen05.ld -> release -- is ~1000-1200 clk long and only two T stages (next to the
+// 288 columns of P) fit in TMEM, so a tile retires every ~600 clk whatever the MMAs cost: a build
+// without any MMA is as fast as one without any epilogue work (161 k vs 165 k clk of 204 k), and
+// the stores add the rest.  Shared-memory traffic (~1.1 MB per super-tile, 8.5 k clk at 128 B/clk
+// of the ~13 k) is the next limit, not the current one: moving the W16 operand to TMEM (k_body_wt
+// below) changed nothing.  Also measured equal or slower: a second set of epilogue warps, a
+// software-pipelined (two register sets) epilogue, N = 192 skinning MMAs with a single T stage,
+// plain instead of evict-first stores (+5 %).
 //
 // Persistent, warp-specialised: warp 0 TMA producer of the blend operands, warp 1 blend MMA issuer
 // and TMEM allocator, warp 2 TMA producer of the skinning operands, warp 3 skinning MMA issuer,
@@ -421,6 +424,340 @@ __global__ void __launch_bounds__(C::THREADS, 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Variant with the W16 tile as a TMEM-resident "A" operand (tcgen05.mma with A in tensor memory);
+// smplb_debug_set("fused", 5).  Measured equal to k_body_tc (127.0 vs 127.8 us), so it is not the
+// default; it stays as the tested reference for TS-mode MMAs and tcgen05.st in this code base.
+// In k_body_tc the skinning MMAs re-read the 16 KB W16 tile from shared memory for every one of
+// their 60 K-steps per super-tile (240 KB of the ~1.1 MB of shared-memory traffic that bounds the
+// kernel).  A W16 row is 64 fp16 = 32 TMEM columns -- exactly what 3 * 96 + 2 * 96 leaves free -- so
+// the epilogue threads (thread = vertex = TMEM lane) copy their row there with tcgen05.st whenever
+// the vertex tile changes.  To make that rare the super-tiles are ordered vertex-tile major (a CTA
+// walks ~16 consecutive sample blocks of one vertex tile) and the x16 tile, which now changes every
+// super-tile, is double-buffered in the space the W16 ring used.
+struct BodyW {
+  static constexpr int NS = 96, ST = 8, TBUF = 2, DSTAGES = 4, ASTAGES = 3, PRE = 4;
+  static constexpr int TN = 12 * ST, NT = NS / ST;
+  static constexpr int X_KB_BYTES = NS * 128, X_BYTES = 4 * X_KB_BYTES;
+  static constexpr int A_BYTES = TN * 128;
+  static constexpr int SM_X = 0;                                  // two x16 tiles
+  static constexpr int SM_D = SM_X + 2 * X_BYTES;
+  static constexpr int SM_A = SM_D + DSTAGES * FB_D_BYTES;
+  static constexpr int SM_BAR = SM_A + ASTAGES * A_BYTES;
+  static constexpr int SM_TOTAL = SM_BAR + 256;
+  static constexpr int TCOL = 3 * NS;                             // T stages
+  static constexpr int WCOL = TCOL + TBUF * TN;                   // W16 tile: 32 columns
+  static constexpr int THREADS = 32 * 12;
+  static_assert(WCOL + 32 <= 512, "TMEM budget");
+  static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+};
+
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns from registers: thread i writes row (lane base + i)
+__device__ __forceinline__ void tc_st_32x16(uint32_t taddr, const uint32_t *r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(BodyW::THREADS, 1)
+    k_body_wt(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_d,
+              const __grid_constant__ CUtensorMap map_a, const uint4 *__restrict__ W16, int B, int V, int Vp, int n_vt,
+              int n_m, float inv_scale, float *__restrict__ verts) {
+  using C = BodyW;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + C::SM_BAR;
+  const uint32_t full_x = bar0 + 0, empty_x = bar0 + 16;      // 2 each
+  const uint32_t full_d = bar0 + 32, empty_d = bar0 + 64;     // DSTAGES (<= 4) each
+  const uint32_t p_full = bar0 + 96, p_empty = bar0 + 104, w_ready = bar0 + 112;
+  const uint32_t full_a = bar0 + 128, empty_a = bar0 + 160;   // ASTAGES (<= 4) each
+  const uint32_t t_full = bar0 + 192, t_empty = bar0 + 208;   // TBUF (<= 2) each
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + C::SM_BAR + 224);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = n_vt * n_m;
+  const int t0 = (int)(((long long)blockIdx.x * total) / gridDim.x);
+  const int t1 = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(full_x + 8 * i, 1);
+      mbar_init(empty_x + 8 * i, 1);
+    }
+    mbar_init(p_full, 1);
+    mbar_init(p_empty, 8);                 // one arrival per epilogue warp
+    mbar_init(w_ready, 8);
+    for (int i = 0; i < C::DSTAGES; ++i) {
+      mbar_init(full_d + 8 * i, 1);
+      mbar_init(empty_d + 8 * i, 1);
+    }
+    for (int i = 0; i < C::ASTAGES; ++i) {
+      mbar_init(full_a + 8 * i, 1);
+      mbar_init(empty_a + 8 * i, 1);
+    }
+    for (int i = 0; i < C::TBUF; ++i) {
+      mbar_init(t_full + 8 * i, 1);
+      mbar_init(t_empty + 8 * i, 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::SM_BAR + 224), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // super-tile t -> vertex tile t / n_m, sample block t % n_m
+  if (warp == 0) {
+    // =========================== blend operand producer ===========================
+    if (lane == 0) {
+      int stage = 0, phase = 0, n_tiles = 0;
+      for (int t = t0; t < t1; ++t, ++n_tiles) {
+        const int vt = t / n_m, m = t % n_m;
+        const int xb = n_tiles & 1;
+        mbar_wait(empty_x + 8 * xb, ((n_tiles >> 1) & 1) ^ 1);
+        mbar_expect_tx(full_x + 8 * xb, C::X_BYTES);
+        for (int kb = 0; kb < 4; ++kb)
+          tma_load_2d(sbase + C::SM_X + xb * C::X_BYTES + kb * C::X_KB_BYTES, &map_x, kb * 64, m * C::NS, full_x + 8 * xb);
+        for (int cc = 0; cc < 3; ++cc)
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(empty_d + 8 * stage, phase ^ 1);
+            mbar_expect_tx(full_d + 8 * stage, FB_D_BYTES);
+            tma_load_2d(sbase + C::SM_D + stage * FB_D_BYTES, &map_d, kb * 64, cc * Vp + vt * FB_VT, full_d + 8 * stage);
+            if (++stage == C::DSTAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // =========================== skinning operand producer (A16 rows) ===========================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        const int m = t % n_m;
+        for (int st = 0; st < C::NT; ++st) {
+          mbar_wait(empty_a + 8 * stage, phase ^ 1);
+          mbar_expect_tx(full_a + 8 * stage, C::A_BYTES);
+          tma_load_2d(sbase + C::SM_A + stage * C::A_BYTES, &map_a, 0, (m * C::NS + st * C::ST) * 12, full_a + 8 * stage);
+          if (++stage == C::ASTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== blend MMA issuer ===========================
+    constexpr uint32_t idesc_p = umma_idesc_f16(FB_VT, C::NS);
+    const uint64_t desc_d0 = umma_desc_sw128(sbase + C::SM_D), desc_x0 = umma_desc_sw128(sbase + C::SM_X);
+    int dstage = 0, dphase = 0, n_tiles = 0;
+    for (int t = t0; t < t1; ++t, ++n_tiles) {
+      const int xb = n_tiles & 1;
+      mbar_wait(full_x + 8 * xb, (n_tiles >> 1) & 1);
+      mbar_wait(p_empty, (n_tiles & 1) ^ 1);       // the epilogue has read the previous P
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 3; ++cc) {
+        const uint32_t d_tmem = tmem_base + cc * C::NS;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(full_d + 8 * dstage, dphase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_add(desc_d0, dstage * FB_D_BYTES);
+          const uint64_t b_desc = umma_desc_add(desc_x0, xb * C::X_BYTES + kb * C::X_KB_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (kb == 3 && k == 3) continue;      // K = 240: the last 16 columns are zero padding
+              tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_p, (kb | k) != 0);
+            }
+            tc_commit(empty_d + 8 * dstage);
+          }
+          __syncwarp();
+          if (++dstage == C::DSTAGES) {
+            dstage = 0;
+            dphase ^= 1;
+          }
+        }
+      }
+      if (elect_one()) {
+        tc_commit(p_full);
+        tc_commit(empty_x + 8 * xb);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 3) {
+    // =========================== skinning MMA issuer (A = W16 in TMEM) ===========================
+    constexpr uint32_t idesc_t = umma_idesc_f16(FB_VT, C::TN);
+    const uint64_t desc_a0 = umma_desc_sw128(sbase + C::SM_A);
+    const uint32_t w_tmem = tmem_base + C::WCOL;     // window w of the W16 row = columns 8 w .. 8 w + 7
+    int astage = 0, aphase = 0, tb = 0, tphase = 0, cur_vt = -1, w_loads = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int vt = t / n_m;
+      if (vt != cur_vt) {
+        mbar_wait(w_ready, w_loads & 1);             // the epilogue has put this vertex tile's W16 rows in TMEM
+        ++w_loads;
+        cur_vt = vt;
+        tc_fence_after();
+      }
+#pragma unroll 1
+      for (int st = 0; st < C::NT; ++st) {
+        mbar_wait(t_empty + 8 * tb, tphase ^ 1);
+        mbar_wait(full_a + 8 * astage, aphase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + C::TCOL + tb * C::TN;
+        const uint64_t a_desc = umma_desc_add(desc_a0, astage * C::A_BYTES);
+        if (elect_one()) {
+          // (W window, A window) pairs of the table in k_skin_tc.cu
+          tc_mma_f16_ts(d_tmem, w_tmem + 0, a_desc + 0, idesc_t, 0);
+          tc_mma_f16_ts(d_tmem, w_tmem + 8, a_desc + 2, idesc_t, 1);
+          tc_mma_f16_ts(d_tmem, w_tmem + 0, a_desc + 4, idesc_t, 1);
+          tc_mma_f16_ts(d_tmem, w_tmem + 16, a_desc + 0, idesc_t, 1);
+          tc_mma_f16_ts(d_tmem, w_tmem + 24, a_desc + 2, idesc_t, 1);
+          tc_commit(empty_a + 8 * astage);
+          tc_commit(t_full + 8 * tb);
+        }
+        __syncwarp();
+        if (++astage == C::ASTAGES) {
+          astage = 0;
+          aphase ^= 1;
+        }
+        if (++tb == C::TBUF) {
+          tb = 0;
+          tphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue (warps 4..11), as in k_body_tc ===========================
+    const int q = warp & 3;
+    const int half = ((warp - 4) >> 2) & 1;
+    constexpr int PRE = C::PRE;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
+    int tb = 0, tphase = 0, n_tiles = 0, cur_vt = -1;
+    for (int t = t0; t < t1; ++t, ++n_tiles) {
+      const int vt = t / n_m, m = t % n_m;
+      const int v0 = vt * FB_VT + 32 * q;
+      const bool v_ok = v0 + lane < V;
+      float *const vbase = verts + ((size_t)(m * C::NS) * V + v0 + lane) * 3;
+      const int b_left = B - m * C::NS;
+      if (vt != cur_vt) {
+        // Every skinning MMA of the previous vertex tile has completed (this warp has waited for the
+        // T of its last tile): copy this thread's half of its W16 row (rows >= V are zero) to TMEM.
+        cur_vt = vt;
+        uint32_t wr[16];
+        const uint4 *src = W16 + (size_t)(v0 + lane) * 8 + half * 4;   // 128 B per row
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 x = src[i];
+          wr[4 * i + 0] = x.x;
+          wr[4 * i + 1] = x.y;
+          wr[4 * i + 2] = x.z;
+          wr[4 * i + 3] = x.w;
+        }
+        tc_st_32x16(lane_base + C::WCOL + half * 16, wr);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(w_ready);
+      }
+
+      auto do_tile = [&](int st, const uint32_t(*p_in)[4], bool release_p) {
+        const uint32_t my_full = t_full + 8 * tb, my_empty = t_empty + 8 * tb;
+        const uint32_t tcol0 = lane_base + C::TCOL + tb * C::TN + half * 48;
+        mbar_wait(my_full, tphase);
+        tc_fence_after();
+        const int s_loc = st * C::ST + half * 4;
+        uint32_t r[48], pc[3][4];
+        tc_ld_32x32(tcol0, r);
+        tc_ld_32x16(tcol0 + 32, r + 32);
+        if (p_in == nullptr) {
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) tc_ld_32x4(lane_base + cc * C::NS + s_loc, pc[cc]);
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+            for (int si = 0; si < 4; ++si) pc[cc][si] = p_in[cc][si];
+        }
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(my_empty);
+          if (release_p) mbar_arrive(p_empty);
+        }
+#pragma unroll
+        for (int si = 0; si < 4; ++si) {
+          const uint32_t *T = r + 12 * si;
+          const float px = __uint_as_float(pc[0][si]) * inv_scale, py = __uint_as_float(pc[1][si]) * inv_scale,
+                      pz = __uint_as_float(pc[2][si]) * inv_scale;
+          float o[3];
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr)
+            o[rr] = fmaf(__uint_as_float(T[4 * rr]), px,
+                         fmaf(__uint_as_float(T[4 * rr + 1]), py,
+                              fmaf(__uint_as_float(T[4 * rr + 2]), pz, __uint_as_float(T[4 * rr + 3]))));
+          const int sl = s_loc + si;
+          if (sl < b_left && v_ok) {
+            float *dst = vbase + sl * (V * 3);
+            __stcs(dst, o[0]);
+            __stcs(dst + 1, o[1]);
+            __stcs(dst + 2, o[2]);
+          }
+        }
+        if (++tb == C::TBUF) {
+          tb = 0;
+          tphase ^= 1;
+        }
+      };
+
+      mbar_wait(p_full, n_tiles & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int st = 0; st < C::NT - PRE; ++st) do_tile(st, nullptr, false);
+      uint32_t pre[PRE][3][4];
+#pragma unroll
+      for (int i = 0; i < PRE; ++i)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) tc_ld_32x4(lane_base + cc * C::NS + (C::NT - PRE + i) * C::ST + half * 4, pre[i][cc]);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_empty);
+#pragma unroll
+      for (int i = 0; i < PRE; ++i) do_tile(C::NT - PRE + i, pre[i], false);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------ host side
 typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -457,6 +794,7 @@ int body_tc_init(smplb_ctx *c) {
   CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyA>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyA::SM_TOTAL));
   CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyB>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyB::SM_TOTAL));
   CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyC::SM_TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(k_body_wt, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyW::SM_TOTAL));
   c->body_tc_ok = true;
   return 0;
 }
@@ -474,6 +812,18 @@ static int launch_body_cfg(smplb_ctx *c, int B, const void *x16, const void *A16
   return 0;
 }
 
+static int launch_body_wt(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts) {
+  alignas(64) CUtensorMap map_x, map_a;
+  TRY(make_map_rows16(&map_x, x16, 256, (uint64_t)B, BodyW::NS));
+  TRY(make_map_rows16(&map_a, A16, 64, (uint64_t)B * 12, BodyW::TN));
+  const int n_vt = c->Vp / FB_VT, n_m = cdiv(B, BodyW::NS);
+  const int total = n_vt * n_m;
+  const int grid = total < c->num_sms ? total : c->num_sms;
+  LAUNCH(c, "body_fwd_tc", grid, BodyW::THREADS, BodyW::SM_TOTAL, k_body_wt, map_x, *(const CUtensorMap *)c->map_d, map_a,
+         (const uint4 *)c->d_W16, B, c->V, c->Vp, n_vt, n_m, c->tc_inv_scale, verts);
+  return 0;
+}
+
 // verts [B][V][3] from the operand rows pose_fwd wrote (x16 [B][256], A16 [12 B][64]).
 // smplb_debug_set("fused", 2 | 3) selects the alternative configurations (tuning / validation).
 int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts) {
@@ -481,6 +831,7 @@ int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, fl
   switch (c->use_fused) {
     case 2: return launch_body_cfg<BodyB>(c, B, x16, A16, verts);
     case 3: return launch_body_cfg<BodyC>(c, B, x16, A16, verts);
+    case 5: return launch_body_wt(c, B, x16, A16, verts);
     default: return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
   }
 }

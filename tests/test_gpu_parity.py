@@ -381,15 +381,18 @@ def test_fused_blend_skinning_matches_two_kernel_path(smpl_full, full_model):
         try:
             ctx.debug_set("fused", 0)
             v0, j0, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
+            # 1: the default configuration; 2, 3: tuning variants; 5: W16 as a TMEM-resident operand
+            for variant in (1, 2, 3, 5):
+                ctx.debug_set("fused", variant)
+                v1, j1, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
+                assert np.isfinite(v1).all()
+                assert rel_err(v1, v0) < 2e-6, (B, variant)
+                assert np.array_equal(j1, j0)
+                n = min(B, 4)
+                v, _, _ = o(inp["beta"][:n].astype(np.float64), inp["theta"][:n].astype(np.float64), get_skin=True)
+                assert rel_err(v1[:n], v) < TOL
         finally:
             ctx.debug_set("fused", 1)
-        v1, j1, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
-        assert np.isfinite(v1).all()
-        assert rel_err(v1, v0) < 2e-6, B
-        assert np.array_equal(j1, j0)
-        n = min(B, 4)
-        v, _, _ = o(inp["beta"][:n].astype(np.float64), inp["theta"][:n].astype(np.float64), get_skin=True)
-        assert rel_err(v1[:n], v) < TOL
     # the dense backward after a fused forward rebuilds v_posed on demand
     inp = synthetic.make_inputs(33, seed=77)
     rng = np.random.default_rng(5)
