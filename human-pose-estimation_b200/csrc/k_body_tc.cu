@@ -25,8 +25,9 @@
 // without any MMA is as fast as one without any epilogue work (161 k vs 165 k clk of 204 k), and
 // the stores add the rest.  Shared-memory traffic (~1.1 MB per super-tile, 8.5 k clk at 128 B/clk
 // of the ~13 k) is the next limit, not the current one: moving the W16 operand to TMEM (k_body_wt
-// below) changed nothing.  Also measured equal or slower: a second set of epilogue warps, a
-// software-pipelined (two register sets) epilogue, N = 192 skinning MMAs with a single T stage,
+// below) changed nothing.  Also measured equal or slower: a second set of epilogue warps, four
+// instead of two epilogue warps per lane quarter (EW = 4: 137 vs 129 us), a software-pipelined
+// (two register sets) epilogue, N = 192 skinning MMAs with a single T stage,
 // plain instead of evict-first stores (+5 %).
 //
 // Persistent, warp-specialised: warp 0 TMA producer of the blend operands, warp 1 blend MMA issuer
@@ -55,9 +56,9 @@
 #define FB_W_BYTES (FB_VT * 128)      // W16 tile: 16 KB
 
 // NS samples per super-tile (blend MMA N), ST samples per skinning MMA, TBUF T accumulator stages.
-template <int NS_, int ST_, int TBUF_, int DSTAGES_ = 4, int ASTAGES_ = 3, int PRE_ = 0>
+template <int NS_, int ST_, int TBUF_, int DSTAGES_ = 4, int ASTAGES_ = 3, int PRE_ = 0, int EW_ = 2>
 struct BodyCfg {
-  static constexpr int NS = NS_, ST = ST_, TBUF = TBUF_, DSTAGES = DSTAGES_, ASTAGES = ASTAGES_, PRE = PRE_;
+  static constexpr int NS = NS_, ST = ST_, TBUF = TBUF_, DSTAGES = DSTAGES_, ASTAGES = ASTAGES_, PRE = PRE_, EW = EW_;
   static constexpr int TN = 12 * ST;            // skinning MMA N
   static constexpr int NT = NS / ST;            // skinning tiles per super-tile
   static constexpr int X_KB_BYTES = NS * 128;   // one k-block of the x16 tile
@@ -71,9 +72,12 @@ struct BodyCfg {
   static constexpr int SM_TOTAL = SM_BAR + 256;
   static constexpr int TCOL = 3 * NS;           // first TMEM column of the T stages
   // warps: 0 blend-operand producer, 1 blend MMA issuer, 2 skinning-operand producer, 3 skinning MMA issuer,
-  // 4..11 epilogue.  PRE = skinning tiles whose v_posed the epilogue fetches early (see there)
-  static constexpr int THREADS = 32 * 12;
+  // 4.. epilogue, EW warps per TMEM lane quarter, each HS = ST / EW samples of a tile.
+  // PRE = skinning tiles whose v_posed the epilogue fetches early (see there)
+  static constexpr int HS = ST / EW;
+  static constexpr int THREADS = 32 * (4 + 4 * EW);
   static_assert(NT % TBUF == 0 && PRE < NT, "tile counts");
+  static_assert(HS == 2 || HS == 4 || HS == 8, "samples per epilogue warp");
   static_assert(NS % 16 == 0 && NS % ST == 0 && ST % 8 == 0, "tile shape");
   static_assert(3 * NS + TBUF * TN <= 512, "TMEM budget");
   static_assert(X_KB_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "swizzle atoms need 1024 B alignment");
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     mbar_init(full_x, 1);
     mbar_init(empty_x, 1);
     mbar_init(p_full, 1);
-    mbar_init(p_empty, 8);                 // one arrival per epilogue warp
+    mbar_init(p_empty, 4 * C::EW);         // one arrival per epilogue warp
     for (int i = 0; i < C::DSTAGES; ++i) {
       mbar_init(full_d + 8 * i, 1);
       mbar_init(empty_d + 8 * i, 1);
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     }
     for (int i = 0; i < C::TBUF; ++i) {
       mbar_init(t_full + 8 * i, 1);
-      mbar_init(t_empty + 8 * i, 8);
+      mbar_init(t_empty + 8 * i, 4 * C::EW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -304,18 +308,17 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 #endif
     }
   } else if (warp >= 4) {
-    // =========================== epilogue (warps 4..11) ===========================
-    // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31), each taking
-    // half of a skinning tile's samples.  Thread = vertex: T (12 columns per sample) and the three
-    // coordinates of v_posed come out of TMEM; nothing passes through shared memory.
+    // =========================== epilogue (warps 4..) ===========================
+    // EW warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31), each taking
+    // HS = ST / EW samples of a skinning tile.  Thread = vertex: T (12 columns per sample) and the
+    // three coordinates of v_posed come out of TMEM; nothing passes through shared memory.
     // P has a single TMEM stage, so the blend of the next super-tile cannot start before the
     // last read of this one: the v_posed values of the last PRE tiles are therefore fetched into
     // registers early and P is handed back PRE tiles before the super-tile ends, which hides most
     // of the blend behind the remaining skinning tiles.
     const int q = warp & 3;
-    const int half = ((warp - 4) >> 2) & 1;
-    constexpr int HS = C::ST / 2;                 // samples per warp per tile
-    constexpr int G = HS / 4;                     // groups of 4 samples per warp per tile
+    const int part = (warp - 4) >> 2;             // which HS samples of a tile
+    constexpr int HS = C::HS;
     constexpr int PRE = C::PRE;
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
     int tb = 0, tphase = 0, n_tiles = 0;
@@ -327,58 +330,75 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       float *const vbase = verts + ((size_t)(m * C::NS) * V + v0 + lane) * 3;
       const int b_left = B - m * C::NS;           // samples of this super-tile inside the batch
 
+      // the three coordinates of HS samples' v_posed (columns s_loc.. of the three planes of P)
+      auto load_p = [&](int s_loc, uint32_t(*pc)[HS]) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          const uint32_t col = lane_base + cc * C::NS + s_loc;
+          if (HS == 2) tc_ld_32x2(col, pc[cc]);
+          if (HS == 4) tc_ld_32x4(col, pc[cc]);
+          if (HS == 8) tc_ld_32x8(col, pc[cc]);
+        }
+      };
       // one skinning tile; p_in == nullptr: v_posed comes from TMEM (P), else from registers
-      auto do_tile = [&](int st, const uint32_t(*p_in)[3][4], bool release_p) {
+      auto do_tile = [&](int st, const uint32_t(*p_in)[HS], bool release_p) {
         const uint32_t my_full = t_full + 8 * tb, my_empty = t_empty + 8 * tb;
-        const uint32_t tcol0 = lane_base + C::TCOL + tb * C::TN + half * HS * 12;
+        const uint32_t tcol0 = lane_base + C::TCOL + tb * C::TN + part * HS * 12;
         tq = TCLK();
         mbar_wait(my_full, tphase);
         TADD(w_tf, tq);
         tc_fence_after();
-        const int s_loc = st * C::ST + half * HS;   // first sample (within the super-tile) of this warp
+        const int s_loc = st * C::ST + part * HS;   // first sample (within the super-tile) of this warp
+        uint32_t r[12 * HS], pc[3][HS];
+        if (HS == 2) {
+          tc_ld_32x16(tcol0, r);
+          tc_ld_32x8(tcol0 + 16, r + 16);
+        }
+        if (HS == 4) {
+          tc_ld_32x32(tcol0, r);
+          tc_ld_32x16(tcol0 + 32, r + 32);
+        }
+        if (HS == 8) {
+          tc_ld_32x32(tcol0, r);
+          tc_ld_32x32(tcol0 + 32, r + 32);
+          tc_ld_32x32(tcol0 + 64, r + 64);
+        }
+        if (p_in == nullptr) {
+          load_p(s_loc, pc);
+        } else {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          uint32_t r[48], pc[3][4];
-          tc_ld_32x32(tcol0 + g * 48, r);
-          tc_ld_32x16(tcol0 + g * 48 + 32, r + 32);
-          if (p_in == nullptr) {
+          for (int cc = 0; cc < 3; ++cc)
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) tc_ld_32x4(lane_base + cc * C::NS + s_loc + 4 * g, pc[cc]);
-          } else {
+            for (int si = 0; si < HS; ++si) pc[cc][si] = p_in[cc][si];
+        }
+        tq = TCLK();
+        tc_wait_ld();
+        TADD(w_ld, tq);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(my_empty);
+          if (release_p) mbar_arrive(p_empty);   // this warp's last read of the super-tile's P
+        }
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc)
+        for (int si = 0; si < HS; ++si) {
+          const uint32_t *T = r + 12 * si;
+          const float px = __uint_as_float(pc[0][si]) * inv_scale, py = __uint_as_float(pc[1][si]) * inv_scale,
+                      pz = __uint_as_float(pc[2][si]) * inv_scale;
+          float o[3];
 #pragma unroll
-              for (int si = 0; si < 4; ++si) pc[cc][si] = p_in[g][cc][si];
-          }
-          tq = TCLK();
-          tc_wait_ld();
-          TADD(w_ld, tq);
-          if (g == G - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(my_empty);
-              if (release_p) mbar_arrive(p_empty);   // this warp's last read of the super-tile's P
-            }
-          }
-#pragma unroll
-          for (int si = 0; si < 4; ++si) {
-            const uint32_t *T = r + 12 * si;
-            const float px = __uint_as_float(pc[0][si]) * inv_scale, py = __uint_as_float(pc[1][si]) * inv_scale,
-                        pz = __uint_as_float(pc[2][si]) * inv_scale;
-            float o[3];
-#pragma unroll
-            for (int rr = 0; rr < 3; ++rr)
-              o[rr] = fmaf(__uint_as_float(T[4 * rr]), px,
-                           fmaf(__uint_as_float(T[4 * rr + 1]), py,
-                                fmaf(__uint_as_float(T[4 * rr + 2]), pz, __uint_as_float(T[4 * rr + 3]))));
-            const int sl = s_loc + 4 * g + si;
-            if (FB_ABLATE != 3 && sl < b_left && v_ok) {
-              float *dst = vbase + sl * (V * 3);
-              __stcs(dst, o[0]);
-              __stcs(dst + 1, o[1]);
-              __stcs(dst + 2, o[2]);
-            }
+          for (int rr = 0; rr < 3; ++rr)
+            o[rr] = fmaf(__uint_as_float(T[4 * rr]), px,
+                         fmaf(__uint_as_float(T[4 * rr + 1]), py,
+                              fmaf(__uint_as_float(T[4 * rr + 2]), pz, __uint_as_float(T[4 * rr + 3]))));
+          // verts[b][v][xyz]: three strided scalar stores per sample (rows are only 8 B aligned, so no
+          // vector or bulk stores); L2 merges the partial sectors
+          const int sl = s_loc + si;
+          if (FB_ABLATE != 3 && sl < b_left && v_ok) {
+            float *dst = vbase + sl * (V * 3);
+            __stcs(dst, o[0]);
+            __stcs(dst + 1, o[1]);
+            __stcs(dst + 2, o[2]);
           }
         }
         if (++tb == C::TBUF) {
@@ -391,17 +411,26 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       mbar_wait(p_full, n_tiles & 1);
       TADD(w_pf, tq);
       tc_fence_after();
+      if (FB_ABLATE == 1) {
+        for (int st = 0; st < C::NT; ++st) {
+          mbar_wait(t_full + 8 * tb, tphase);
+          if (lane == 0) {
+            mbar_arrive(t_empty + 8 * tb);
+            if (st == C::NT - 1) mbar_arrive(p_empty);
+          }
+          if (++tb == C::TBUF) {
+            tb = 0;
+            tphase ^= 1;
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int st = 0; st < C::NT - PRE; ++st) do_tile(st, nullptr, PRE == 0 && st == C::NT - 1);
       if (PRE > 0) {
-        uint32_t pre[PRE > 0 ? PRE : 1][G][3][4];
+        uint32_t pre[PRE > 0 ? PRE : 1][3][HS];
 #pragma unroll
-        for (int i = 0; i < PRE; ++i)
-#pragma unroll
-          for (int g = 0; g < G; ++g)
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc)
-              tc_ld_32x4(lane_base + cc * C::NS + (C::NT - PRE + i) * C::ST + half * HS + 4 * g, pre[i][g][cc]);
+        for (int i = 0; i < PRE; ++i) load_p((C::NT - PRE + i) * C::ST + part * HS, pre[i]);
         tc_wait_ld();
         tc_fence_before();
         __syncwarp();
@@ -786,7 +815,7 @@ static int make_map_rows16(CUtensorMap *map, const void *ptr, uint64_t row_halve
 // Needs the operands of both tensor-core kernels (Dt16 + its scale, W16).
 using BodyA = BodyCfg<96, 8, 2, 4, 3, 4>;   // default: double-buffered T, v_posed of the last 4 tiles fetched early
 using BodyB = BodyCfg<96, 8, 2, 4, 3, 0>;   // no early fetch (the blend is exposed)
-using BodyC = BodyCfg<96, 16, 1, 4, 2, 0>;  // N = 192 skinning MMAs, single T stage
+using BodyC = BodyCfg<96, 8, 2, 4, 3, 4, 4>;  // four epilogue warps per lane quarter, 2 samples of a tile each
 
 int body_tc_init(smplb_ctx *c) {
   c->body_tc_ok = false;

@@ -131,3 +131,15 @@ __device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t *r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+
+// 32 lanes x 8 consecutive fp32 columns.
+__device__ __forceinline__ void tc_ld_32x8(uint32_t taddr, uint32_t *r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+
+// 32 lanes x 2 consecutive fp32 columns.
+__device__ __forceinline__ void tc_ld_32x2(uint32_t taddr, uint32_t *r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+}

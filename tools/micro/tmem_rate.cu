@@ -295,9 +295,79 @@ static void run_mma_ld(long long *d_out, int nld) {
   printf("mma 128x%dx16 SS in groups of 5 + commit, %d warps streaming tcgen05.ld: %.1f clk per MMA\n", N, nld, (double)mx / iters);
 }
 
+// tcgen05.ld throughput with several loads in flight per warp (K loads, then one wait::ld):
+// is the cost per instruction or per byte?
+template <int W>   // W = 2, 4, 8, 16, 32 columns per load
+__global__ void __launch_bounds__(512, 1) k_ld_tp(int iters, long long *out) {
+  __shared__ uint32_t tptr;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tptr)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tptr + ((uint32_t)(32 * (warp & 3)) << 16) + (warp >> 2) * 128;
+  uint32_t acc = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    uint32_t r[4][32];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (W == 2) tc_ld_32x2(tbase + u * 32, r[u]);
+      if (W == 4) tc_ld_32x4(tbase + u * 32, r[u]);
+      if (W == 8) tc_ld_32x8(tbase + u * 32, r[u]);
+      if (W == 16) tc_ld_32x16(tbase + u * 32, r[u]);
+      if (W == 32) tc_ld_32x32(tbase + u * 32, r[u]);
+    }
+    tc_wait_ld();
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < W; ++j) acc ^= r[u][j];
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  if (acc == 0x12345678u) out[1000] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tptr), "n"(512) : "memory");
+  }
+}
+
+template <int W>
+static void run_ld_tp(long long *d_out, int warps) {
+  long long h[148];
+  const int iters = 2000;
+  for (int rep = 0; rep < 2; ++rep) k_ld_tp<W><<<148, 32 * warps>>>(iters, d_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("ld_tp: %s\n", cudaGetErrorString(e));
+    return;
+  }
+  cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+  long long mx = 0;
+  for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+  double n_ld = (double)iters * 4 * warps;
+  printf("tcgen05.ld x%-2d, %2d warps, 4 in flight each: %.1f clk per load per SM, %.1f B/clk/SM\n", W, warps, mx / n_ld,
+         n_ld * 32 * W * 4 / mx);
+}
+
 int main() {
   long long *d_out;
   cudaMalloc(&d_out, 2048 * sizeof(long long));
+  for (int w = 4; w <= 16; w *= 2) {
+    run_ld_tp<2>(d_out, w);
+    run_ld_tp<4>(d_out, w);
+    run_ld_tp<8>(d_out, w);
+    run_ld_tp<16>(d_out, w);
+    run_ld_tp<32>(d_out, w);
+  }
   for (int w = 0; w <= 8; w += 4) run_mma_ld<96>(d_out, w);
   run_mma_ld<192>(d_out, 0);
   run_mma_ld<192>(d_out, 8);
