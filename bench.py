@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--engines", type=int, default=2, help="contexts in flight per GPU")
+    ap.add_argument("--engines", type=int, default=3, help="contexts in flight per GPU")
     ap.add_argument("--fused", type=int, default=-1, help="tuning: smplb_debug_set('fused', n) on every context")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -381,11 +381,11 @@ def main():
                        "global_batch": world * B, "parallelism": "batch-sharded x%d" % world, "contexts_in_flight_per_gpu": NE,
                        "l2": "per-step working set (verts, 340 MB per context) exceeds the 126 MB L2; inputs rotate "
                              "over %d buffer sets" % NSET,
-                       "timing": "value: CUDA events around the K steps, which alternate between two contexts of the GPU "
+                       "timing": "value: CUDA events around the K steps, which rotate over the contexts in flight on the GPU "
                                  "(each overlaps its 6890-vertex kernels with its keypoint path on a second stream); "
                                  "roofline / kernels_ms_per_step: K more steps on one context with events around every "
                                  "launch, single stream",
-                       "e2e": "host-buffer smpl.step on two alternating contexts (copies of one step overlap kernels of the "
+                       "e2e": "host-buffer smpl.step rotating over the contexts in flight (copies of one step overlap kernels of the "
                               "other): per step pinned H2D of beta/theta/cam/kp_gt and D2H of loss + d_beta/d_theta/d_cam; "
                               "verts are computed and stay in device memory"},
             "roofline": roof,

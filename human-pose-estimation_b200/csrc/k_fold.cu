@@ -42,22 +42,38 @@ __global__ void __launch_bounds__(224) k_fold_build(int Vp, int pitch, const int
   if (xk == 0) cc[k * NJ + j] = (float)ac;
 }
 
-// GEMM operands.  G16 [NUp][704]: G_hi | G_lo | G_hi | 0 (pairs with x_hi | x_hi | x_lo).
+// GEMM operands.  G16 [NUp][256] pairs with the blend operand row x16 that k_pose_fwd writes anyway
+// (same K map as Dt16 in k_blend_tc.cu): columns 0..206 G_pose (single fp16: it multiplies the small
+// pose_feature), 207.. the shape columns as hi | lo | hi against beta_hi | beta_hi | beta_lo and the
+// template column as hi | mid | lo against 1 | 1 | 1, so the ~1 m terms keep fp32 accuracy.
 // Gt16 [224][3*NUp]: Gt_hi | Gt_hi | Gt_lo (pairs with du_hi | du_lo | du_hi).  Values are scaled
 // by `scale` (a power of two) first.
-__global__ void k_fold_operands(int nu, int nup, float scale, const float *__restrict__ G, __half *__restrict__ G16,
-                                __half *__restrict__ Gt16) {
+__global__ void k_fold_operands(int nu, int nup, int NB, float scale, const float *__restrict__ G,
+                                __half *__restrict__ G16, __half *__restrict__ Gt16) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nup * KX) return;
   int n = i / KX, xk = i % KX;
   float g = n < nu ? G[(size_t)n * KX + xk] * scale : 0.f;
   __half hi = __float2half_rn(g);
   __half lo = __float2half_rn(g - __half2float(hi));
-  __half *r1 = G16 + (size_t)n * 704;
-  r1[xk] = hi;
-  r1[KX + xk] = lo;
-  r1[2 * KX + xk] = hi;
-  if (xk < 32) r1[3 * KX + xk] = __float2half_rn(0.f);
+  __half *r1 = G16 + (size_t)n * 256;
+  if (xk < NPF) {
+    r1[xk] = hi;
+  } else if (xk < NPF + NB) {
+    int bi = xk - NPF;
+    r1[NPF + bi] = hi;
+    r1[NPF + 10 + bi] = lo;
+    r1[NPF + 20 + bi] = hi;
+  } else if (xk == NPF + NB) {
+    float mid = __half2float(lo);
+    r1[NPF + 30] = hi;
+    r1[NPF + 31] = lo;
+    r1[NPF + 32] = __float2half_rn(g - __half2float(hi) - mid);
+    for (int bi = NB; bi < 10; ++bi) {          // unused shape slots
+      r1[NPF + bi] = r1[NPF + 10 + bi] = r1[NPF + 20 + bi] = __float2half_rn(0.f);
+    }
+    for (int k = NPF + 33; k < 256; ++k) r1[k] = __float2half_rn(0.f);
+  }
   __half *r2 = Gt16 + (size_t)xk * (3 * nup);
   r2[n] = hi;
   r2[nup + n] = hi;
@@ -567,22 +583,22 @@ int fold_init(smplb_ctx *c) {
   s = s < -8 ? -8 : (s > 24 ? 24 : s);
   c->fold_scale = ldexpf(1.0f, s);
   c->fold_inv_scale = ldexpf(1.0f, -s);
-  CUDA_TRY(cudaMalloc((void **)&c->d_G16, (size_t)nup * 704 * 2));
+  CUDA_TRY(cudaMalloc((void **)&c->d_G16, (size_t)nup * 256 * 2));
   CUDA_TRY(cudaMalloc((void **)&c->d_Gt16, (size_t)KX * 3 * nup * 2));
-  k_fold_operands<<<cdiv(nup * KX, 256), 256, 0, c->stream>>>(nu, nup, c->fold_scale, c->d_G, (__half *)c->d_G16,
+  k_fold_operands<<<cdiv(nup * KX, 256), 256, 0, c->stream>>>(nu, nup, c->NB, c->fold_scale, c->d_G, (__half *)c->d_G16,
                                                              (__half *)c->d_Gt16);
   c->launches += 3;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  TRY(tc_make_map(c->map_g1, 0, c->d_G16, 704, (uint64_t)nup, 704 * 2, 64, 128));
+  TRY(tc_make_map(c->map_g1, 0, c->d_G16, 256, (uint64_t)nup, 256 * 2, 64, 128));
   TRY(tc_make_map(c->map_g2, 0, c->d_Gt16, (uint64_t)3 * nup, (uint64_t)KX, (uint64_t)3 * nup * 2, 64, 128));
   c->fold_ok = true;
   return 0;
 }
 
-// U [B][nup] = x G^T.
-int launch_fold_gemm_u(smplb_ctx *c, int B, const void *x16b) {
+// U [B][nup] = x G^T, x16 = the blend operand rows [B][256].
+int launch_fold_gemm_u(smplb_ctx *c, int B, const void *x16) {
   RET_IF(!c->fold_ok, SMPLB_ESTATE, "folded keypoint path is not initialised");
-  return launch_gemm_tc(c, "fold_gemm_u", B, c->fold_nup, 704, x16b, c->map_g1, c->ws_U, c->fold_nup, 1, c->fold_inv_scale);
+  return launch_gemm_tc(c, "fold_gemm_u", B, c->fold_nup, 256, x16, c->map_g1, c->ws_U, c->fold_nup, 1, c->fold_inv_scale);
 }
 
 // joints / projection / kp-loss partials from U and A.

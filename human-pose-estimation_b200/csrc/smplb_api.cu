@@ -212,7 +212,6 @@ static int ensure_ws(smplb_ctx *c, int B) {
     WS_ALLOC(ws_du16, nb * 3 * c->fold_nup / 2);
     CUDA_TRY(cudaMemsetAsync(c->ws_du16, 0, nb * 3 * c->fold_nup * 2, c->stream));
     WS_ALLOC(ws_rowscale, nb);
-    WS_ALLOC(ws_x16b, nb * 352);
   }
   WS_ALLOC(ws_A16, nb * 12 * 32);   // 12 rows x 64 halves per sample; columns 48..63 stay zero
   CUDA_TRY(cudaMemsetAsync(c->ws_A16, 0, nb * 12 * 32 * 4, c->stream));
@@ -669,7 +668,7 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   bool fold = tc && c->fold_ok && c->use_fold;
   TRY(launch_pose_fwd(c, B, c->ws_beta, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, Jtr ? Jtr : c->ws_Jtr,
                       tc ? nullptr : c->ws_x, tc ? c->ws_x16 : nullptr, stc ? c->ws_A16 : nullptr,
-                      fold ? c->ws_x16b : nullptr));
+                      nullptr));   // (the 704-wide fold operand row is no longer used: the fold GEMM reads x16)
   if (Rs) CUDA_TRY(cudaMemcpyAsync(Rs, c->ws_Rs, (size_t)B * NJ * 9 * 4, cudaMemcpyDeviceToDevice, c->stream));
   // Keypoint path on the active vertices only (rows of joint_regressor with a non-zero): the
   // same two tensor-core kernels on ~9 % of the vertices give joints without reading verts back.
@@ -692,7 +691,7 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   bool fused = full && tc && stc && c->body_tc_ok && c->use_fused && !chunked && !want_vposed;
   // the fold GEMM needs TMEM and ~160 KB of shared memory, which the persistent blend / skinning
   // CTAs would deny it: issue it before forking so only the light per-body kernels overlap them
-  if (fold) TRY(launch_fold_gemm_u(c, B, c->ws_x16b));
+  if (fold) TRY(launch_fold_gemm_u(c, B, c->ws_x16));
   bool overlap = full && (fold || compact) && c->use_overlap && !c->profile_serial;
   if (overlap) {
     CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));

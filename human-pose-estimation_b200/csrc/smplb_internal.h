@@ -87,7 +87,7 @@ struct smplb_ctx {
   float *ws_U = nullptr;           // [B][fold_nup]
   void *ws_du16 = nullptr;         // [B][3 * fold_nup] fp16
   float *ws_rowscale = nullptr;    // [B]
-  void *ws_x16b = nullptr;         // [B][704] fp16: x_hi | x_hi | x_lo | 0
+  void *ws_x16b = nullptr;         // unused since the fold GEMM reads the blend operand rows (ws_x16); kept for the kernel signature
   bool saved_fold = false;
   bool saved_fold_step = false;    // the forward already ran the fused keypoint forward + backward (k_fold_step_w)
   int use_fold_step = 1;           // smplb_debug_set("fold_step", 0): separate forward / backward kernels
