@@ -27,8 +27,9 @@
 // of the ~13 k) is the next limit, not the current one: moving the W16 operand to TMEM (k_body_wt
 // below) changed nothing.  Also measured equal or slower: a second set of epilogue warps, four
 // instead of two epilogue warps per lane quarter (EW = 4: 137 vs 129 us), a software-pipelined
-// (two register sets) epilogue, N = 192 skinning MMAs with a single T stage,
-// plain instead of evict-first stores (+5 %).
+// (two register sets) epilogue, N = 192 skinning MMAs with a single T stage, plain instead of
+// evict-first stores (+5 %), 8-byte stores (transposed through shared memory +28 %, lane pairs +7 %),
+// CTA pairs with the Dt16 k-blocks multicast (CL = 2, +5 %: the L2 reads are not the limit either).
 //
 // Persistent, warp-specialised: warp 0 TMA producer of the blend operands, warp 1 blend MMA issuer
 // and TMEM allocator, warp 2 TMA producer of the skinning operands, warp 3 skinning MMA issuer,
@@ -56,9 +57,13 @@
 #define FB_W_BYTES (FB_VT * 128)      // W16 tile: 16 KB
 
 // NS samples per super-tile (blend MMA N), ST samples per skinning MMA, TBUF T accumulator stages.
-template <int NS_, int ST_, int TBUF_, int DSTAGES_ = 4, int ASTAGES_ = 3, int PRE_ = 0, int EW_ = 2>
+template <int NS_, int ST_, int TBUF_, int DSTAGES_ = 4, int ASTAGES_ = 3, int PRE_ = 0, int EW_ = 2, int CL_ = 1>
 struct BodyCfg {
   static constexpr int NS = NS_, ST = ST_, TBUF = TBUF_, DSTAGES = DSTAGES_, ASTAGES = ASTAGES_, PRE = PRE_, EW = EW_;
+  // CL = 2: the kernel runs as clusters of two CTAs that walk the same vertex tiles on adjacent
+  // sample blocks, so every Dt16 k-block is read from L2 once and multicast to both (the kernel is
+  // bound by L2 throughput: ~1.26 GB of operand reads + output writes per launch)
+  static constexpr int CL = CL_;
   static constexpr int TN = 12 * ST;            // skinning MMA N
   static constexpr int NT = NS / ST;            // skinning tiles per super-tile
   static constexpr int X_KB_BYTES = NS * 128;   // one k-block of the x16 tile
@@ -101,9 +106,13 @@ __global__ void __launch_bounds__(C::THREADS, 1)
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + C::SM_BAR + 224);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total = n_vt * n_m;
-  const int t0 = (int)(((long long)blockIdx.x * total) / gridDim.x);
-  const int t1 = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
+  // Super-tile t of this CTA (or, CL = 2, of this cluster) -> sample block t / n_vt (times two plus
+  // the CTA's rank in the pair), vertex tile t % n_vt.
+  const int crank = C::CL == 2 ? (int)cluster_ctarank() : 0;
+  const int n_units = gridDim.x / C::CL, unit = blockIdx.x / C::CL;
+  const int total = n_vt * ((n_m + C::CL - 1) / C::CL);
+  const int t0 = (int)(((long long)unit * total) / n_units);
+  const int t1 = (int)(((long long)(unit + 1) * total) / n_units);
 
   if (threadIdx.x == 0) {
     mbar_init(full_x, 1);
@@ -112,7 +121,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     mbar_init(p_empty, 4 * C::EW);         // one arrival per epilogue warp
     for (int i = 0; i < C::DSTAGES; ++i) {
       mbar_init(full_d + 8 * i, 1);
-      mbar_init(empty_d + 8 * i, 1);
+      mbar_init(empty_d + 8 * i, C::CL);   // a Dt16 stage is free when the MMAs of every CTA of the pair have read it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(full_w + 8 * i, 1);
@@ -135,6 +144,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (C::CL == 2) cluster_sync_all();     // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -144,9 +154,9 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     // block; the Dt16 k-blocks of the vertex tile (3 planes x 4 k-blocks, L2-resident) stream
     // through the ring.
     if (lane == 0) {
-      int cur_m = -1, x_loads = 0, stage = 0, phase = 0;
+      int cur_m = -1, x_loads = 0, stage = 0, phase = 0, n_loads = 0;
       for (int t = t0; t < t1; ++t) {
-        const int m = t / n_vt, vt = t % n_vt;
+        const int m = (t / n_vt) * C::CL + crank, vt = t % n_vt;
         if (m != cur_m) {
           if (x_loads > 0) mbar_wait(empty_x, (x_loads - 1) & 1);
           mbar_expect_tx(full_x, C::X_BYTES);
@@ -158,7 +168,14 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(empty_d + 8 * stage, phase ^ 1);
             mbar_expect_tx(full_d + 8 * stage, FB_D_BYTES);
-            tma_load_2d(sbase + C::SM_D + stage * FB_D_BYTES, &map_d, kb * 64, cc * Vp + vt * FB_VT, full_d + 8 * stage);
+            if (C::CL == 1) {
+              tma_load_2d(sbase + C::SM_D + stage * FB_D_BYTES, &map_d, kb * 64, cc * Vp + vt * FB_VT, full_d + 8 * stage);
+            } else if ((n_loads & 1) == crank) {
+              // the two CTAs take turns issuing; the data and the complete_tx reach both
+              tma_load_2d_mc(sbase + C::SM_D + stage * FB_D_BYTES, &map_d, kb * 64, cc * Vp + vt * FB_VT, full_d + 8 * stage,
+                             (uint16_t)3);
+            }
+            ++n_loads;
             if (++stage == C::DSTAGES) {
               stage = 0;
               phase ^= 1;
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     if (lane == 0) {
       int wbuf = 0, wphase = 0, stage = 0, phase = 0;
       for (int t = t0; t < t1; ++t) {
-        const int m = t / n_vt, vt = t % n_vt;
+        const int m = (t / n_vt) * C::CL + crank, vt = t % n_vt;
         mbar_wait(empty_w + 8 * wbuf, wphase ^ 1);
         mbar_expect_tx(full_w + 8 * wbuf, FB_W_BYTES);
         tma_load_2d(sbase + C::SM_W + wbuf * FB_W_BYTES, &map_w, 0, vt * FB_VT, full_w + 8 * wbuf);
@@ -202,7 +219,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       int cur_m = -1, x_loads = 0, dstage = 0, dphase = 0, n_tiles = 0;
       [[maybe_unused]] long long w_pe = 0, w_fd = 0, w_tot = TCLK(), tq;
       for (int t = t0; t < t1; ++t, ++n_tiles) {
-        const int m = t / n_vt;
+        const int m = t / n_vt;                       // (the pair's sample-block pair)
         if (m != cur_m) {
           mbar_wait(full_x, x_loads & 1);
           ++x_loads;
@@ -230,7 +247,8 @@ __global__ void __launch_bounds__(C::THREADS, 1)
                 if (kb == 3 && k == 3) continue;      // K = 240: the last 16 columns are zero padding
                 if (FB_ABLATE != 2) tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_p, (kb | k) != 0);
               }
-              tc_commit(empty_d + 8 * dstage);
+              if (C::CL == 1) tc_commit(empty_d + 8 * dstage);
+              else tc_commit_mc(empty_d + 8 * dstage, (uint16_t)3);   // releases the stage in both CTAs
             }
             __syncwarp();
             if (++dstage == C::DSTAGES) {
@@ -324,11 +342,11 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     int tb = 0, tphase = 0, n_tiles = 0;
     [[maybe_unused]] long long w_pf = 0, w_tf = 0, w_ld = 0, w_tot = TCLK(), tq;
     for (int t = t0; t < t1; ++t, ++n_tiles) {
-      const int m = t / n_vt, vt = t % n_vt;
+      const int m = (t / n_vt) * C::CL + crank, vt = t % n_vt;
       const int v0 = vt * FB_VT + 32 * q;
       const bool v_ok = v0 + lane < V;
       float *const vbase = verts + ((size_t)(m * C::NS) * V + v0 + lane) * 3;
-      const int b_left = B - m * C::NS;           // samples of this super-tile inside the batch
+      const int b_left = B - m * C::NS;           // samples of this super-tile inside the batch (<= 0: a padding block)
 
       // the three coordinates of HS samples' v_posed (columns s_loc.. of the three planes of P)
       auto load_p = [&](int s_loc, uint32_t(*pc)[HS]) {
@@ -380,25 +398,32 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           mbar_arrive(my_empty);
           if (release_p) mbar_arrive(p_empty);   // this warp's last read of the super-tile's P
         }
+        float o[HS][3];
 #pragma unroll
         for (int si = 0; si < HS; ++si) {
           const uint32_t *T = r + 12 * si;
           const float px = __uint_as_float(pc[0][si]) * inv_scale, py = __uint_as_float(pc[1][si]) * inv_scale,
                       pz = __uint_as_float(pc[2][si]) * inv_scale;
-          float o[3];
 #pragma unroll
           for (int rr = 0; rr < 3; ++rr)
-            o[rr] = fmaf(__uint_as_float(T[4 * rr]), px,
-                         fmaf(__uint_as_float(T[4 * rr + 1]), py,
-                              fmaf(__uint_as_float(T[4 * rr + 2]), pz, __uint_as_float(T[4 * rr + 3]))));
-          // verts[b][v][xyz]: three strided scalar stores per sample (rows are only 8 B aligned, so no
-          // vector or bulk stores); L2 merges the partial sectors
-          const int sl = s_loc + si;
-          if (FB_ABLATE != 3 && sl < b_left && v_ok) {
-            float *dst = vbase + sl * (V * 3);
-            __stcs(dst, o[0]);
-            __stcs(dst + 1, o[1]);
-            __stcs(dst + 2, o[2]);
+            o[si][rr] = fmaf(__uint_as_float(T[4 * rr]), px,
+                             fmaf(__uint_as_float(T[4 * rr + 1]), py,
+                                  fmaf(__uint_as_float(T[4 * rr + 2]), pz, __uint_as_float(T[4 * rr + 3]))));
+        }
+        if (FB_ABLATE == 3) {
+        } else {
+          // verts[b][v][xyz]: three scalar stores 12 B apart per sample.  Rows are only 8-byte aligned
+          // (82,680 B), so no 16-byte or bulk stores; 8-byte stores were measured slower both ways
+          // (transposed through shared memory: 162 us; lane pairs with one shuffle: 135 us; this: 127 us)
+#pragma unroll
+          for (int si = 0; si < HS; ++si) {
+            const int sl = s_loc + si;
+            if (sl < b_left && v_ok) {
+              float *dst = vbase + sl * (V * 3);
+              __stcs(dst, o[si][0]);
+              __stcs(dst + 1, o[si][1]);
+              __stcs(dst + 2, o[si][2]);
+            }
           }
         }
         if (++tb == C::TBUF) {
@@ -447,6 +472,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (C::CL == 2) cluster_sync_all();     // no CTA leaves while its peer may still multicast to it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
@@ -816,6 +842,7 @@ static int make_map_rows16(CUtensorMap *map, const void *ptr, uint64_t row_halve
 using BodyA = BodyCfg<96, 8, 2, 4, 3, 4>;   // default: double-buffered T, v_posed of the last 4 tiles fetched early
 using BodyB = BodyCfg<96, 8, 2, 4, 3, 0>;   // no early fetch (the blend is exposed)
 using BodyC = BodyCfg<96, 8, 2, 4, 3, 4, 4>;  // four epilogue warps per lane quarter, 2 samples of a tile each
+using BodyP = BodyCfg<96, 8, 2, 4, 3, 4, 2, 2>;  // CTA pairs, Dt16 multicast
 
 int body_tc_init(smplb_ctx *c) {
   c->body_tc_ok = false;
@@ -824,6 +851,7 @@ int body_tc_init(smplb_ctx *c) {
   CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyB>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyB::SM_TOTAL));
   CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyC::SM_TOTAL));
   CUDA_TRY(cudaFuncSetAttribute(k_body_wt, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyW::SM_TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyP>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyP::SM_TOTAL));
   c->body_tc_ok = true;
   return 0;
 }
@@ -838,6 +866,42 @@ static int launch_body_cfg(smplb_ctx *c, int B, const void *x16, const void *A16
   const int grid = total < c->num_sms ? total : c->num_sms;
   LAUNCH(c, "body_fwd_tc", grid, C::THREADS, C::SM_TOTAL, k_body_tc<C>, map_x, *(const CUtensorMap *)c->map_d,
          *(const CUtensorMap *)c->map_w, map_a, B, c->V, c->Vp, n_vt, n_m, c->tc_inv_scale, verts);
+  return 0;
+}
+
+// CTA-pair variant: launched as clusters of two (the grid is rounded down to an even CTA count).
+static int launch_body_pair(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts) {
+  using C = BodyP;
+  alignas(64) CUtensorMap map_x, map_a;
+  TRY(make_map_rows16(&map_x, x16, 256, (uint64_t)B, C::NS));
+  TRY(make_map_rows16(&map_a, A16, 64, (uint64_t)B * 12, C::TN));
+  const int n_vt = c->Vp / FB_VT, n_m = cdiv(B, C::NS);
+  const int total = n_vt * cdiv(n_m, 2);
+  int grid = 2 * (total < c->num_sms / 2 ? total : c->num_sms / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SM_TOTAL;
+  cfg.stream = c->cur;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const CUtensorMap map_d = *(const CUtensorMap *)c->map_d, map_w = *(const CUtensorMap *)c->map_w;
+  int Vv = c->V, Vp = c->Vp;
+  float inv = c->tc_inv_scale;
+  {
+    ProfScope ps(c, "body_fwd_tc");
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_body_tc<C>, map_x, map_d, map_w, map_a, B, Vv, Vp, n_vt, n_m, inv, verts);
+    if (e != cudaSuccess) {
+      smplb_set_error("launch body_fwd_tc (cluster) failed: %s", cudaGetErrorString(e));
+      return SMPLB_ECUDA;
+    }
+  }
+  c->launches++;
   return 0;
 }
 
@@ -861,6 +925,7 @@ int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, fl
     case 2: return launch_body_cfg<BodyB>(c, B, x16, A16, verts);
     case 3: return launch_body_cfg<BodyC>(c, B, x16, A16, verts);
     case 5: return launch_body_wt(c, B, x16, A16, verts);
+    case 6: return launch_body_pair(c, B, x16, A16, verts);
     default: return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
   }
 }
