@@ -142,8 +142,10 @@ __device__ __forceinline__ float d2_expand(float ax, float ay, float a2, float b
 // candidate.  Candidates are compared with the SAME fp32 expansion as the brute-force scan
 // (and the smaller index on equal values), and the stopping rule carries a margin that bounds
 // the rounding error of that expansion, so the result is bit-identical to the full scan
-// (tests/test_gpu_parity.py::test_mesh_grid_search_equals_brute_force) at ~1/40 of the pairs.
-#define GRID_G 32
+// (tests/test_gpu_parity.py::test_mesh_grid_search_equals_brute_force) at a few percent of the pairs.
+// 64 x 64 cells (~2 points per cell for 6890 vertices, ~6 for a 10 k-pixel silhouette): 32 x 32 made
+// the pixel -> vertex search 2.9x slower, 96 x 96 the vertex -> pixel search 1.4x slower.
+#define GRID_G 64
 #define GRID_NC (GRID_G * GRID_G)
 #define GP_STRIDE 8   // x0, y0, x1, y1, inv_h, h, max |p|^2, -
 
@@ -199,9 +201,11 @@ __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restri
     atomicAdd(&hist[cy * GRID_G + cx], 1);
   }
   __syncthreads();
-  // exclusive scan of the 1024 counts: 4 cells per thread + block scan
-  int c0 = hist[4 * t], c1 = hist[4 * t + 1], c2 = hist[4 * t + 2], c3 = hist[4 * t + 3];
-  scan[t] = c0 + c1 + c2 + c3;
+  // exclusive scan of the cell counts: GRID_NC / 256 cells per thread + block scan
+  constexpr int CPT = GRID_NC / 256;
+  int cs = 0;
+  for (int q = 0; q < CPT; ++q) cs += hist[CPT * t + q];
+  scan[t] = cs;
   __syncthreads();
   for (int o = 1; o < 256; o <<= 1) {
     int v = t >= o ? scan[t - o] : 0;
@@ -209,16 +213,14 @@ __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restri
     scan[t] += v;
     __syncthreads();
   }
-  int base = scan[t] - (c0 + c1 + c2 + c3);
+  int base = scan[t] - cs;
   __syncthreads();
-  hist[4 * t] = base;                 // hist now holds the running cursors
-  hist[4 * t + 1] = base + c0;
-  hist[4 * t + 2] = base + c0 + c1;
-  hist[4 * t + 3] = base + c0 + c1 + c2;
-  gs[4 * t] = base;
-  gs[4 * t + 1] = base + c0;
-  gs[4 * t + 2] = base + c0 + c1;
-  gs[4 * t + 3] = base + c0 + c1 + c2;
+  for (int q = 0; q < CPT; ++q) {     // hist now holds the running cursors
+    int cq = hist[CPT * t + q];
+    hist[CPT * t + q] = base;
+    gs[CPT * t + q] = base;
+    base += cq;
+  }
   if (t == 255) gs[GRID_NC] = n;
   __syncthreads();
   for (int k = t; k < n; k += 256) {
@@ -580,7 +582,7 @@ int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *of
   }
   if (d_sil_pred) CUDA_TRY(cudaMemsetAsync(cnt_scratch, 0, (size_t)B * V * 2 * sizeof(int), c->cur));
   if (c->use_mesh_grid) {
-    // grid workspace: per image and set 8 floats + 1025 ints, sorted copies of both point sets
+    // grid workspace: per image and set 8 floats + GRID_NC + 1 ints, sorted copies of both point sets
     size_t need = (size_t)B * 2 * GP_STRIDE * 4 + (size_t)B * 2 * (GRID_NC + 1) * 4 + ((size_t)B * V + (size_t)P + 16) * 16 + 256;
     if (need > c->ws_grid_cap) {
       CUDA_TRY(cudaStreamSynchronize(c->stream));
