@@ -256,32 +256,53 @@ __device__ __forceinline__ void grid_search(float qx, float qy, float q2, const 
   int cy = min(GRID_G - 1, max(0, (int)((qcy - y0) * inv_h)));
   best = 3.4e38f;
   bi = 0x7fffffff;
+  auto scan = [&](int k0, int k1) {
+    for (int k = k0; k < k1; ++k) {
+      float4 cnd = sorted[k];
+      float d = QUERY_IS_A ? d2_expand(qx, qy, q2, cnd.x, cnd.y, cnd.z) : d2_expand(cnd.x, cnd.y, cnd.z, qx, qy, q2);
+      int id = __float_as_int(cnd.w);
+      if (d < best || (d == best && id < bi)) {
+        best = d;
+        bi = id;
+      }
+    }
+  };
   int rmax = max(max(cx, GRID_G - 1 - cx), max(cy, GRID_G - 1 - cy));
-  for (int r = 0; r <= rmax; ++r) {
-    int ylo = cy - r, yhi = cy + r;
-    for (int y = max(ylo, 0); y <= min(yhi, GRID_G - 1); ++y) {
-      bool full_row = (y == ylo) || (y == yhi);
-      int xa = max(cx - r, 0), xb = min(cx + r, GRID_G - 1);
-      // full rows of the ring are one contiguous cell range; inner rows contribute their two end cells
-      int nseg = full_row ? 1 : 2;
-      for (int sgi = 0; sgi < nseg; ++sgi) {
-        int c_lo, c_hi;
-        if (full_row) {
-          c_lo = y * GRID_G + xa;
-          c_hi = y * GRID_G + xb;
-        } else {
-          int x = sgi == 0 ? cx - r : cx + r;
-          if (x < 0 || x > GRID_G - 1) continue;
-          c_lo = c_hi = y * GRID_G + x;
-        }
-        for (int k = gs[c_lo]; k < gs[c_hi + 1]; ++k) {
-          float4 cnd = sorted[k];
-          float d = QUERY_IS_A ? d2_expand(qx, qy, q2, cnd.x, cnd.y, cnd.z) : d2_expand(cnd.x, cnd.y, cnd.z, qx, qy, q2);
-          int id = __float_as_int(cnd.w);
-          if (d < best || (d == best && id < bi)) {
-            best = d;
-            bi = id;
+  // Rings 0 and 1 together: ring 0 alone can never satisfy the stopping rule (0 * h), and the 3 x 3
+  // block is three contiguous cell ranges whose six range bounds load independently (the ring
+  // walk below needs five ranges and a dependent pair of loads for each).
+  {
+    int xa = max(cx - 1, 0), xb = min(cx + 1, GRID_G - 1);
+    int ya = max(cy - 1, 0), yb = min(cy + 1, GRID_G - 1);
+    int lo[3], hi[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      int y = min(ya + j, yb);
+      lo[j] = gs[y * GRID_G + xa];
+      hi[j] = (ya + j <= yb) ? gs[y * GRID_G + xb + 1] : lo[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) scan(lo[j], hi[j]);
+  }
+  for (int r = 1; r <= rmax; ++r) {
+    if (r >= 2) {
+      int ylo = cy - r, yhi = cy + r;
+      for (int y = max(ylo, 0); y <= min(yhi, GRID_G - 1); ++y) {
+        bool full_row = (y == ylo) || (y == yhi);
+        int xa = max(cx - r, 0), xb = min(cx + r, GRID_G - 1);
+        // full rows of the ring are one contiguous cell range; inner rows contribute their two end cells
+        int nseg = full_row ? 1 : 2;
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+          int c_lo, c_hi;
+          if (full_row) {
+            c_lo = y * GRID_G + xa;
+            c_hi = y * GRID_G + xb;
+          } else {
+            int x = sgi == 0 ? cx - r : cx + r;
+            if (x < 0 || x > GRID_G - 1) continue;
+            c_lo = c_hi = y * GRID_G + x;
           }
+          scan(gs[c_lo], gs[c_hi + 1]);
         }
       }
     }
