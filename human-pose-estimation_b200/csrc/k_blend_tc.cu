@@ -280,40 +280,10 @@ __global__ void k_build_dt16(int pitch, int NB, float scale, const float *__rest
 }
 
 // ------------------------------------------------------------------------------ host side
-typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static encode_fn_t g_encode = nullptr;
-
-static int get_encode() {
-  if (g_encode) return 0;
-  void *fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-  RET_IF(!fn || qres != cudaDriverEntryPointSuccess, SMPLB_ECUDA, "cuTensorMapEncodeTiled is unavailable");
-  g_encode = (encode_fn_t)fn;
-  return 0;
-}
-
-static int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, int elem_bytes, void *ptr, uint64_t inner,
-                       uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {row_stride_bytes};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  (void)elem_bytes;
-  CUresult r = g_encode(map, dt, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  RET_IF(r != CUDA_SUCCESS, SMPLB_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  return 0;
-}
-
 // Called from smplb_create: builds Dt16 and picks the power-of-two scale.
 int blend_tc_init(smplb_ctx *c) {
   c->tc_ok = false;
   if (c->NB > 10) return 0;   // the K map above reserves 10 slots per shape term
-  TRY(get_encode());
   unsigned int *d_max = nullptr;
   CUDA_TRY(cudaMalloc((void **)&d_max, 4));
   CUDA_TRY(cudaMemsetAsync(d_max, 0, 4, c->stream));
@@ -339,7 +309,7 @@ int blend_tc_init(smplb_ctx *c) {
   int sms = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
   c->num_sms = sms;
-  TRY(make_map_2d((CUtensorMap *)c->map_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c->d_Dt16, TC_KP, (uint64_t)c->pitch,
+  TRY(tc_make_map(c->map_d, 0, c->d_Dt16, TC_KP, (uint64_t)c->pitch,
                   TC_KP * 2, TC_KB, TC_BN));
   c->tc_ok = true;
   return 0;
@@ -350,8 +320,8 @@ int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed, bo
   RET_IF(!c->tc_ok || (act && !c->compact_ok), SMPLB_ESTATE, "tcgen05 blend path is not initialised");
   int pitch = act ? c->pitch_act : c->pitch;
   alignas(64) CUtensorMap map_x, map_c;
-  TRY(make_map_2d(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)x16, TC_KP, (uint64_t)B, TC_KP * 2, TC_KB, TC_BM));
-  TRY(make_map_2d(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)v_posed, (uint64_t)pitch, (uint64_t)B,
+  TRY(tc_make_map(&map_x, 0, x16, TC_KP, (uint64_t)B, TC_KP * 2, TC_KB, TC_BM));
+  TRY(tc_make_map(&map_c, 1, v_posed, (uint64_t)pitch, (uint64_t)B,
                   (uint64_t)pitch * 4, 32, 32));
   int n_mblk = cdiv(B, TC_BM * TC_MSUB), n_nblk = pitch / TC_BN;
   int total = n_mblk * n_nblk;
@@ -385,9 +355,9 @@ int compact_tc_init(smplb_ctx *c) {
                                                 (const __half *)c->d_W16, (__half *)c->d_W16_act);
   c->launches += 2;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  TRY(make_map_2d((CUtensorMap *)c->map_d_act, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c->d_Dt16_act, TC_KP,
+  TRY(tc_make_map(c->map_d_act, 0, c->d_Dt16_act, TC_KP,
                   (uint64_t)c->pitch_act, TC_KP * 2, TC_KB, TC_BN));
-  TRY(make_map_2d((CUtensorMap *)c->map_w_act, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c->d_W16_act, 64, (uint64_t)c->Vpa,
+  TRY(tc_make_map(c->map_w_act, 0, c->d_W16_act, 64, (uint64_t)c->Vpa,
                   64 * 2, 64, 128));
   c->compact_ok = true;
   return 0;

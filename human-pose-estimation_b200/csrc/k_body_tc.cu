@@ -814,28 +814,9 @@ __global__ void __launch_bounds__(BodyW::THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------ host side
-typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static encode_fn_t g_encode3 = nullptr;
-
+// operand rows of 16-bit elements, box = 64 columns (one swizzle atom) x box_rows
 static int make_map_rows16(CUtensorMap *map, const void *ptr, uint64_t row_halves, uint64_t rows, uint32_t box_rows) {
-  if (!g_encode3) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    RET_IF(!fn || qres != cudaDriverEntryPointSuccess, SMPLB_ECUDA, "cuTensorMapEncodeTiled is unavailable");
-    g_encode3 = (encode_fn_t)fn;
-  }
-  cuuint64_t dims[2] = {row_halves, rows};
-  cuuint64_t strides[1] = {row_halves * 2};
-  cuuint32_t box[2] = {64, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode3(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)ptr, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  RET_IF(r != CUDA_SUCCESS, SMPLB_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  return 0;
+  return tc_make_map(map, 0, ptr, row_halves, rows, row_halves * 2, 64, box_rows);
 }
 
 // Needs the operands of both tensor-core kernels (Dt16 + its scale, W16).

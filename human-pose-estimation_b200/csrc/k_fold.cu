@@ -544,10 +544,6 @@ __global__ void __launch_bounds__(32 * FS_WARPS)
 }
 
 // ------------------------------------------------------------------------------------- host
-int tc_make_map(void *map, int is_f32, void *ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                uint32_t box_inner, uint32_t box_outer);
-int launch_gemm_tc(smplb_ctx *c, const char *name, int M, int N, int K, const void *A16, const void *map_b, float *C,
-                   int ldc, int ksplit, float scale);
 
 __global__ void k_absmax_f(size_t n, const float *__restrict__ x, unsigned int *__restrict__ out) {
   float m = 0.f;

@@ -167,13 +167,16 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   }
 }
 
+// The one place tensor maps are encoded (cuTensorMapEncodeTiled through the runtime's driver entry
+// point, so libsmplb.so does not link libcuda): 2-D row-major tensors of fp16 (is_f32 = 0) or fp32
+// elements, box = box_inner x box_outer elements, 128-byte swizzle unless swizzle = 0.
 typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static encode_fn_t g_enc = nullptr;
 
-int tc_make_map(void *map, int is_f32, void *ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                uint32_t box_inner, uint32_t box_outer) {
+int tc_make_map(void *map, int is_f32, const void *ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                uint32_t box_inner, uint32_t box_outer, int swizzle) {
   if (!g_enc) {
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -185,9 +188,10 @@ int tc_make_map(void *map, int is_f32, void *ptr, uint64_t inner, uint64_t outer
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_enc((CUtensorMap *)map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr,
-                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_enc((CUtensorMap *)map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RET_IF(r != CUDA_SUCCESS, SMPLB_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
   return 0;
 }

@@ -271,31 +271,6 @@ __global__ void k_build_w16(int V, int Vp, const float *__restrict__ W, __half *
   W16[i] = __float2half_rn(out);
 }
 
-typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static encode_fn_t g_encode2 = nullptr;
-
-static int make_map_f16(CUtensorMap *map, void *ptr, uint64_t inner, uint64_t outer, uint32_t box_inner,
-                        uint32_t box_outer) {
-  if (!g_encode2) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    RET_IF(!fn || qres != cudaDriverEntryPointSuccess, SMPLB_ECUDA, "cuTensorMapEncodeTiled is unavailable");
-    g_encode2 = (encode_fn_t)fn;
-  }
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {inner * 2};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode2(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  RET_IF(r != CUDA_SUCCESS, SMPLB_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  return 0;
-}
-
 int skin_tc_init(smplb_ctx *c) {
   c->skin_tc_ok = false;
   CUDA_TRY(cudaMalloc((void **)&c->d_W16, (size_t)c->Vp * 64 * sizeof(__half)));
@@ -303,7 +278,7 @@ int skin_tc_init(smplb_ctx *c) {
   c->launches++;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaFuncSetAttribute(k_skin_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SM_TOTAL));
-  TRY(make_map_f16((CUtensorMap *)c->map_w, c->d_W16, ST_KP, (uint64_t)c->Vp, 64, ST_VT));
+  TRY(tc_make_map(c->map_w, 0, c->d_W16, ST_KP, (uint64_t)c->Vp, ST_KP * 2, 64, ST_VT));
   if (!c->num_sms) CUDA_TRY(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
   c->skin_tc_ok = true;
   return 0;
@@ -314,18 +289,9 @@ int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_pose
   RET_IF(!c->skin_tc_ok || (act && !c->compact_ok), SMPLB_ESTATE, "tcgen05 skinning path is not initialised");
   const int V = act ? c->n_act : c->V, Vp = act ? c->Vpa : c->Vp, pitch = act ? c->pitch_act : c->pitch;
   alignas(64) CUtensorMap map_a, map_p;
-  TRY(make_map_f16(&map_a, (void *)A16, ST_KP, (uint64_t)B * 12, 64, ST_N));
-  {
-    // v_posed [B][3 * Vp] fp32, box = 128 vertices x 16 samples of one coordinate plane, no swizzle
-    cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)B};
-    cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
-    cuuint32_t box[2] = {ST_VT, ST_S};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode2(&map_p, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)v_posed, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RET_IF(r != CUDA_SUCCESS, SMPLB_ECUDA, "cuTensorMapEncodeTiled(v_posed) failed with %d", (int)r);
-  }
+  TRY(tc_make_map(&map_a, 0, A16, ST_KP, (uint64_t)B * 12, ST_KP * 2, 64, ST_N));
+  // v_posed [B][3 * Vp] fp32, box = 128 vertices x 16 samples of one coordinate plane, no swizzle
+  TRY(tc_make_map(&map_p, 1, v_posed, (uint64_t)pitch, (uint64_t)B, (uint64_t)pitch * 4, ST_VT, ST_S, /*swizzle=*/0));
   int n_vt = Vp / ST_VT, n_ch = cdiv(B, ST_S);
   int total = n_vt * n_ch;
   int grid = total < c->num_sms ? total : c->num_sms;

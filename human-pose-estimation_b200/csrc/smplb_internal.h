@@ -242,6 +242,11 @@ int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, 
 int launch_fold_step(smplb_ctx *c, int B, const float *A, const float *cam, const float *kp_gt, float *joints,
                      float *kp_pred, float *part, int *cnt, float *d_cam, float *dA_part, float *dx_part, int ksplit);
 int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long long count_override, float *loss_parts);
+// k_gemm_tc.cu
+int tc_make_map(void *map, int is_f32, const void *ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                uint32_t box_inner, uint32_t box_outer, int swizzle = 1);
+int launch_gemm_tc(smplb_ctx *c, const char *name, int M, int N, int K, const void *A16, const void *map_b, float *C,
+                   int ldc, int ksplit, float scale);
 // k_skin_tc.cu
 int skin_tc_init(smplb_ctx *c);
 int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts, bool act);
