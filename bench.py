@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--engines", type=int, default=3, help="contexts in flight per GPU")
     ap.add_argument("--fused", type=int, default=-1, help="tuning: smplb_debug_set('fused', n) on every context")
+    ap.add_argument("--debug", action="append", default=[], help="tuning: key=value for smplb_debug_set on every context")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -239,6 +240,10 @@ def main():
     if args.fused >= 0:
         for e in engines:
             e.ctx.debug_set("fused", args.fused)
+    for kv in args.debug:
+        k, v = kv.split("=")
+        for e in engines:
+            e.ctx.debug_set(k, int(v))
     if world > 1:
         for e in engines:
             uid = [runtime.Context.comm_unique_id() if rank == 0 else None]
