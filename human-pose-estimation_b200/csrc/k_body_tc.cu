@@ -52,6 +52,15 @@
 #ifndef FB_ABLATE
 #define FB_ABLATE 0   // tuning builds: 1 = epilogue only hand-shakes (MMA-side time), 2 = no MMAs (epilogue-side time), 3 = no stores
 #endif
+#if defined(FB_ST_MODE) && FB_ST_MODE == 1
+#define FB_ST(p, v) __stcg((p), (v))
+#elif defined(FB_ST_MODE) && FB_ST_MODE == 2
+#define FB_ST(p, v) __stwt((p), (v))
+#elif defined(FB_ST_MODE) && FB_ST_MODE == 3
+#define FB_ST(p, v) (*(p) = (v))
+#else
+#define FB_ST(p, v) __stcs((p), (v))   // evict-first: verts are written once and never re-read here
+#endif
 #define FB_VT 128                     // vertices per super-tile (MMA M)
 #define FB_D_BYTES (FB_VT * 128)      // one Dt16 k-block of one plane: 16 KB
 #define FB_W_BYTES (FB_VT * 128)      // W16 tile: 16 KB
@@ -89,6 +98,38 @@ struct BodyCfg {
   static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
   static_assert(DSTAGES <= 4 && ASTAGES <= 4 && TBUF <= 2, "barrier slots");
 };
+
+// The 12 stores of a warp's 4 samples (verts[b][v][xyz]: three scalar stores 12 B apart per sample; rows
+// are only 8-byte aligned, so nothing wider) as a real call.  Inlined into the epilogue, the compiler
+// runs out of uniform registers, keeps the 64-bit global-memory descriptor that every STG needs in
+// a vector register pair and converts it back with two R2UR per store: 15 % of all instructions
+// executed, on the 16-cycle XU pipe, which ncu showed 88 % busy.  In its own frame the descriptor
+// is one uniform load.
+__device__ __noinline__ void store_rows4(float *dst, int row_stride, int rows_left, bool v_ok, float a0, float a1, float a2,
+                                         float b0, float b1, float b2, float c0, float c1, float c2, float d0, float d1,
+                                         float d2) {
+  if (!v_ok) return;
+  if (rows_left > 0) {
+    FB_ST(dst, a0);
+    FB_ST(dst + 1, a1);
+    FB_ST(dst + 2, a2);
+  }
+  if (rows_left > 1) {
+    FB_ST(dst + row_stride, b0);
+    FB_ST(dst + row_stride + 1, b1);
+    FB_ST(dst + row_stride + 2, b2);
+  }
+  if (rows_left > 2) {
+    FB_ST(dst + 2 * row_stride, c0);
+    FB_ST(dst + 2 * row_stride + 1, c1);
+    FB_ST(dst + 2 * row_stride + 2, c2);
+  }
+  if (rows_left > 3) {
+    FB_ST(dst + 3 * row_stride, d0);
+    FB_ST(dst + 3 * row_stride + 1, d1);
+    FB_ST(dst + 3 * row_stride + 2, d2);
+  }
+}
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1)
@@ -415,14 +456,19 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           // verts[b][v][xyz]: three scalar stores 12 B apart per sample.  Rows are only 8-byte aligned
           // (82,680 B), so no 16-byte or bulk stores; 8-byte stores were measured slower both ways
           // (transposed through shared memory: 162 us; lane pairs with one shuffle: 135 us; this: 127 us)
+          if (HS == 4) {
+            store_rows4(vbase + s_loc * (V * 3), V * 3, b_left - s_loc, v_ok, o[0][0], o[0][1], o[0][2], o[1][0], o[1][1], o[1][2],
+                        o[2 % HS][0], o[2 % HS][1], o[2 % HS][2], o[3 % HS][0], o[3 % HS][1], o[3 % HS][2]);
+          } else {
 #pragma unroll
-          for (int si = 0; si < HS; ++si) {
-            const int sl = s_loc + si;
-            if (sl < b_left && v_ok) {
-              float *dst = vbase + sl * (V * 3);
-              __stcs(dst, o[si][0]);
-              __stcs(dst + 1, o[si][1]);
-              __stcs(dst + 2, o[si][2]);
+            for (int si = 0; si < HS; ++si) {
+              const int sl = s_loc + si;
+              if (sl < b_left && v_ok) {
+                float *dst = vbase + sl * (V * 3);
+                FB_ST(dst, o[si][0]);
+                FB_ST(dst + 1, o[si][1]);
+                FB_ST(dst + 2, o[si][2]);
+              }
             }
           }
         }
