@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_full = bar0 + 80, tmem_empty = bar0 + 96;
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + SM_BAR_OFF + 120);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the shuffle tells the compiler the warp index is warp-uniform: role branches and the addresses
+  // derived from it stay in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int total = n_mblk * n_nblk;          // n_mblk counts 256-sample super blocks
   const int t0 = (int)(((long long)blockIdx.x * total) / gridDim.x);
   const int t1 = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);

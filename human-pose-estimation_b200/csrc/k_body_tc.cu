@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(C::THREADS, 1)
   const uint32_t t_full = bar0 + 192, t_empty = bar0 + 208;   // C::TBUF (<= 2) each
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + C::SM_BAR + 224);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the shuffle tells the compiler the warp index is warp-uniform: role branches and the addresses
+  // derived from it stay in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // Super-tile t of this CTA (or, CL = 2, of this cluster) -> sample block t / n_vt (times two plus
   // the CTA's rank in the pair), vertex tile t % n_vt.
   const int crank = C::CL == 2 ? (int)cluster_ctarank() : 0;
@@ -590,7 +592,9 @@ __global__ void __launch_bounds__(BodyW::THREADS, 1)
   const uint32_t t_full = bar0 + 192, t_empty = bar0 + 208;   // TBUF (<= 2) each
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + C::SM_BAR + 224);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the shuffle tells the compiler the warp index is warp-uniform: role branches and the addresses
+  // derived from it stay in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int total = n_vt * n_m;
   const int t0 = (int)(((long long)blockIdx.x * total) / gridDim.x);
   const int t1 = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);

@@ -33,7 +33,9 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   const uint32_t bar0 = sbase + G_SM_BAR;
   const uint32_t full = bar0 + 0, empty = bar0 + 32, tmem_full = bar0 + 64, tmem_empty = bar0 + 80;
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + G_SM_BAR + 96);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the shuffle tells the compiler the warp index is warp-uniform: role branches and the addresses
+  // derived from it stay in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int total = n_mblk * n_nblk * ksplit;
   const int kb_per = (n_kblk + ksplit - 1) / ksplit;
 

@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
   const uint32_t full_p = bar0 + 128, empty_p = bar0 + 160;
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + ST_SM_BAR + 96);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the shuffle tells the compiler the warp index is warp-uniform: role branches and the addresses
+  // derived from it stay in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int total = n_vt * n_ch;
   const int t0 = (int)(((long long)blockIdx.x * total) / gridDim.x);
   const int t1 = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
