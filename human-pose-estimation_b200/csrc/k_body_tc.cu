@@ -455,9 +455,11 @@ __global__ void __launch_bounds__(C::THREADS, 1)
         }
         if (FB_ABLATE == 3) {
         } else {
-          // verts[b][v][xyz]: three scalar stores 12 B apart per sample.  Rows are only 8-byte aligned
-          // (82,680 B), so no 16-byte or bulk stores; 8-byte stores were measured slower both ways
-          // (transposed through shared memory: 162 us; lane pairs with one shuffle: 135 us; this: 127 us)
+          // verts[b][v][xyz]: three scalar stores 12 B apart per sample.  A build without the stores
+          // is 37 % faster, but how they are issued is not the lever: 8-byte stores (transposed through
+          // shared memory +28 %, lane pairs with one shuffle +7 %) and rows staged in shared memory and
+          // written with cp.async.bulk copies (+17 %; rows are 8-byte aligned, so odd rows need a
+          // scalar head and tail) were all measured slower than this
           if (HS == 4) {
             store_rows4(vbase + s_loc * (V * 3), V * 3, b_left - s_loc, v_ok, o[0][0], o[0][1], o[0][2], o[1][0], o[1][1], o[1][2],
                         o[2 % HS][0], o[2 % HS][1], o[2 % HS][2], o[3 % HS][0], o[3 % HS][1], o[3 % HS][2]);
