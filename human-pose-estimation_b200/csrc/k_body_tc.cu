@@ -18,18 +18,19 @@
 // shapes are chosen to keep the instruction count per sample low under the 512-column TMEM
 // budget: 3 * NS (P) + TBUF * 12 * ST (T) <= 512.
 //
-// What bounds it (tools/fused_timing.py builds, profiles/r01/v7_*): the hand-shake chain of a
-// skinning tile -- T stage released -> issuer wakes -> 5 MMAs through the tensor pipe -> commit ->
-// epilogue wakes -> tcgen05.ld -> release -- is ~1000-1200 clk long and only two T stages (next to the
-// 288 columns of P) fit in TMEM, so a tile retires every ~600 clk whatever the MMAs cost: a build
-// without any MMA is as fast as one without any epilogue work (161 k vs 165 k clk of 204 k), and
-// the stores add the rest.  Shared-memory traffic (~1.1 MB per super-tile, 8.5 k clk at 128 B/clk
-// of the ~13 k) is the next limit, not the current one: moving the W16 operand to TMEM (k_body_wt
-// below) changed nothing.  Also measured equal or slower: a second set of epilogue warps, four
-// instead of two epilogue warps per lane quarter (EW = 4: 137 vs 129 us), a software-pipelined
-// (two register sets) epilogue, N = 192 skinning MMAs with a single T stage, plain instead of
-// evict-first stores (+5 %), 8-byte stores (transposed through shared memory +28 %, lane pairs +7 %),
-// CTA pairs with the Dt16 k-blocks multicast (CL = 2, +5 %: the L2 reads are not the limit either).
+// What bounds it (tools/fused_timing.py builds with -DFB_TIMING / -DFB_ABLATE, profiles/r01): the
+// bytes an SM exchanges with L2.  Per launch every SM reads 5.7 MB of operands (per super-tile 192 KB
+// of Dt16, 144 KB of A16, 16 KB of W16, and the x16 tile per sample block) and writes 2.3 MB of
+// verts (+20 % for partially written sectors): 8.5 MB in ~177 k clk = 48 B/clk/SM.  The same rate
+// shows in every ablation -- without stores 111 k clk for the reads alone; stores redirected to
+// lines that stay in L2 (no HBM traffic) change nothing; neither does the way the stores are
+// issued (8-byte stores, bulk copies from shared memory) nor multicasting the Dt16 stream to a CTA
+// pair (the bytes still enter each SM) nor keeping W16 in TMEM (it removes shared-memory reads,
+// not L2 reads).  What did help was instruction-level: warp-uniform MMA issue (157 -> 135 us),
+// separate issuer warps (-> 134), the early v_posed fetch (-> 127), the stores as a real call and
+// the warp index through a shuffle, both of which keep the hot loops in uniform registers
+// (-> 119).  The remaining lever is fewer bytes per SM: cta_group::2 MMAs share the "B" operands
+// (A16, x16) of a CTA pair through the pair's shared memory (-20 % of the reads).
 //
 // Persistent, warp-specialised: warp 0 TMA producer of the blend operands, warp 1 blend MMA issuer
 // and TMEM allocator, warp 2 TMA producer of the skinning operands, warp 3 skinning MMA issuer,
@@ -388,8 +389,10 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       const int m = (t / n_vt) * C::CL + crank, vt = t % n_vt;
       const int v0 = vt * FB_VT + 32 * q;
       const bool v_ok = v0 + lane < V;
-      float *const vbase = verts + ((size_t)(m * C::NS) * V + v0 + lane) * 3;
-      const int b_left = B - m * C::NS;           // samples of this super-tile inside the batch (<= 0: a padding block)
+      // (FB_ABLATE == 4: every super-tile writes the rows of sample block 0 -- same store instructions and
+      // L2 traffic, but the lines are overwritten in L2 and never reach HBM)
+      float *const vbase = verts + ((size_t)((FB_ABLATE == 4 ? 0 : m) * C::NS) * V + v0 + lane) * 3;
+      const int b_left = FB_ABLATE == 4 ? C::NS : B - m * C::NS;   // samples of this super-tile inside the batch (<= 0: a padding block)
 
       // the three coordinates of HS samples' v_posed (columns s_loc.. of the three planes of P)
       auto load_p = [&](int s_loc, uint32_t(*pc)[HS]) {
