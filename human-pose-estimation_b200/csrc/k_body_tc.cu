@@ -14,9 +14,9 @@
 // MMA shapes: blend M = 128 (vertices; "A" = a Dt16 k-block of one coordinate plane streamed through
 // a ring), N = NS (samples; "B" = the x16 tile, resident for all vertex tiles of the sample block),
 // 15 K-steps per plane; skinning M = 128, N = 12 * ST, five K-steps (window layout of
-// k_skin_tc.cu).  A tcgen05.mma costs >= ~100 clk whatever its N (tools/micro/tmem_rate.cu), so the
-// shapes are chosen to keep the instruction count per sample low under the 512-column TMEM
-// budget: 3 * NS (P) + TBUF * 12 * ST (T) <= 512.
+// k_skin_tc.cu).  An MMA of these shapes takes 56 clk when it is issued from warp-uniform code (40
+// clk is the floor for any shape, tools/micro/tmem_rate.cu); the shapes are what fits the 512-column
+// TMEM budget, 3 * NS (P) + TBUF * 12 * ST (T) <= 512, with two T stages.
 //
 // What bounds it (tools/fused_timing.py builds with -DFB_TIMING / -DFB_ABLATE, profiles/r01): the
 // bytes an SM exchanges with L2.  Per launch every SM reads 5.7 MB of operands (per super-tile 192 KB
@@ -34,8 +34,7 @@
 //
 // Persistent, warp-specialised: warp 0 TMA producer of the blend operands, warp 1 blend MMA issuer
 // and TMEM allocator, warp 2 TMA producer of the skinning operands, warp 3 skinning MMA issuer,
-// warps 4.. epilogue (one set of 8
-// warps per T stage; two warps per TMEM lane quarter, each half of a tile's samples).
+// warps 4-11 epilogue (two warps per TMEM lane quarter, each half of a tile's samples).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdio.h>
@@ -51,17 +50,11 @@
 #define TADD(acc, t)
 #endif
 #ifndef FB_ABLATE
-#define FB_ABLATE 0   // tuning builds: 1 = epilogue only hand-shakes (MMA-side time), 2 = no MMAs (epilogue-side time), 3 = no stores
+#define FB_ABLATE 0   // tuning builds: 1 = epilogue only hand-shakes (MMA-side time), 2 = no MMAs (epilogue-side time),
+                      // 3 = no stores, 4 = stores to lines that stay in L2
 #endif
-#if defined(FB_ST_MODE) && FB_ST_MODE == 1
-#define FB_ST(p, v) __stcg((p), (v))
-#elif defined(FB_ST_MODE) && FB_ST_MODE == 2
-#define FB_ST(p, v) __stwt((p), (v))
-#elif defined(FB_ST_MODE) && FB_ST_MODE == 3
-#define FB_ST(p, v) (*(p) = (v))
-#else
-#define FB_ST(p, v) __stcs((p), (v))   // evict-first: verts are written once and never re-read here
-#endif
+// evict-first stores: verts are written once and never re-read here (.cg, .wt and plain stores: +7 %)
+#define FB_ST(p, v) __stcs((p), (v))
 #define FB_VT 128                     // vertices per super-tile (MMA M)
 #define FB_D_BYTES (FB_VT * 128)      // one Dt16 k-block of one plane: 16 KB
 #define FB_W_BYTES (FB_VT * 128)      // W16 tile: 16 KB
@@ -71,8 +64,8 @@ template <int NS_, int ST_, int TBUF_, int DSTAGES_ = 4, int ASTAGES_ = 3, int P
 struct BodyCfg {
   static constexpr int NS = NS_, ST = ST_, TBUF = TBUF_, DSTAGES = DSTAGES_, ASTAGES = ASTAGES_, PRE = PRE_, EW = EW_;
   // CL = 2: the kernel runs as clusters of two CTAs that walk the same vertex tiles on adjacent
-  // sample blocks, so every Dt16 k-block is read from L2 once and multicast to both (the kernel is
-  // bound by L2 throughput: ~1.26 GB of operand reads + output writes per launch)
+  // sample blocks, so every Dt16 k-block is read from L2 once and multicast to both (measured: no
+  // gain, the bytes still enter each SM)
   static constexpr int CL = CL_;
   static constexpr int TN = 12 * ST;            // skinning MMA N
   static constexpr int NT = NS / ST;            // skinning tiles per super-tile
