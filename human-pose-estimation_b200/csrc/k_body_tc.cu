@@ -86,7 +86,7 @@ struct BodyCfg {
   static constexpr int THREADS = 32 * (4 + 4 * EW);
   static_assert(NT % TBUF == 0 && PRE < NT, "tile counts");
   static_assert(HS == 2 || HS == 4 || HS == 8, "samples per epilogue warp");
-  static_assert(NS % 16 == 0 && NS % ST == 0 && ST % 8 == 0, "tile shape");
+  static_assert(NS % 16 == 0 && NS % ST == 0 && ST % 4 == 0, "tile shape");
   static_assert(3 * NS + TBUF * TN <= 512, "TMEM budget");
   static_assert(X_KB_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "swizzle atoms need 1024 B alignment");
   static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
@@ -870,7 +870,7 @@ static int make_map_rows16(CUtensorMap *map, const void *ptr, uint64_t row_halve
 // Needs the operands of both tensor-core kernels (Dt16 + its scale, W16).
 using BodyA = BodyCfg<96, 8, 2, 4, 3, 4>;   // default: double-buffered T, v_posed of the last 4 tiles fetched early
 using BodyB = BodyCfg<96, 8, 2, 4, 3, 0>;   // no early fetch (the blend is exposed)
-using BodyC = BodyCfg<128, 8, 1, 4, 3, 4>;   // 128-sample super-tiles (25 % fewer Dt16 bytes per sample), single T stage
+using BodyC = BodyCfg<128, 4, 2, 4, 4, 8>;   // 128-sample super-tiles (25 % fewer Dt16 bytes per sample), two 4-sample T stages
 using BodyP = BodyCfg<96, 8, 2, 4, 3, 4, 2, 2>;  // CTA pairs, Dt16 multicast
 
 int body_tc_init(smplb_ctx *c) {

@@ -16,7 +16,7 @@ ctx = smpl.ctx
 inp = synthetic.make_inputs(B, seed=1000)
 d = {k: ctx.to_device(v) for k, v in inp.items()}
 out = {}
-names = {0: "two kernels", 1: "NS=96 ST=8 x2 PRE=4", 2: "NS=96 ST=8 x2 PRE=0", 3: "NS=128 ST=8 x1 PRE=4", 5: "W16 in TMEM, vertex-tile major", 6: "CTA pairs, Dt16 multicast"}
+names = {0: "two kernels", 1: "NS=96 ST=8 x2 PRE=4", 2: "NS=96 ST=8 x2 PRE=0", 3: "NS=128 ST=4 x2 PRE=8", 5: "W16 in TMEM, vertex-tile major", 6: "CTA pairs, Dt16 multicast"}
 for variant in (0, 1, 2, 3, 5, 6):
     ctx.debug_set("fused", variant)
     for it in range(3):
