@@ -433,6 +433,42 @@ def test_fused_keypoint_forward_backward_matches_separate_kernels(smpl_full):
         assert not a["d_theta"][1].any() and not a["d_cam"][1].any()     # sample 1 has no visible keypoint
 
 
+def test_many_keypoints_and_trace_mode():
+    """(a) A regressor with more keypoints than k_fold_step_w stages in shared memory (24 * 3 * K
+    floats > 1536, i.e. K > 21) takes the separate forward / backward kernels: results against the
+    oracle.  (b) The timeline trace (smplb_profile_enable(ctx, 2)) lists every launch of a step
+    with start <= end, without serialising the streams."""
+    import scipy.sparse as sp
+    model = synthetic.make_model(seed=3, num_verts=300, regressor_nnz=8)
+    rng = np.random.default_rng(9)
+    extra = synthetic._sparse_regressor(rng, 7, 300, 8)
+    model["cocoplus_regressor"] = sp.vstack([model["cocoplus_regressor"], extra]).tocsc()
+    s = SMPL(model, max_batch=16)
+    K = s.num_keypoints
+    assert K == 26
+    B = 11
+    inp = synthetic.make_inputs(B, seed=5)
+    kp_gt = np.concatenate([inp["kp_gt"], inp["kp_gt"][:, :7]], axis=1).astype(np.float32)
+    s.ctx.profile(2)
+    out = s.step(inp["beta"], inp["theta"], inp["cam"], kp_gt, w_kp=1.0)
+    trace = s.ctx.profile_trace()
+    s.ctx.profile(0)
+    names = [n for n, _, _ in trace]
+    assert "pose_fwd" in names and "pose_bwd" in names and "fold_step_fwd_bwd" not in names
+    assert all(t1 >= t0 for _, t0, t1 in trace)
+    o = onp.SMPL(model, dtype=np.float64)
+    b = {k: v.astype(np.float64) for k, v in inp.items()}
+    verts, joints, Rs = o(b["beta"], b["theta"], get_skin=True)
+    kp = onp.batch_orth_proj_idrot(joints, b["cam"])
+    assert rel_err(out["verts"], verts) < TOL and rel_err(out["joints"], joints) < TOL
+    num, cnt = onp.kp_loss_parts(kp_gt.astype(np.float64), kp)
+    assert int(out["loss_parts"][1]) == cnt
+    assert abs(out["loss_parts"][3] - num / cnt) < TOL * num / cnt
+    dj, dcam = onp.orth_proj_backward(joints, b["cam"], onp.kp_loss_backward(kp_gt.astype(np.float64), kp))
+    db, dth = onp.smpl_backward(o, b["beta"], b["theta"], None, dj, None)
+    assert rel_err(out["d_beta"], db) < TOL and rel_err(out["d_theta"], dth) < TOL and rel_err(out["d_cam"], dcam) < TOL
+
+
 def test_folded_keypoint_path_matches_per_vertex_path(smpl_full):
     """joints / kp loss / gradients from the folded formulation (G x, no vertices) against the
     per-vertex keypoint path; both are checked against the oracle elsewhere, this pins them to
