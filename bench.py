@@ -104,7 +104,8 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def finish(self):
+    def finish(self, first_row=0):
+        """Clocks over the samples taken from row `first_row` on (the ones under load)."""
         self.stop_flag = True
         if self.proc:
             try:
@@ -112,7 +113,7 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[first_row:]:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -278,7 +279,10 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.15)
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 8.0:      # nvidia-smi takes a while to start on an 8-GPU box
+        time.sleep(0.05)
+    rows0 = len(sampler.rows)
     launches0 = sum(e.ctx.launch_count() for e in engines)
     barrier()
     ctx.timer_start(0)
@@ -299,8 +303,13 @@ def main():
         gpu_step(i, 1)
     prof = ctx.profile_read()
     ctx.profile(False)
+    # the timed region is ~0.1 s: keep the same load running (untimed, the same number of steps on every
+    # rank: the steps all-reduce) for another ~0.4 s so that nvidia-smi samples the clocks under it
+    for i in range(2000):
+        gpu_step(i)
+    sync_all()
     barrier()
-    clocks = sampler.finish()
+    clocks = sampler.finish(rows0)
     loss_parts = outs[0]["loss_parts"].numpy()
 
     # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region.
