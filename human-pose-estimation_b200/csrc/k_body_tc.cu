@@ -53,11 +53,7 @@
 #define FB_ABLATE 0   // tuning builds: 1 = epilogue only hand-shakes (MMA-side time), 2 = no MMAs (epilogue-side time),
                       // 3 = no stores, 4 = stores to lines that stay in L2
 #endif
-// evict-first stores: verts are written once and never re-read here (.cg, .wt and plain stores: +7 %)
-#define FB_ST(p, v) __stcs((p), (v))
-#define FB_VT 128                     // vertices per super-tile (MMA M)
-#define FB_D_BYTES (FB_VT * 128)      // one Dt16 k-block of one plane: 16 KB
-#define FB_W_BYTES (FB_VT * 128)      // W16 tile: 16 KB
+#include "body_common.cuh"
 
 // NS samples per super-tile (blend MMA N), ST samples per skinning MMA, TBUF T accumulator stages.
 template <int NS_, int ST_, int TBUF_, int DSTAGES_ = 4, int ASTAGES_ = 3, int PRE_ = 0, int EW_ = 2, int CL_ = 1>
@@ -92,38 +88,6 @@ struct BodyCfg {
   static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
   static_assert(DSTAGES <= 4 && ASTAGES <= 4 && TBUF <= 2, "barrier slots");
 };
-
-// The 12 stores of a warp's 4 samples (verts[b][v][xyz]: three scalar stores 12 B apart per sample; rows
-// are only 8-byte aligned, so nothing wider) as a real call.  Inlined into the epilogue, the compiler
-// runs out of uniform registers, keeps the 64-bit global-memory descriptor that every STG needs in
-// a vector register pair and converts it back with two R2UR per store: 15 % of all instructions
-// executed, on the 16-cycle XU pipe, which ncu showed 88 % busy.  In its own frame the descriptor
-// is one uniform load.
-__device__ __noinline__ void store_rows4(float *dst, int row_stride, int rows_left, bool v_ok, float a0, float a1, float a2,
-                                         float b0, float b1, float b2, float c0, float c1, float c2, float d0, float d1,
-                                         float d2) {
-  if (!v_ok) return;
-  if (rows_left > 0) {
-    FB_ST(dst, a0);
-    FB_ST(dst + 1, a1);
-    FB_ST(dst + 2, a2);
-  }
-  if (rows_left > 1) {
-    FB_ST(dst + row_stride, b0);
-    FB_ST(dst + row_stride + 1, b1);
-    FB_ST(dst + row_stride + 2, b2);
-  }
-  if (rows_left > 2) {
-    FB_ST(dst + 2 * row_stride, c0);
-    FB_ST(dst + 2 * row_stride + 1, c1);
-    FB_ST(dst + 2 * row_stride + 2, c2);
-  }
-  if (rows_left > 3) {
-    FB_ST(dst + 3 * row_stride, d0);
-    FB_ST(dst + 3 * row_stride + 1, d1);
-    FB_ST(dst + 3 * row_stride + 2, d2);
-  }
-}
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1)
@@ -881,6 +845,7 @@ int body_tc_init(smplb_ctx *c) {
   CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyC::SM_TOTAL));
   CUDA_TRY(cudaFuncSetAttribute(k_body_wt, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyW::SM_TOTAL));
   CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyP>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyP::SM_TOTAL));
+  TRY(body_pair_init(c));
   c->body_tc_ok = true;
   return 0;
 }
@@ -955,6 +920,9 @@ int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, fl
     case 3: return launch_body_cfg<BodyC>(c, B, x16, A16, verts);
     case 5: return launch_body_wt(c, B, x16, A16, verts);
     case 6: return launch_body_pair(c, B, x16, A16, verts);
+    case 7:
+      if ((c->Vp / FB_VT) % 2 == 0) return launch_body_fwd_pair(c, B, x16, A16, verts);
+      return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
     default: return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
   }
 }

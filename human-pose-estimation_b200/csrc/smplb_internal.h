@@ -254,6 +254,9 @@ int compact_tc_init(smplb_ctx *c);
 // k_body_tc.cu
 int body_tc_init(smplb_ctx *c);
 int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts);
+// k_body_pair.cu (cta_group::2 variant; needs an even number of 128-vertex tiles)
+int body_pair_init(smplb_ctx *c);
+int launch_body_fwd_pair(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts);
 // k_skin.cu
 int launch_skin_fwd(smplb_ctx *c, int B, const float *A, const float *v_posed, float *verts);
 int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, const float *kp_gt, float *joints,

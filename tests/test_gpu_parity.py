@@ -382,8 +382,8 @@ def test_fused_blend_skinning_matches_two_kernel_path(smpl_full, full_model):
             ctx.debug_set("fused", 0)
             v0, j0, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
             # 1: the default configuration; 2, 3: tuning variants; 5: W16 as a TMEM-resident operand;
-            # 6: CTA pairs with the Dt16 tiles multicast
-            for variant in (1, 2, 3, 5, 6):
+            # 6: CTA pairs with the Dt16 tiles multicast; 7: CTA pairs with cta_group::2 MMAs (k_body_pair)
+            for variant in (1, 2, 3, 5, 6, 7):
                 ctx.debug_set("fused", variant)
                 v1, j1, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
                 assert np.isfinite(v1).all()
