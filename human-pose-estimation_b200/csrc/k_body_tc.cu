@@ -832,7 +832,7 @@ static int make_map_rows16(CUtensorMap *map, const void *ptr, uint64_t row_halve
 }
 
 // Needs the operands of both tensor-core kernels (Dt16 + its scale, W16).
-using BodyA = BodyCfg<96, 8, 2, 4, 3, 4>;   // default: double-buffered T, v_posed of the last 4 tiles fetched early
+using BodyA = BodyCfg<96, 8, 2, 4, 3, 4>;   // best single-CTA configuration: double-buffered T, v_posed of the last 4 tiles fetched early
 using BodyB = BodyCfg<96, 8, 2, 4, 3, 0>;   // no early fetch (the blend is exposed)
 using BodyC = BodyCfg<128, 4, 2, 4, 4, 8>;   // 128-sample super-tiles (25 % fewer Dt16 bytes per sample), two 4-sample T stages
 using BodyP = BodyCfg<96, 8, 2, 4, 3, 4, 2, 2>;  // CTA pairs, Dt16 multicast
@@ -912,17 +912,19 @@ static int launch_body_wt(smplb_ctx *c, int B, const void *x16, const void *A16,
 }
 
 // verts [B][V][3] from the operand rows pose_fwd wrote (x16 [B][256], A16 [12 B][64]).
-// smplb_debug_set("fused", 2 | 3) selects the alternative configurations (tuning / validation).
+// Default: the CTA-pair kernel of k_body_pair.cu (it needs an even number of 128-vertex tiles; SMPL
+// has 54).  smplb_debug_set("fused", 2 .. 6) selects the single-CTA configurations of this file
+// (tuning / validation; 4 = the best of them, which is also the fallback).
 int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts) {
   RET_IF(!c->body_tc_ok, SMPLB_ESTATE, "fused tcgen05 blend+skinning path is not initialised");
   switch (c->use_fused) {
     case 2: return launch_body_cfg<BodyB>(c, B, x16, A16, verts);
     case 3: return launch_body_cfg<BodyC>(c, B, x16, A16, verts);
+    case 4: return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
     case 5: return launch_body_wt(c, B, x16, A16, verts);
     case 6: return launch_body_pair(c, B, x16, A16, verts);
-    case 7:
+    default:
       if ((c->Vp / FB_VT) % 2 == 0) return launch_body_fwd_pair(c, B, x16, A16, verts);
       return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
-    default: return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
   }
 }

@@ -370,7 +370,7 @@ def test_tcgen05_skinning_matches_fp32_kernel(smpl_full):
 
 
 def test_fused_blend_skinning_matches_two_kernel_path(smpl_full, full_model):
-    """k_body_tc (blend + skinning in one kernel, v_posed stays in TMEM) against k_blend_tc +
+    """k_body_pair / k_body_tc (blend + skinning in one kernel, v_posed stays in TMEM) against k_blend_tc +
     k_skin_tc: the same fp16 operands and fp32 accumulation, so the two may differ only by fp32
     summation order; and against the fp64 oracle at the stated tolerance.  Batch sizes straddle
     the 96-sample super-tile and the 8-sample skinning tile (ragged tails)."""
@@ -381,9 +381,10 @@ def test_fused_blend_skinning_matches_two_kernel_path(smpl_full, full_model):
         try:
             ctx.debug_set("fused", 0)
             v0, j0, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
-            # 1: the default configuration; 2, 3: tuning variants; 5: W16 as a TMEM-resident operand;
-            # 6: CTA pairs with the Dt16 tiles multicast; 7: CTA pairs with cta_group::2 MMAs (k_body_pair)
-            for variant in (1, 2, 3, 5, 6, 7):
+            # 1: the default (CTA pairs with cta_group::2 MMAs, k_body_pair); 4: the best single-CTA
+            # configuration; 2, 3: tuning variants; 5: W16 as a TMEM-resident operand; 6: CTA pairs
+            # with the Dt16 tiles multicast
+            for variant in (1, 2, 3, 4, 5, 6):
                 ctx.debug_set("fused", variant)
                 v1, j1, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
                 assert np.isfinite(v1).all()

@@ -16,8 +16,9 @@ ctx = smpl.ctx
 inp = synthetic.make_inputs(B, seed=1000)
 d = {k: ctx.to_device(v) for k, v in inp.items()}
 out = {}
-names = {0: "two kernels", 1: "NS=96 ST=8 x2 PRE=4", 2: "NS=96 ST=8 x2 PRE=0", 3: "NS=128 ST=4 x2 PRE=8", 5: "W16 in TMEM, vertex-tile major", 6: "CTA pairs, Dt16 multicast", 7: "CTA pairs, cta_group::2 MMAs"}
-for variant in (0, 1, 2, 3, 5, 6, 7):
+names = {0: "two kernels", 1: "CTA pairs, cta_group::2 MMAs (default)", 2: "NS=96 ST=8 x2 PRE=0", 3: "NS=128 ST=4 x2 PRE=8",
+         4: "NS=96 ST=8 x2 PRE=4 (best single-CTA)", 5: "W16 in TMEM, vertex-tile major", 6: "CTA pairs, Dt16 multicast"}
+for variant in (0, 1, 2, 3, 4, 5, 6):
     ctx.debug_set("fused", variant)
     for it in range(3):
         smpl.step(d["beta"], d["theta"], d["cam"], d["kp_gt"], out=out)
@@ -29,4 +30,4 @@ for variant in (0, 1, 2, 3, 5, 6, 7):
     prof = ctx.profile_read()
     ctx.profile(False)
     heavy = sum(ms for k, (ms, n) in prof.items() if k in ("body_fwd_tc", "blend_fwd_tc", "skin_fwd_tc")) / N
-    print("variant %d (%-15s): %.1f us" % (variant, names[variant], heavy * 1e3))
+    print("variant %d (%-40s): %.1f us" % (variant, names[variant], heavy * 1e3))
