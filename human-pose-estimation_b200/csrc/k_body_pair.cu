@@ -374,9 +374,12 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------ host side
-// (ring depths and the early-fetch depth make no difference here: 6 or 8 Dt16 stages, 4 A16 stages,
-// PRE = 2 / 6 all measured 106-109 us; this is the smallest footprint, 136 KB of shared memory)
-using PairA = PairCfg<96, 8, 4, 3, 4>;
+// Ring depths make no difference to the kernel alone (6 or 8 Dt16 stages, 4 A16 stages: 106-109 us).
+// The early-fetch depth does, through the register count: PRE = 4 is the fastest alone (126
+// registers, 106 us), PRE = 2 needs 96 registers (109 us) and leaves the kernels of the other
+// contexts in flight room for twice as many co-resident warps -- the step is 2.5 % faster with it;
+// PRE = 0 (78 registers, 115 us) loses more than it frees.  136 KB of shared memory.
+using PairA = PairCfg<96, 8, 4, 3, 2>;
 
 int body_pair_init(smplb_ctx *c) {
   CUDA_TRY(cudaFuncSetAttribute(k_body_pair<PairA>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairA::SM_TOTAL));
@@ -390,7 +393,8 @@ static int launch_pair_cfg(smplb_ctx *c, int B, const void *x16, const void *A16
   TRY(tc_make_map(&map_a, 0, A16, 64, (uint64_t)B * 12, 128, 64, C::TN / 2));
   const int n_vp = c->Vp / (2 * FB_VT), n_m = cdiv(B, C::NS);
   const int total = n_vp * n_m;
-  const int grid = 2 * (total < c->num_sms / 2 ? total : c->num_sms / 2);
+  const int max_pairs = c->body_pairs > 0 && c->body_pairs < c->num_sms / 2 ? c->body_pairs : c->num_sms / 2;
+  const int grid = 2 * (total < max_pairs ? total : max_pairs);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(C::THREADS);

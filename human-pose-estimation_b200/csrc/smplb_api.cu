@@ -575,6 +575,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->use_fused = value;
     return 0;
   }
+  if (!strcmp(key, "body_pairs")) {
+    c->body_pairs = value;
+    return 0;
+  }
   if (!strcmp(key, "skin_tc")) {
     c->use_skin_tc = value;
     return 0;
