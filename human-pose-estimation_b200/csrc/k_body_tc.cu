@@ -29,8 +29,10 @@
 // not L2 reads).  What did help was instruction-level: warp-uniform MMA issue (157 -> 135 us),
 // separate issuer warps (-> 134), the early v_posed fetch (-> 127), the stores as a real call and
 // the warp index through a shuffle, both of which keep the hot loops in uniform registers
-// (-> 119).  The remaining lever is fewer bytes per SM: cta_group::2 MMAs share the "B" operands
-// (A16, x16) of a CTA pair through the pair's shared memory (-20 % of the reads).
+// (-> 119).  Fewer bytes per SM is what k_body_pair.cu does: cta_group::2 MMAs share the "B"
+// operands (A16, x16) of a CTA pair through the pair's shared memory (-20 % of the reads, 107 us).
+// That kernel is the default; this one is its single-CTA form (variant 4, and the fallback when the
+// number of 128-vertex tiles is odd).
 //
 // Persistent, warp-specialised: warp 0 TMA producer of the blend operands, warp 1 blend MMA issuer
 // and TMEM allocator, warp 2 TMA producer of the skinning operands, warp 3 skinning MMA issuer,
