@@ -411,6 +411,26 @@ def test_fused_blend_skinning_matches_two_kernel_path(smpl_full, full_model):
         assert rel_err(a, b) < 2e-6
 
 
+def test_fused_blend_skinning_small_vertex_counts():
+    """The CTA-pair kernel needs an even number of 128-vertex tiles: 200 vertices = 2 tiles = one
+    pair (its second tile mostly padding), 300 = 3 tiles -> single-CTA fallback, 700 = 6 tiles = 3
+    pairs; each against the two-kernel path and the fp64 oracle."""
+    for nv in (200, 300, 700):
+        model = synthetic.make_model(seed=nv, num_verts=nv, regressor_nnz=8)
+        s = SMPL(model, max_batch=128)
+        o = onp.SMPL(model, dtype=np.float64)
+        for B in (3, 101):
+            inp = synthetic.make_inputs(B, seed=nv + B)
+            s.ctx.debug_set("fused", 0)
+            v0, j0, _ = s(inp["beta"], inp["theta"], get_skin=True)
+            s.ctx.debug_set("fused", 1)
+            v1, j1, _ = s(inp["beta"], inp["theta"], get_skin=True)
+            assert v1.shape == (B, nv, 3) and np.isfinite(v1).all()
+            assert rel_err(v1, v0) < 2e-6, (nv, B)
+            v, _, _ = o(inp["beta"][:3].astype(np.float64), inp["theta"][:3].astype(np.float64), get_skin=True)
+            assert rel_err(v1[:3], v) < TOL
+
+
 def test_fused_keypoint_forward_backward_matches_separate_kernels(smpl_full):
     """k_fold_step_w (forward + backward of the folded keypoint path in one kernel, gradients formed
     for a unit loss scale and scaled by w_kp / num_present in k_pose_bwd) against the separate
