@@ -21,6 +21,19 @@ static __device__ __noinline__ void store_rows4(float *dst, int row_stride, int 
                                          float b0, float b1, float b2, float c0, float c1, float c2, float d0, float d1,
                                          float d2) {
   if (!v_ok) return;
+#if FB_ABLATE == 5
+  // tuning build: same stores and bytes, but a warp's three stores of a row each cover 128 contiguous
+  // bytes (WRONG element order) -- what fully coalesced store requests would buy
+  {
+    const int ln = threadIdx.x & 31;
+    dst -= 2 * ln;
+    if (rows_left > 0) { FB_ST(dst, a0); FB_ST(dst + 32, a1); FB_ST(dst + 64, a2); }
+    if (rows_left > 1) { FB_ST(dst + row_stride, b0); FB_ST(dst + row_stride + 32, b1); FB_ST(dst + row_stride + 64, b2); }
+    if (rows_left > 2) { FB_ST(dst + 2 * row_stride, c0); FB_ST(dst + 2 * row_stride + 32, c1); FB_ST(dst + 2 * row_stride + 64, c2); }
+    if (rows_left > 3) { FB_ST(dst + 3 * row_stride, d0); FB_ST(dst + 3 * row_stride + 32, d1); FB_ST(dst + 3 * row_stride + 64, d2); }
+    return;
+  }
+#endif
   if (rows_left > 0) {
     FB_ST(dst, a0);
     FB_ST(dst + 1, a1);

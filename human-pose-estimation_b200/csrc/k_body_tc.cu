@@ -53,7 +53,8 @@
 #endif
 #ifndef FB_ABLATE
 #define FB_ABLATE 0   // tuning builds: 1 = epilogue only hand-shakes (MMA-side time), 2 = no MMAs (epilogue-side time),
-                      // 3 = no stores, 4 = stores to lines that stay in L2
+                      // 3 = no stores, 4 = stores to lines that stay in L2, 5 = a warp's stores cover 128 contiguous bytes
+                      // (wrong element order, body_common.cuh)
 #endif
 #include "body_common.cuh"
 
