@@ -26,6 +26,15 @@
 #include "tc_ptx.cuh"
 #include "body_common.cuh"
 
+// -DFB_TIMING: per-role wait / busy cycle counts of two pairs (tools/fused_timing.py)
+#ifdef FB_TIMING
+#define TCLK() clock64()
+#define TADD(acc, t) acc += clock64() - (t)
+#else
+#define TCLK() 0ll
+#define TADD(acc, t)
+#endif
+
 template <int NS_, int ST_, int DSTAGES_, int ASTAGES_, int PRE_>
 struct PairCfg {
   static constexpr int NS = NS_, ST = ST_, TBUF = 2, DSTAGES = DSTAGES_, ASTAGES = ASTAGES_, PRE = PRE_, EW = 2;
@@ -195,6 +204,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       constexpr uint32_t idesc_p = umma_idesc_f16(2 * FB_VT, C::NS);
       const uint64_t desc_d0 = umma_desc_sw128(sbase + C::SM_D), desc_x0 = umma_desc_sw128(sbase + C::SM_X);
       int cur_m = -1, x_loads = 0, dstage = 0, dphase = 0, n_tiles = 0;
+      [[maybe_unused]] long long w_pe = 0, w_fd = 0, w_tot = TCLK(), tq;
       for (int t = t0; t < t1; ++t, ++n_tiles) {
         const int m = t / n_vp;
         if (m != cur_m) {
@@ -202,14 +212,18 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           ++x_loads;
           cur_m = m;
         }
+        tq = TCLK();
         mbar_wait(p_empty, (n_tiles & 1) ^ 1);       // both epilogues have read the previous P
+        TADD(w_pe, tq);
         tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < 3; ++cc) {
           const uint32_t d_tmem = tmem_base + cc * C::NS;
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
+            tq = TCLK();
             mbar_wait(full_d + 8 * dstage, dphase);
+            TADD(w_fd, tq);
             tc_fence_after();
             const uint64_t a_desc = umma_desc_add(desc_d0, dstage * FB_D_BYTES);
             const uint64_t b_desc = umma_desc_add(desc_x0, kb * C::X_KB_HALF);
@@ -235,6 +249,11 @@ __global__ void __launch_bounds__(C::THREADS, 1)
         }
         __syncwarp();
       }
+#ifdef FB_TIMING
+      if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 76))
+        printf("cta %d blend MMA warp: total %lld, wait p_empty %lld, full_d %lld (tiles %d)\n", blockIdx.x, clock64() - w_tot,
+               w_pe, w_fd, t1 - t0);
+#endif
     }
   } else if (warp == 3) {
     // =========================== skinning MMA issuer (leader) ===========================
@@ -242,13 +261,18 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       constexpr uint32_t idesc_t = umma_idesc_f16(2 * FB_VT, C::TN);
       const uint64_t desc_w0 = umma_desc_sw128(sbase + C::SM_W), desc_a0 = umma_desc_sw128(sbase + C::SM_A);
       int wbuf = 0, wphase = 0, astage = 0, aphase = 0, tb = 0, tphase = 0;
+      [[maybe_unused]] long long w_te = 0, w_fa = 0, w_tot = TCLK(), tq;
       for (int t = t0; t < t1; ++t) {
         mbar_wait(full_w + 8 * wbuf, wphase);
         const uint64_t w_desc = umma_desc_add(desc_w0, wbuf * FB_W_BYTES);
 #pragma unroll 1
         for (int st = 0; st < C::NT; ++st) {
+          tq = TCLK();
           mbar_wait(t_empty + 8 * tb, tphase ^ 1);
+          TADD(w_te, tq);
+          tq = TCLK();
           mbar_wait(full_a + 8 * astage, aphase);
+          TADD(w_fa, tq);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + C::TCOL + tb * C::TN;
           const uint64_t a_desc = umma_desc_add(desc_a0, astage * C::A_HALF);
@@ -279,6 +303,10 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           wphase ^= 1;
         }
       }
+#ifdef FB_TIMING
+      if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 76))
+        printf("cta %d skin MMA warp: total %lld, wait t_empty %lld, full_a %lld\n", blockIdx.x, clock64() - w_tot, w_te, w_fa);
+#endif
     }
   } else if (warp >= 4) {
     // =========================== epilogue (warps 4..11, both CTAs) ===========================
@@ -292,6 +320,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
     const uint32_t l_p_empty = cluster_map_shared(p_empty, 0), l_t_empty = cluster_map_shared(t_empty, 0);
     int tb = 0, tphase = 0, n_tiles = 0;
+    [[maybe_unused]] long long w_pf = 0, w_tf = 0, w_ld = 0, w_st = 0, w_tot = TCLK(), tq;
     for (int t = t0; t < t1; ++t, ++n_tiles) {
       const int m = t / n_vp, vt = 2 * (t % n_vp) + crank;
       const int v0 = vt * FB_VT + 32 * q;
@@ -306,7 +335,9 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       // one skinning tile; p_in == nullptr: v_posed comes from TMEM (P), else from registers
       auto do_tile = [&](int st, const uint32_t(*p_in)[HS], bool release_p) {
         const uint32_t tcol0 = lane_base + C::TCOL + tb * C::TN + part * HS * 12;
+        tq = TCLK();
         mbar_wait(t_full + 8 * tb, tphase);
+        TADD(w_tf, tq);
         tc_fence_after();
         const int s_loc = st * C::ST + part * HS;   // first sample (within the super-tile) of this warp
         uint32_t r[12 * HS], pc[3][HS];
@@ -320,7 +351,9 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 #pragma unroll
             for (int si = 0; si < HS; ++si) pc[cc][si] = p_in[cc][si];
         }
+        tq = TCLK();
         tc_wait_ld();
+        TADD(w_ld, tq);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -339,15 +372,19 @@ __global__ void __launch_bounds__(C::THREADS, 1)
                              fmaf(__uint_as_float(T[4 * rr + 1]), py,
                                   fmaf(__uint_as_float(T[4 * rr + 2]), pz, __uint_as_float(T[4 * rr + 3]))));
         }
+        tq = TCLK();
         store_rows4(vbase + s_loc * (V * 3), V * 3, b_left - s_loc, v_ok, o[0][0], o[0][1], o[0][2], o[1][0], o[1][1], o[1][2],
                     o[2][0], o[2][1], o[2][2], o[3][0], o[3][1], o[3][2]);
+        TADD(w_st, tq);
         if (++tb == C::TBUF) {
           tb = 0;
           tphase ^= 1;
         }
       };
 
+      tq = TCLK();
       mbar_wait(p_full, n_tiles & 1);
+      TADD(w_pf, tq);
       tc_fence_after();
 #pragma unroll 1
       for (int st = 0; st < C::NT - PRE; ++st) do_tile(st, nullptr, PRE == 0 && st == C::NT - 1);
@@ -363,6 +400,11 @@ __global__ void __launch_bounds__(C::THREADS, 1)
         for (int i = 0; i < PRE; ++i) do_tile(C::NT - PRE + i, pre[i], false);
       }
     }
+#ifdef FB_TIMING
+    if (lane == 0 && (warp == 4 || warp == 9) && (blockIdx.x == 0 || blockIdx.x == 1 || blockIdx.x == 76))
+      printf("cta %d epilogue warp %d: total %lld, wait p_full %lld, t_full %lld, tmem ld %lld, stores %lld\n", blockIdx.x, warp,
+             clock64() - w_tot, w_pf, w_tf, w_ld, w_st);
+#endif
   }
   tc_fence_before();
   __syncthreads();

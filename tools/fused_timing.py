@@ -1,4 +1,4 @@
-"""Run two steps at B = 4096 (for builds of k_body_tc.cu with -DFB_TIMING, which print per-warp
+"""Run two steps at B = 4096 (for builds of k_body_pair.cu / k_body_tc.cu with -DFB_TIMING, which print per-warp
 wait/busy cycle counts of CTAs 0 and 77).  Usage: python tools/fused_timing.py [fused variant]"""
 import os
 import sys
