@@ -640,6 +640,12 @@ int launch_fold_step(smplb_ctx *c, int B, const float *A, const float *cam, cons
   RET_IF(c->K * NJ * 3 > FS_MAXU, SMPLB_EINVAL, "too many keypoints for k_fold_step_w");
   LAUNCH(c, "fold_step_fwd_bwd", cdiv(B, FS_WARPS), 32 * FS_WARPS, 0, k_fold_step_w, B, c->K, c->fold_nup, c->fold_nup, c->ws_U,
          c->d_cc, A, cam, kp_gt, joints, kp_pred, part, cnt, d_cam, dA_part, (__half *)c->ws_du16, c->ws_rowscale);
+  // smplb_step reduces the loss partials on stream3 from here on, next to the GEMM
+  c->red_fork_recorded = false;
+  if (c->ev_red_fork && c->cur == c->stream) {
+    CUDA_TRY(cudaEventRecord(c->ev_red_fork, c->cur));
+    c->red_fork_recorded = true;
+  }
   TRY(launch_gemm_tc(c, "fold_gemm_dx", B, KX, 3 * c->fold_nup, c->ws_du16, c->map_g2, dx_part, KX, ksplit,
                      c->fold_inv_scale));
   return 0;

@@ -294,6 +294,9 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
   };
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_red_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_red_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess)
     return fail(SMPLB_ECUDA);
@@ -438,6 +441,12 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
     cudaStreamSynchronize(c->stream2);
     cudaStreamDestroy(c->stream2);
   }
+  if (c->stream3) {
+    cudaStreamSynchronize(c->stream3);
+    cudaStreamDestroy(c->stream3);
+  }
+  if (c->ev_red_fork) cudaEventDestroy(c->ev_red_fork);
+  if (c->ev_red_join) cudaEventDestroy(c->ev_red_join);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -612,6 +621,7 @@ extern "C" int smplb_profile_read(smplb_ctx *c, char *buf, size_t buflen) {
   RET_IF(!buf || buflen == 0, SMPLB_EINVAL, "null buffer");
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (c->stream2) CUDA_TRY(cudaStreamSynchronize(c->stream2));
+  if (c->stream3) CUDA_TRY(cudaStreamSynchronize(c->stream3));
   if (c->profile_trace && g_trace_ref) {
     std::string s;
     char line[256];
@@ -1127,6 +1137,19 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
                        /*step_d_cam=*/(bwd && !have_mesh) ? odc : nullptr));
   const float *vbuf = c->saved_verts;
   bool comm = c->nccl_comm && c->nranks > 1;
+  // Keypoint step: the loss reduction (and the all-reduce over ranks) only needs what k_fold_step_w
+  // wrote, so it runs on stream3 next to the dx GEMM that was queued behind that kernel; the
+  // main stream picks the result (num_present for k_pose_bwd, the loss) up again below.
+  const bool red_aside = c->red_fork_recorded && c->saved_fold_step && !have_mesh && !c->profile_serial;
+  c->red_fork_recorded = false;
+  if (red_aside) {
+    CUDA_TRY(cudaStreamWaitEvent(c->stream3, c->ev_red_fork, 0));
+    c->cur = c->stream3;
+  }
+  struct CurGuard {   // error returns must not leave the context launching on stream3
+    smplb_ctx *c;
+    ~CurGuard() { c->cur = c->stream; }
+  } cur_guard{c};
   if (!have_mesh && !comm) {
     TRY(launch_reduce_finalize(c, B, w_kp, w_mesh, (long long)kp_count_override, oloss));
   } else {
@@ -1139,10 +1162,15 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
     }
     if (comm) {
       // the path's one exchange: {kp numerator, kp count, mesh sum} summed over the batch shards
-      if (!have_mesh) CUDA_TRY(cudaMemsetAsync(c->ws_scal + 2, 0, 4, c->stream));
+      if (!have_mesh) CUDA_TRY(cudaMemsetAsync(c->ws_scal + 2, 0, 4, c->cur));
       TRY(smplb_comm_allreduce_sum(c, c->ws_scal, 3));
     }
     TRY(launch_finalize_loss(c, w_kp, w_mesh, (long long)kp_count_override, have_mesh ? 1 : 0, oloss));
+  }
+  if (red_aside) {
+    CUDA_TRY(cudaEventRecord(c->ev_red_join, c->stream3));
+    c->cur = c->stream;
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_red_join, 0));
   }
   if (bwd && c->saved_fold_step) {
     // the forward ran k_fold_step_w + the dx GEMM; the loss reduction above supplied num_present
@@ -1240,12 +1268,13 @@ extern "C" int smplb_comm_init(smplb_ctx *c, int nranks, int rank, const void *i
   return 0;
 }
 
+// (on the stream the context currently launches on: the main stream, or stream3 inside smplb_step)
 extern "C" int smplb_comm_allreduce_sum(smplb_ctx *c, float *dev_buf, int count) {
   CHECK_CTX(c);
   RET_IF(!dev_buf || count < 1, SMPLB_EINVAL, "null buffer or count < 1");
   if (c->nranks == 1 && !c->nccl_comm) return 0;
   RET_IF(!c->nccl_comm, SMPLB_ENCCL, "smplb_comm_init has not been called");
-  NCCL_TRY(g_nccl.allreduce(dev_buf, dev_buf, (size_t)count, /*ncclFloat*/ 7, /*ncclSum*/ 0, c->nccl_comm, c->stream));
+  NCCL_TRY(g_nccl.allreduce(dev_buf, dev_buf, (size_t)count, /*ncclFloat*/ 7, /*ncclSum*/ 0, c->nccl_comm, c->cur));
   return 0;
 }
 

@@ -31,6 +31,10 @@ struct smplb_ctx {
   cudaStream_t stream2 = nullptr;   // side stream: the 6890-vertex blend + skinning, overlapped with the keypoint path
   cudaStream_t cur = nullptr;       // stream the LAUNCH macro uses
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // third stream: the loss reduction (+ the all-reduce over ranks) of a keypoint step runs next to the dx GEMM
+  cudaStream_t stream3 = nullptr;
+  cudaEvent_t ev_red_fork = nullptr, ev_red_join = nullptr;
+  bool red_fork_recorded = false;   // ev_red_fork was recorded behind k_fold_step_w in this step
   bool verts_pending = false;       // stream2 work not yet joined into the main stream
   int keep_verts = 0;               // smplb_debug_set("keep_verts", 1): always compute verts (device-resident workspace)
   int use_overlap = 1;              // smplb_debug_set("overlap", 0) keeps everything on the main stream
