@@ -642,9 +642,21 @@ int launch_fold_step(smplb_ctx *c, int B, const float *A, const float *cam, cons
          c->d_cc, A, cam, kp_gt, joints, kp_pred, part, cnt, d_cam, dA_part, (__half *)c->ws_du16, c->ws_rowscale);
   // smplb_step reduces the loss partials on stream3 from here on, next to the GEMM
   c->red_fork_recorded = false;
-  if (c->ev_red_fork && c->cur == c->stream) {
+  if (c->ev_red_fork && c->cur == c->stream && c->use_overlap && !c->profile_serial) {
     CUDA_TRY(cudaEventRecord(c->ev_red_fork, c->cur));
     c->red_fork_recorded = true;
+  }
+  if (c->red_fork_recorded && c->use_prio && c->stream_g) {
+    // the GEMM goes to the low-priority stream (smplb_internal.h: stream_g); smplb_step joins it before k_pose_bwd
+    CUDA_TRY(cudaStreamWaitEvent(c->stream_g, c->ev_red_fork, 0));
+    c->cur = c->stream_g;
+    int rc = launch_gemm_tc(c, "fold_gemm_dx", B, KX, 3 * c->fold_nup, c->ws_du16, c->map_g2, dx_part, KX, ksplit,
+                            c->fold_inv_scale);
+    c->cur = c->stream;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_g_join, c->stream_g));
+    c->gdx_pending = true;
+    return 0;
   }
   TRY(launch_gemm_tc(c, "fold_gemm_dx", B, KX, 3 * c->fold_nup, c->ws_du16, c->map_g2, dx_part, KX, ksplit,
                      c->fold_inv_scale));

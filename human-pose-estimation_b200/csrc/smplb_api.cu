@@ -292,9 +292,14 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
     smplb_destroy(c);
     return code;
   };
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess ||
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);   // (equal when the device has no priorities)
+  if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&c->stream_g, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_g_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_g_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_red_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_red_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -445,6 +450,12 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
     cudaStreamSynchronize(c->stream3);
     cudaStreamDestroy(c->stream3);
   }
+  if (c->stream_g) {
+    cudaStreamSynchronize(c->stream_g);
+    cudaStreamDestroy(c->stream_g);
+  }
+  if (c->ev_g_fork) cudaEventDestroy(c->ev_g_fork);
+  if (c->ev_g_join) cudaEventDestroy(c->ev_g_join);
   if (c->ev_red_fork) cudaEventDestroy(c->ev_red_fork);
   if (c->ev_red_join) cudaEventDestroy(c->ev_red_join);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -584,6 +595,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->use_fused = value;
     return 0;
   }
+  if (!strcmp(key, "prio")) {
+    c->use_prio = value;
+    return 0;
+  }
   if (!strcmp(key, "body_pairs")) {
     c->body_pairs = value;
     return 0;
@@ -622,6 +637,7 @@ extern "C" int smplb_profile_read(smplb_ctx *c, char *buf, size_t buflen) {
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (c->stream2) CUDA_TRY(cudaStreamSynchronize(c->stream2));
   if (c->stream3) CUDA_TRY(cudaStreamSynchronize(c->stream3));
+  if (c->stream_g) CUDA_TRY(cudaStreamSynchronize(c->stream_g));
   if (c->profile_trace && g_trace_ref) {
     std::string s;
     char line[256];
@@ -705,10 +721,21 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   bool fused = full && tc && stc && c->body_tc_ok && c->use_fused && !chunked && !want_vposed;
   // the fold GEMM needs TMEM and ~160 KB of shared memory, which the persistent blend / skinning
   // CTAs would deny it: issue it before forking so only the light per-body kernels overlap them
-  if (fold) TRY(launch_fold_gemm_u(c, B, c->ws_x16));
   bool overlap = full && (fold || compact) && c->use_overlap && !c->profile_serial;
+  const bool prio = fold && c->use_prio && c->use_overlap && !c->profile_serial;   // (see stream_g)
+  if (fold && !prio) TRY(launch_fold_gemm_u(c, B, c->ws_x16));
+  if (overlap || prio) CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+  if (prio) {
+    // U = x G^T on the low-priority stream; the main stream resumes behind it
+    CUDA_TRY(cudaStreamWaitEvent(c->stream_g, c->ev_fork, 0));
+    c->cur = c->stream_g;
+    int rc = launch_fold_gemm_u(c, B, c->ws_x16);
+    c->cur = c->stream;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_g_join, c->stream_g));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_g_join, 0));
+  }
   if (overlap) {
-    CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
     CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
     c->cur = c->stream2;
   }
@@ -1171,6 +1198,10 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
     CUDA_TRY(cudaEventRecord(c->ev_red_join, c->stream3));
     c->cur = c->stream;
     CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_red_join, 0));
+  }
+  if (c->gdx_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_g_join, 0));
+    c->gdx_pending = false;
   }
   if (bwd && c->saved_fold_step) {
     // the forward ran k_fold_step_w + the dx GEMM; the loss reduction above supplied num_present

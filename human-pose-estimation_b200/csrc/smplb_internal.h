@@ -35,6 +35,16 @@ struct smplb_ctx {
   cudaStream_t stream3 = nullptr;
   cudaEvent_t ev_red_fork = nullptr, ev_red_join = nullptr;
   bool red_fork_recorded = false;   // ev_red_fork was recorded behind k_fold_step_w in this step
+  // The GPU dispatches the grids of equal-priority streams in launch order, and a grid that cannot be
+  // placed blocks every later one, whatever its stream: the two tcgen05 GEMMs of the keypoint path
+  // wait for SMs without a resident vertex-kernel CTA (tensor memory, shared memory), and while one
+  // of them waits nothing launched after it starts -- not even the small per-body kernels of other
+  // contexts that would fit next to the vertex kernel.  So the GEMMs (and the vertex kernel) run on
+  // low-priority streams and everything else on high-priority ones, whose grids are dispatched first.
+  cudaStream_t stream_g = nullptr;  // low priority: fold_gemm_u, fold_gemm_dx
+  cudaEvent_t ev_g_fork = nullptr, ev_g_join = nullptr;
+  bool gdx_pending = false;         // fold_gemm_dx is on stream_g and not yet joined into the main stream
+  int use_prio = 1;                 // smplb_debug_set("prio", 0): the GEMMs stay on the main stream
   bool verts_pending = false;       // stream2 work not yet joined into the main stream
   int keep_verts = 0;               // smplb_debug_set("keep_verts", 1): always compute verts (device-resident workspace)
   int use_overlap = 1;              // smplb_debug_set("overlap", 0) keeps everything on the main stream

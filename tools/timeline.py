@@ -1,6 +1,6 @@
 """Timeline of the kernels of N contexts running steps back to back (events around every launch,
 streams NOT serialised): where the step time goes when the contexts overlap.
-Usage: python tools/timeline.py [B] [contexts] [steps]"""
+Usage: python tools/timeline.py [B] [contexts] [steps] [fused variant]"""
 import os
 import sys
 
@@ -12,8 +12,11 @@ from hpe_b200.tf_smpl.batch_smpl import SMPL  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 NE = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 STEPS = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+FUSED = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 model = synthetic.make_model(seed=0)
 engines = [SMPL(model, max_batch=B) for _ in range(NE)]
+for e in engines:
+    e.ctx.debug_set("fused", FUSED)
 inp = synthetic.make_inputs(B, seed=1000)
 dev = [{k: e.ctx.to_device(v) for k, v in inp.items()} for e in engines]
 outs = [{} for _ in engines]
