@@ -722,7 +722,10 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   // the fold GEMM needs TMEM and ~160 KB of shared memory, which the persistent blend / skinning
   // CTAs would deny it: issue it before forking so only the light per-body kernels overlap them
   bool overlap = full && (fold || compact) && c->use_overlap && !c->profile_serial;
-  const bool prio = fold && c->use_prio && c->use_overlap && !c->profile_serial;   // (see stream_g)
+  // (see stream_g; not with a communicator attached: there the all-reduce of the loss sums was observed to
+  // run concurrently with the reduction kernel queued before it on the same stream -- stale counts in
+  // 70 % of the steps, tools/determinism.py under torchrun -- which is not understood yet)
+  const bool prio = fold && c->use_prio && c->use_overlap && !c->profile_serial && !(c->nccl_comm && c->nranks > 1);
   if (fold && !prio) TRY(launch_fold_gemm_u(c, B, c->ws_x16));
   if (overlap || prio) CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
   if (prio) {
