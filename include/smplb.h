@@ -25,7 +25,10 @@
  *     (smplb_host_alloc) and outputs are valid after smplb_sync -- lets a caller keep two
  *     contexts in flight so copies of one step overlap the kernels of the other.
  *   - a pointer documented "may be NULL" is an optional output/input.
- *   - a context is bound to one device, owns one stream and is not thread-safe.
+ *   - a context is bound to one device and is not thread-safe.  Callers order against ONE stream,
+ *     the context's main stream; internally a step also uses side streams (the 6890-vertex kernel,
+ *     the tcgen05 GEMMs and the loss reduction overlap the per-body kernels), all of which are
+ *     joined back into the main stream before the call returns.
  */
 #ifndef SMPLB_H_
 #define SMPLB_H_
