@@ -595,3 +595,40 @@ def test_mocap_preprocessing_batched(smpl_full, full_model):
     o = onp.SMPL(full_model, dtype=np.float64)
     _, j64, R64 = o(inp["beta"][:4].astype(np.float64), inp["theta"][:4].astype(np.float64), get_skin=True)
     assert rel_err(joints[:4], j64) < TOL and rel_err(rots[:4], R64) < TOL
+
+
+def test_steps_repeat_bit_exactly_with_contexts_in_flight(full_model):
+    """A step uses four streams per context (per-body kernels, the vertex kernel, the tcgen05 GEMMs
+    on a low-priority stream, the loss reduction) and several contexts share the GPU: with three
+    contexts taking steps back to back over rotating inputs, every step's loss and gradients must
+    equal, bit for bit, the first result for the same (context, inputs) -- a missing dependency
+    between the streams shows up as a difference (tools/determinism.py is the long version, also
+    for torchrun)."""
+    B, NE, NSET, STEPS = 1024, 3, 3, 150
+    engines = [SMPL(full_model, max_batch=B) for _ in range(NE)]
+    host_sets = [synthetic.make_inputs(B, seed=4000 + i) for i in range(NSET)]
+    dev_sets = [[{k: e.ctx.to_device(v) for k, v in s.items()} for s in host_sets] for e in engines]
+    depth = 2 * NE
+    outs = [{} for _ in range(depth)]
+    ref, pending, bad = {}, [], []
+
+    def check(item):
+        key, o = item
+        engines[key[0]].ctx.sync()
+        got = tuple(o[n].numpy().tobytes() for n in ("loss_parts", "d_theta", "d_beta", "d_cam"))
+        if ref.setdefault(key, got) != got:
+            bad.append(key)
+
+    for i in range(STEPS):
+        e, s = i % NE, (i // NE) % NSET
+        if len(pending) >= depth:
+            check(pending.pop(0))
+        d = dev_sets[e][s]
+        engines[e].step(d["beta"], d["theta"], d["cam"], d["kp_gt"], w_kp=60.0, out=outs[i % depth])
+        pending.append(((e, s), outs[i % depth]))
+    while pending:
+        check(pending.pop(0))
+    assert not bad, bad[:5]
+    # and the three contexts agree with each other
+    for s in range(NSET):
+        assert ref[(0, s)] == ref[(1, s)] == ref[(2, s)]
