@@ -245,11 +245,21 @@ def main():
         k, v = kv.split("=")
         for e in engines:
             e.ctx.debug_set(k, int(v))
+    comm_backend = os.environ.get("SMPLB_COMM", "mailbox") if world > 1 else "none"
     if world > 1:
+        # the batch is sharded over the ranks; smplb_step exchanges the visibility count and the loss
+        # numerators inside its own kernels through mailboxes in peer memory (CUDA IPC handles passed
+        # around with torch.distributed), or with NCCL when SMPLB_COMM=nccl
         for e in engines:
-            uid = [runtime.Context.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(uid, src=0)
-            e.ctx.comm_init(world, rank, uid[0])
+            if comm_backend == "nccl":
+                uid = [runtime.Context.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0)
+                e.ctx.comm_init(world, rank, uid[0])
+            else:
+                hs = [None] * world
+                dist.all_gather_object(hs, e.ctx.p2p_export())
+                e.ctx.p2p_attach(world, rank, hs)
+        dist.barrier()
 
     # inputs: 4 rotating sets so no step re-reads what the previous one left in L2
     NSET = 4

@@ -46,8 +46,7 @@ SIGNATURES = {
     "smplb_launch_count": [_P, C.POINTER(_L)],
     "smplb_profile_enable": [_P, _I],
     "smplb_profile_read": [_P, C.c_char_p, _SZ],
-    "smplb_debug_set": [_P, C.c_char_p, _I],
-    "smplb_smpl_forward": [_P, _I, _P, _P, _P, _P, _P, _P, _I],
+    "smplb_smpl_forward": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I],
     "smplb_smpl_backward": [_P, _I, _P, _P, _P, _P, _P, _I],
     "smplb_last_verts": [_P, C.POINTER(_P)],
     "smplb_rodrigues": [_P, _I, _P, _P, _I],
@@ -66,12 +65,22 @@ SIGNATURES = {
     "smplb_kcs": [_P, _I, _I, _P, _P, _P, _I],
     "smplb_kcs_backward": [_P, _I, _I, _P, _P, _P, _P, _I],
     "smplb_interpolate": [_P, _I, _I, _P, _P, _P, _P, _I],
-    "smplb_step": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I],
+    "smplb_step": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I],
+    "smplb_comm_p2p_export": [_P, _P],
+    "smplb_comm_p2p_attach": [_P, _I, _I, _P],
+    "smplb_comm_p2p_attach_local": [_P, _I, _I, C.POINTER(_P)],
+    "smplb_comm_status": [_P, C.POINTER(_I)],
     "smplb_comm_unique_id": [_P],
     "smplb_comm_init": [_P, _I, _I, _P],
     "smplb_comm_allreduce_sum": [_P, _P, _I],
     "smplb_comm_destroy": [_P],
 }
+
+# private hooks (csrc/smplb_debug.h), not part of include/smplb.h
+PRIVATE_SIGNATURES = {
+    "smplb_debug_set": [_P, C.c_char_p, _I],
+}
+STEP_KEEP_VERTS = 1
 
 _lib = None
 
@@ -85,7 +94,7 @@ def lib():
             raise ImportError("libsmplb.so not found at %s: build it with __graft_entry__.build(); "
                               "there is no CPU fallback" % LIB_PATH)
         l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
-        for name, args in SIGNATURES.items():
+        for name, args in list(SIGNATURES.items()) + list(PRIVATE_SIGNATURES.items()):
             f = getattr(l, name)
             f.argtypes = args
             f.restype = C.c_int

@@ -646,7 +646,7 @@ int launch_fold_step(smplb_ctx *c, int B, const float *A, const float *cam, cons
     CUDA_TRY(cudaEventRecord(c->ev_red_fork, c->cur));
     c->red_fork_recorded = true;
   }
-  if (c->red_fork_recorded && c->use_prio && c->stream_g && !(c->nccl_comm && c->nranks > 1)) {
+  if (c->red_fork_recorded && c->use_prio && c->stream_g) {
     // the GEMM goes to the low-priority stream (smplb_internal.h: stream_g); smplb_step joins it before k_pose_bwd
     CUDA_TRY(cudaStreamWaitEvent(c->stream_g, c->ev_red_fork, 0));
     c->cur = c->stream_g;

@@ -303,6 +303,8 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
       cudaEventCreateWithFlags(&c->ev_red_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_red_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_step0, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_cnt, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess)
     return fail(SMPLB_ECUDA);
   c->cur = c->stream;
@@ -407,8 +409,10 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(SMPLB_ECUDA);
   }
   if (cudaMalloc((void **)&c->ws_scal, 64 * 4) != cudaSuccess ||
-      cudaMalloc((void **)&c->ws_cnt64, 8 * sizeof(long long)) != cudaSuccess)
+      cudaMalloc((void **)&c->ws_cnt64, 8 * sizeof(long long)) != cudaSuccess ||
+      cudaMalloc((void **)&c->x_status, sizeof(int)) != cudaSuccess)
     return fail(SMPLB_ECUDA);
+  cudaMemset(c->x_status, 0, sizeof(int));
   cudaMemset(c->ws_scal, 0, 64 * 4);
   cudaMemset(c->ws_cnt64, 0, 8 * sizeof(long long));
   if ((rc = blend_tc_init(c))) return fail(rc);
@@ -430,7 +434,8 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
   void *ptrs[] = {c->d_vt,       c->d_shapedirs, c->d_posedirs, c->d_W,        c->d_JR,       c->d_Dext,   c->d_J0,
                   c->d_Jdirs,    c->d_kcsr_off,  c->d_kcsr_idx, c->d_kcsr_val, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val,
                   c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_W16,      c->d_G,        c->d_cc,       c->d_G16,      c->d_Gt16,     c->d_Dt16_act, c->d_W16_act,  c->d_kcsr_slot, c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
-                  c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part, c->ws_grid,  c->ws_vdist};
+                  c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part, c->ws_grid,  c->ws_vdist,
+                  c->x_mbox,     c->x_status};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 16; ++i) {
@@ -459,6 +464,8 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
   if (c->ev_red_fork) cudaEventDestroy(c->ev_red_fork);
   if (c->ev_red_join) cudaEventDestroy(c->ev_red_join);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_step0) cudaEventDestroy(c->ev_step0);
+  if (c->ev_cnt) cudaEventDestroy(c->ev_cnt);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -563,8 +570,12 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->use_tc = value;
     return 0;
   }
-  if (!strcmp(key, "keep_verts")) {
-    c->keep_verts = value;
+  if (!strcmp(key, "comm_backend")) {
+    c->comm_backend = value;
+    return 0;
+  }
+  if (!strcmp(key, "comm_timeout_ms")) {
+    c->x_timeout_ns = (unsigned long long)(value > 0 ? value : 1) * 1000000ull;
     return 0;
   }
   if (!strcmp(key, "mesh_grid")) {
@@ -679,6 +690,25 @@ extern "C" int smplb_profile_read(smplb_ctx *c, char *buf, size_t buflen) {
 // --------------------------------------------------------------------------------- SMPL fwd/bwd
 // The 6890-vertex blend + skinning run on stream2 while the keypoint path continues on the
 // main stream; whoever needs verts / v_posed on the main stream joins first.
+// Error returns in the middle of a step leave work in flight on the side streams that still
+// reads / writes staged buffers: drain them before anything is freed and forget the pending joins.
+static void abort_side_streams(smplb_ctx *c) {
+  for (cudaStream_t s : {c->stream2, c->stream3, c->stream_g, c->stream})
+    if (s) cudaStreamSynchronize(s);
+  c->verts_pending = false;
+  c->gdx_pending = false;
+  c->red_fork_recorded = false;
+  c->cur = c->stream;
+}
+struct StepGuard {   // declared after the Stager, so it runs before the Stager frees its buffers
+  smplb_ctx *c;
+  bool ok = false;
+  ~StepGuard() {
+    if (!ok) abort_side_streams(c);
+    c->cur = c->stream;   // error returns must not leave the context launching on a side stream
+  }
+};
+
 static int join_verts(smplb_ctx *c) {
   if (c->verts_pending) {
     CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
@@ -690,6 +720,7 @@ static int join_verts(smplb_ctx *c) {
 static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float *theta, float *verts, float *joints,
                             float *Rs, float *Jtr, const float *cam, const float *kp_gt, float *kp_pred,
                             bool need_verts, bool want_vposed = false, float *step_d_cam = nullptr) {
+  NvtxRange nvtx("smpl_main");   // batch_smpl.py:105
   TRY(ensure_ws(c, B));
   CUDA_TRY(cudaMemcpyAsync(c->ws_beta, beta, (size_t)B * c->NB * 4, cudaMemcpyDeviceToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->ws_theta, theta, (size_t)B * 72 * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -703,7 +734,7 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   // Keypoint path on the active vertices only (rows of joint_regressor with a non-zero): the
   // same two tensor-core kernels on ~9 % of the vertices give joints without reading verts back.
   bool compact = !fold && tc && stc && c->compact_ok && c->use_compact;
-  bool full = need_verts || c->keep_verts || !(compact || fold);
+  bool full = need_verts || !(compact || fold);
   float *vout = verts;
   if (full && !vout) {
     TRY(ensure_buf(c, &c->ws_verts, (size_t)c->ws_batch * c->V3, false));
@@ -722,10 +753,8 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
   // the fold GEMM needs TMEM and ~160 KB of shared memory, which the persistent blend / skinning
   // CTAs would deny it: issue it before forking so only the light per-body kernels overlap them
   bool overlap = full && (fold || compact) && c->use_overlap && !c->profile_serial;
-  // (see stream_g; not with a communicator attached: there the all-reduce of the loss sums was observed to
-  // run concurrently with the reduction kernel queued before it on the same stream -- stale counts in
-  // 70 % of the steps, tools/determinism.py under torchrun -- which is not understood yet)
-  const bool prio = fold && c->use_prio && c->use_overlap && !c->profile_serial && !(c->nccl_comm && c->nranks > 1);
+  // (see stream_g)
+  const bool prio = fold && c->use_prio && c->use_overlap && !c->profile_serial;
   if (fold && !prio) TRY(launch_fold_gemm_u(c, B, c->ws_x16));
   if (overlap || prio) CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
   if (prio) {
@@ -838,18 +867,23 @@ static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const fl
 }
 
 extern "C" int smplb_smpl_forward(smplb_ctx *c, int B, const float *beta, const float *theta, float *verts,
-                                  float *joints, float *Rs, float *J_transformed, int mem) {
+                                  float *joints, float *Rs, float *J_transformed, int flags, int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
+  RET_IF(flags & ~SMPLB_STEP_KEEP_VERTS, SMPLB_EINVAL, "unknown bits in flags");
   RET_IF(B < 1 || !beta || !theta || !joints, SMPLB_EINVAL, "B >= 1 and non-null beta, theta, joints required");
   Stager st(c, mem);
   const float *dbeta = st.in(beta, (size_t)B * c->NB), *dtheta = st.in(theta, (size_t)B * 72);
   float *dverts = st.out(verts, (size_t)B * c->V3), *djoints = st.out(joints, (size_t)B * c->K * 3);
   float *dRs = st.out(Rs, (size_t)B * NJ * 9), *dJtr = st.out(J_transformed, (size_t)B * NJ * 3);
   RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
-  TRY(smpl_forward_dev(c, B, dbeta, dtheta, dverts, djoints, dRs, dJtr, nullptr, nullptr, nullptr, verts != nullptr));
+  StepGuard guard{c};
+  TRY(smpl_forward_dev(c, B, dbeta, dtheta, dverts, djoints, dRs, dJtr, nullptr, nullptr, nullptr,
+                       verts != nullptr || (flags & SMPLB_STEP_KEEP_VERTS)));
   TRY(join_verts(c));
-  return st.finish();
+  int rc = st.finish();
+  guard.ok = rc == 0;
+  return rc;
 }
 
 extern "C" int smplb_smpl_backward(smplb_ctx *c, int B, const float *d_verts, const float *d_joints,
@@ -1134,14 +1168,18 @@ extern "C" int smplb_interpolate(smplb_ctx *c, int N, int row, const float *fake
 }
 
 // ---------------------------------------------------------------------------------- fused step
+static int allreduce_on(smplb_ctx *c, void *dev_buf, size_t count, int nccl_dtype, cudaStream_t stream);
+
 extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *theta, const float *cam,
                           const float *kp_gt, const float *points_xy, const int32_t *offsets, int P, float w_kp,
                           float w_mesh, float img_size, int64_t kp_count_override, float *verts, float *joints, float *Rs,
-                          float *kp_pred, float *loss_parts, float *d_beta, float *d_theta, float *d_cam, int mem) {
+                          float *kp_pred, float *loss_parts, float *d_beta, float *d_theta, float *d_cam, int flags,
+                          int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
   RET_IF(B < 1 || !beta || !theta || !cam || !kp_gt || !loss_parts, SMPLB_EINVAL,
          "B >= 1 and non-null beta, theta, cam, kp_gt, loss_parts required");
+  RET_IF(flags & ~SMPLB_STEP_KEEP_VERTS, SMPLB_EINVAL, "unknown bits in flags");
   bool have_mesh = offsets != nullptr;
   bool bwd = d_beta || d_theta || d_cam;
   RET_IF(bwd && !(d_beta && d_theta && d_cam), SMPLB_EINVAL, "d_beta, d_theta, d_cam must be all set or all NULL");
@@ -1149,7 +1187,9 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
   TRY(ensure_ws(c, B));
   if (have_mesh) TRY(ensure_mesh_ws(c, B, c->V));
   int K = c->K;
+  NvtxRange nvtx_step("smplb_step");
   Stager st(c, mem);
+  StepGuard guard{c};
   const float *dbeta = st.in(beta, (size_t)B * c->NB), *dtheta = st.in(theta, (size_t)B * 72);
   const float *dcam = st.in(cam, (size_t)B * 3), *dkpgt = st.in(kp_gt, (size_t)B * K * 3);
   const float *dpts = have_mesh ? st.in(points_xy, (size_t)P * 2) : nullptr;
@@ -1161,68 +1201,109 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
   RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
   if (have_mesh && !dpts) dpts = c->ws_scal;
 
+  // ---- batch shards: the visibility count is exchanged first (it depends on kp_gt alone, SURVEY
+  //      section 8e), on stream3, so the backward never waits for a peer.  ws_cnt64[0] = the
+  //      denominator of this step's keypoint gradients; ws_cnt64[1] = the local count.
+  const bool p2p = c->x_attached && !(c->comm_backend == 1 && c->nccl_comm);
+  const bool nccl = !p2p && c->nccl_comm != nullptr;
+  const bool comm = p2p || nccl;
+  long long *den = c->ws_cnt64;
+  bool cnt_aside = false;
+  if (comm) {
+    c->x_epoch++;
+    cnt_aside = c->use_overlap && !c->profile_serial;
+    if (cnt_aside) {
+      CUDA_TRY(cudaEventRecord(c->ev_step0, c->stream));
+      CUDA_TRY(cudaStreamWaitEvent(c->stream3, c->ev_step0, 0));
+      c->cur = c->stream3;
+    }
+    TRY(launch_count_exchange(c, B, dkpgt, (long long)kp_count_override, p2p ? 1 : 2, den));
+    if (nccl && kp_count_override <= 0) TRY(allreduce_on(c, den, 1, /*ncclInt64*/ 4, c->cur));
+    if (cnt_aside) {
+      CUDA_TRY(cudaEventRecord(c->ev_cnt, c->stream3));
+      c->cur = c->stream;
+    }
+  }
+
+  const bool keep = (flags & SMPLB_STEP_KEEP_VERTS) != 0;
   float *jbuf = ojoints ? ojoints : c->ws_joints;
   TRY(smpl_forward_dev(c, B, dbeta, dtheta, overts, jbuf, oRs, nullptr, dcam, dkpgt, okp ? okp : c->ws_kp,
-                       overts != nullptr || have_mesh, /*want_vposed=*/have_mesh && bwd,
+                       overts != nullptr || have_mesh || keep, /*want_vposed=*/have_mesh && bwd,
                        /*step_d_cam=*/(bwd && !have_mesh) ? odc : nullptr));
   const float *vbuf = c->saved_verts;
-  bool comm = c->nccl_comm && c->nranks > 1;
-  // Keypoint step: the loss reduction (and the all-reduce over ranks) only needs what k_fold_step_w
-  // wrote, so it runs on stream3 next to the dx GEMM that was queued behind that kernel; the
-  // main stream picks the result (num_present for k_pose_bwd, the loss) up again below.
+  // Keypoint step: the loss reduction (and the exchange of the numerators) only needs what
+  // k_fold_step_w wrote, so it runs on stream3 next to the dx GEMM that was queued behind that
+  // kernel; the main stream picks the result up again below.
   const bool red_aside = c->red_fork_recorded && c->saved_fold_step && !have_mesh && !c->profile_serial;
   c->red_fork_recorded = false;
   if (red_aside) {
     CUDA_TRY(cudaStreamWaitEvent(c->stream3, c->ev_red_fork, 0));
     c->cur = c->stream3;
   }
-  struct CurGuard {   // error returns must not leave the context launching on stream3
-    smplb_ctx *c;
-    ~CurGuard() { c->cur = c->stream; }
-  } cur_guard{c};
   if (!have_mesh && !comm) {
     TRY(launch_reduce_finalize(c, B, w_kp, w_mesh, (long long)kp_count_override, oloss));
-  } else {
+  } else if (!comm) {
     TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, c->ws_scal + 0, c->ws_cnt64, c->ws_scal + 1));
+    TRY(join_verts(c));
+    TRY(launch_proj(c, B, c->V, vbuf, dcam, 1, img_size, img_size, c->ws_silpred));
+    TRY(launch_mesh_loss(c, B, c->V, dpts, doff, P, c->ws_silpred, c->ws_scal + 2, bwd ? c->ws_dsil : nullptr,
+                         c->ws_silcnt, c->ws_mesh_part, nullptr, nullptr));
+    TRY(launch_finalize_loss(c, w_kp, w_mesh, (long long)kp_count_override, 1, oloss));
+  } else {
+    // the path's one exchange: {kp numerator, mesh sum} summed over the batch shards, everything on
+    // c->cur (stream3 for the keypoint step) -- reduce, exchange and finalize share ONE stream
     if (have_mesh) {
+      TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, c->ws_scal + 0, c->ws_cnt64 + 1, c->ws_scal + 1));
       TRY(join_verts(c));
       TRY(launch_proj(c, B, c->V, vbuf, dcam, 1, img_size, img_size, c->ws_silpred));
       TRY(launch_mesh_loss(c, B, c->V, dpts, doff, P, c->ws_silpred, c->ws_scal + 2, bwd ? c->ws_dsil : nullptr,
                            c->ws_silcnt, c->ws_mesh_part, nullptr, nullptr));
     }
-    if (comm) {
-      // the path's one exchange: {kp numerator, kp count, mesh sum} summed over the batch shards
-      if (!have_mesh) CUDA_TRY(cudaMemsetAsync(c->ws_scal + 2, 0, 4, c->cur));
-      TRY(smplb_comm_allreduce_sum(c, c->ws_scal, 3));
+    if (cnt_aside && c->cur != c->stream3) {
+      CUDA_TRY(cudaStreamWaitEvent(c->cur, c->ev_cnt, 0));   // den (written on stream3) before its first reader here
+      cnt_aside = false;
     }
-    TRY(launch_finalize_loss(c, w_kp, w_mesh, (long long)kp_count_override, have_mesh ? 1 : 0, oloss));
+    if (p2p) {
+      TRY(launch_reduce_exchange_finalize(c, B, have_mesh ? nullptr : c->ws_part, w_kp, w_mesh, have_mesh ? 1 : 0, den,
+                                          oloss));
+    } else {
+      if (!have_mesh) {
+        TRY(launch_reduce_kp(c, B, c->ws_part, c->ws_cnt, c->ws_scal + 0, c->ws_cnt64 + 1, c->ws_scal + 1));
+        CUDA_TRY(cudaMemsetAsync(c->ws_scal + 2, 0, 4, c->cur));
+      }
+      TRY(allreduce_on(c, c->ws_scal, 3, /*ncclFloat*/ 7, c->cur));
+      TRY(launch_finalize_den(c, w_kp, w_mesh, have_mesh ? 1 : 0, den, oloss));
+    }
   }
   if (red_aside) {
     CUDA_TRY(cudaEventRecord(c->ev_red_join, c->stream3));
     c->cur = c->stream;
-    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_red_join, 0));
+    // without shards the denominator comes out of the reduction: the backward waits for it here;
+    // with shards it was exchanged at the start of the step and only the loss is joined, at the end
+    if (!comm) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_red_join, 0));
   }
+  if (comm && cnt_aside) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_cnt, 0));
   if (c->gdx_pending) {
     CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_g_join, 0));
     c->gdx_pending = false;
   }
   if (bwd && c->saved_fold_step) {
-    // the forward ran k_fold_step_w + the dx GEMM; the loss reduction above supplied num_present
+    // the forward ran k_fold_step_w + the dx GEMM; `den` holds num_present
     RET_IF(c->saved_B != B, SMPLB_ESTATE, "internal: forward state lost");
     int rows = cdiv(B, 128) * 128;
     TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, 1, c->ws_dx, 2, rows, c->ws_rowscale, nullptr,
-                        odb, odt, c->ws_cnt64, w_kp, odc));
+                        odb, odt, den, w_kp, odc));
   } else if (bwd) {
     if (!have_mesh && c->saved_fold && c->fold_warp_kernels) {
       // keypoint-only backward: d kp loss -> d joints, d cam, du, dA in one kernel, then the GEMM
       RET_IF(c->saved_B != B, SMPLB_ESTATE, "internal: forward state lost");
       int rows = cdiv(B, 128) * 128;
-      TRY(launch_fold_bwd(c, B, c->ws_A, nullptr, c->ws_dkp, jbuf, dcam, w_kp, c->ws_cnt64, odc, c->ws_dA, c->ws_dx, 2));
+      TRY(launch_fold_bwd(c, B, c->ws_A, nullptr, c->ws_dkp, jbuf, dcam, w_kp, den, odc, c->ws_dA, c->ws_dx, 2));
       TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, 1, c->ws_dx, 2, rows, c->ws_rowscale,
                           nullptr, odb, odt));
     } else {
-      // d kp loss -> d joints, d cam; scale w_kp / num_present (global count if overridden)
-      TRY(launch_proj_bwd(c, B, K, jbuf, dcam, c->ws_dkp, 0, 0.f, 0.f, w_kp, c->ws_cnt64, 0, c->ws_djoints, odc));
+      // d kp loss -> d joints, d cam; scale w_kp / num_present (global count if overridden / exchanged)
+      TRY(launch_proj_bwd(c, B, K, jbuf, dcam, c->ws_dkp, 0, 0.f, 0.f, w_kp, den, 0, c->ws_djoints, odc));
       const float *dverts = nullptr;
       if (have_mesh) {
         TRY(ensure_buf(c, &c->ws_dverts, (size_t)c->ws_batch * c->V3, false));
@@ -1234,7 +1315,10 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
     }
   }
   TRY(join_verts(c));
-  return st.finish();
+  if (comm && red_aside) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_red_join, 0));   // the loss
+  int rc = st.finish();
+  guard.ok = rc == 0;
+  return rc;
 }
 
 // ------------------------------------------------------------------------------ NCCL (dlopen)
@@ -1302,18 +1386,138 @@ extern "C" int smplb_comm_init(smplb_ctx *c, int nranks, int rank, const void *i
   return 0;
 }
 
-// (on the stream the context currently launches on: the main stream, or stream3 inside smplb_step)
+// In place on `stream`; does NOT go through CHECK_CTX (which resets c->cur to the main stream):
+// smplb_step calls this while it launches on stream3.
+static int allreduce_on(smplb_ctx *c, void *dev_buf, size_t count, int nccl_dtype, cudaStream_t stream) {
+  RET_IF(!c->nccl_comm, SMPLB_ENCCL, "smplb_comm_init has not been called");
+  NCCL_TRY(g_nccl.allreduce(dev_buf, dev_buf, count, nccl_dtype, /*ncclSum*/ 0, c->nccl_comm, stream));
+  return 0;
+}
+
+// public: on the context's main stream
 extern "C" int smplb_comm_allreduce_sum(smplb_ctx *c, float *dev_buf, int count) {
   CHECK_CTX(c);
   RET_IF(!dev_buf || count < 1, SMPLB_EINVAL, "null buffer or count < 1");
   if (c->nranks == 1 && !c->nccl_comm) return 0;
-  RET_IF(!c->nccl_comm, SMPLB_ENCCL, "smplb_comm_init has not been called");
-  NCCL_TRY(g_nccl.allreduce(dev_buf, dev_buf, (size_t)count, /*ncclFloat*/ 7, /*ncclSum*/ 0, c->nccl_comm, c->cur));
+  return allreduce_on(c, dev_buf, (size_t)count, /*ncclFloat*/ 7, c->stream);
+}
+
+// ---- mailbox exchange (k_exchange.cu): the peers' mailboxes mapped into this process -----------
+static int x_ensure_mbox(smplb_ctx *c) {
+  if (c->x_mbox) return 0;
+  CUDA_TRY(cudaMalloc((void **)&c->x_mbox, X_MBOX_ENTRIES * sizeof(XEntry)));
+  CUDA_TRY(cudaMemset(c->x_mbox, 0, X_MBOX_ENTRIES * sizeof(XEntry)));
+  return 0;
+}
+
+static void x_detach(smplb_ctx *c) {
+  for (int r = 0; r < X_MAXR; ++r) {
+    if (c->x_peers[r] && c->x_ipc[r]) cudaIpcCloseMemHandle(c->x_peers[r]);
+    c->x_peers[r] = nullptr;
+    c->x_ipc[r] = false;
+  }
+  c->x_attached = false;
+}
+
+extern "C" int smplb_comm_p2p_export(smplb_ctx *c, void *handle64) {
+  CHECK_CTX(c);
+  RET_IF(!handle64, SMPLB_EINVAL, "null handle buffer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  TRY(x_ensure_mbox(c));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, c->x_mbox));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+extern "C" int smplb_comm_p2p_attach(smplb_ctx *c, int nranks, int rank, const void *handles) {
+  CHECK_CTX(c);
+  RET_IF(nranks < 1 || nranks > X_MAXR || rank < 0 || rank >= nranks || !handles, SMPLB_EINVAL,
+         "1 <= nranks <= %d, 0 <= rank < nranks and non-null handles required", X_MAXR);
+  RET_IF(c->nccl_comm && (c->nranks != nranks || c->rank != rank), SMPLB_EINVAL,
+         "nranks / rank differ from the attached NCCL communicator's");
+  TRY(x_ensure_mbox(c));
+  x_detach(c);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) {
+      c->x_peers[r] = c->x_mbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (size_t)r * 64, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      x_detach(c);
+      smplb_set_error("cudaIpcOpenMemHandle(rank %d) -> %s (no peer access between the GPUs?)", r, cudaGetErrorString(e));
+      return SMPLB_ECUDA;
+    }
+    c->x_peers[r] = (XEntry *)p;
+    c->x_ipc[r] = true;
+  }
+  c->nranks = nranks;
+  c->rank = rank;
+  c->x_epoch = 0;
+  c->x_attached = true;
+  return 0;
+}
+
+// Same, for ranks that are contexts of ONE process (tests; several GPUs driven by one process).
+extern "C" int smplb_comm_p2p_attach_local(smplb_ctx *c, int nranks, int rank, smplb_ctx *const *peers) {
+  CHECK_CTX(c);
+  RET_IF(nranks < 1 || nranks > X_MAXR || rank < 0 || rank >= nranks || !peers, SMPLB_EINVAL,
+         "1 <= nranks <= %d, 0 <= rank < nranks and non-null peers required", X_MAXR);
+  RET_IF(peers[rank] != c, SMPLB_EINVAL, "peers[rank] must be the context itself");
+  TRY(x_ensure_mbox(c));
+  x_detach(c);
+  for (int r = 0; r < nranks; ++r) {
+    smplb_ctx *p = peers[r];
+    RET_IF(!p, SMPLB_EINVAL, "peers[%d] is NULL", r);
+    if (p != c) {
+      CUDA_TRY(cudaSetDevice(p->device));
+      int rc = x_ensure_mbox(p);
+      CUDA_TRY(cudaSetDevice(c->device));
+      if (rc) return rc;
+      if (p->device != c->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) {
+          smplb_set_error("cudaDeviceEnablePeerAccess(%d -> %d) -> %s", c->device, p->device, cudaGetErrorString(e));
+          return SMPLB_ECUDA;
+        }
+      }
+    }
+    c->x_peers[r] = p->x_mbox;
+  }
+  c->nranks = nranks;
+  c->rank = rank;
+  c->x_epoch = 0;
+  c->x_attached = true;
+  return 0;
+}
+
+// 0 = every exchange so far completed; 1 = a pull timed out (a peer never arrived): the step that
+// saw it returned a NaN loss and zero gradients' denominator.
+extern "C" int smplb_comm_status(smplb_ctx *c, int *status) {
+  CHECK_CTX(c);
+  RET_IF(!status, SMPLB_EINVAL, "null status");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(status, c->x_status, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
 
 extern "C" int smplb_comm_destroy(smplb_ctx *c) {
-  if (!c || !c->nccl_comm) return 0;
+  if (!c) return 0;
+  if (c->x_attached) {
+    cudaSetDevice(c->device);
+    x_detach(c);
+  }
+  if (!c->nccl_comm) {
+    c->nranks = 1;
+    c->rank = 0;
+    return 0;
+  }
   if (g_nccl.destroy) g_nccl.destroy(c->nccl_comm);
   c->nccl_comm = nullptr;
   c->nranks = 1;

@@ -6,7 +6,10 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "smplb.h"
+#include "smplb_debug.h"
 
 #define NJ 24          // SMPL joints
 #define NPF 207        // pose-feature length, 23 * 9
@@ -18,6 +21,23 @@ struct Tree {
   signed char parent[NJ];
   signed char depth[NJ];
   int max_depth;
+};
+
+// ---- mailbox exchange between batch shards (k_exchange.cu)
+#define X_SLOTS 4
+#define X_MAXR 16
+struct __align__(16) XEntry {
+  float v[2];
+  long long cnt;
+  unsigned flag;   // epoch of the entry
+  unsigned pad[3];
+};
+#define X_MBOX_ENTRIES (2 * X_SLOTS * X_MAXR)   // [kind: 0 counts, 1 numerators][slot][rank]
+struct XArgs {
+  XEntry *peers[X_MAXR];   // mailbox of every rank (own one included), mapped into this process
+  int nranks, rank;
+  unsigned epoch;
+  unsigned long long timeout_ns;
 };
 
 struct ProfRec {
@@ -46,7 +66,6 @@ struct smplb_ctx {
   bool gdx_pending = false;         // fold_gemm_dx is on stream_g and not yet joined into the main stream
   int use_prio = 1;                 // smplb_debug_set("prio", 0): the GEMMs stay on the main stream
   bool verts_pending = false;       // stream2 work not yet joined into the main stream
-  int keep_verts = 0;               // smplb_debug_set("keep_verts", 1): always compute verts (device-resident workspace)
   int use_overlap = 1;              // smplb_debug_set("overlap", 0) keeps everything on the main stream
   int V = 0, NB = 0, K = 0, max_batch = 0;
   int V3 = 0;       // 3V
@@ -174,6 +193,16 @@ struct smplb_ctx {
   // NCCL (dlopen'ed)
   void *nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  int comm_backend = 0;            // smplb_debug_set("comm_backend", 1): NCCL even when the mailboxes are attached
+  // mailbox exchange (k_exchange.cu): own mailbox + the peers' mapped ones
+  XEntry *x_mbox = nullptr;
+  XEntry *x_peers[X_MAXR] = {};
+  bool x_ipc[X_MAXR] = {};         // x_peers[r] came from cudaIpcOpenMemHandle
+  bool x_attached = false;
+  unsigned x_epoch = 0;            // exchanges issued so far (the same on every rank)
+  unsigned long long x_timeout_ns = 20ull * 1000 * 1000 * 1000;
+  int *x_status = nullptr;         // device flag: 1 after a pull timed out
+  cudaEvent_t ev_step0 = nullptr, ev_cnt = nullptr;   // step start -> stream3; count exchanged -> main stream
 };
 
 void smplb_set_error(const char *fmt, ...);
@@ -200,6 +229,15 @@ void smplb_set_error(const char *fmt, ...);
     int _r = (expr);       \
     if (_r != 0) return _r; \
   } while (0)
+
+// NVTX range named after the reference's tf.name_scope of the same stage, so an
+// nsys / ncu timeline of a trainer reads like the reference's graph.  Free when no tool is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 struct ProfScope {
   smplb_ctx *c;
@@ -303,3 +341,8 @@ int launch_gp_colsum(smplb_ctx *c, int M, const float *g0, const float *g1, cons
 int launch_gp_final(smplb_ctx *c, long long M_total, const float *col_sums, float *penalty);
 int launch_gp_bwd(smplb_ctx *c, int M, long long M_total, const float *col_sums, float *d0, float *d1, float *d2,
                   float *d3);
+// k_exchange.cu
+int launch_count_exchange(smplb_ctx *c, int B, const float *kp_gt, long long count_override, int mode, long long *den);
+int launch_reduce_exchange_finalize(smplb_ctx *c, int B, const float *part, float w_kp, float w_mesh, int have_mesh,
+                                    const long long *den, float *loss_parts);
+int launch_finalize_den(smplb_ctx *c, float w_kp, float w_mesh, int have_mesh, const long long *den, float *loss_parts);

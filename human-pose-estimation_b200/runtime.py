@@ -165,6 +165,32 @@ class Context(object):
     def comm_init(self, nranks, rank, uid):
         check(lib().smplb_comm_init(self.handle, nranks, rank, C.c_char_p(uid)))
 
+    # -- mailbox exchange over peer memory (the default transport of a sharded step)
+    def p2p_export(self):
+        """64-byte CUDA IPC handle of this context's mailbox (send it to every rank)."""
+        buf = C.create_string_buffer(64)
+        check(lib().smplb_comm_p2p_export(self.handle, buf))
+        return buf.raw
+
+    def p2p_attach(self, nranks, rank, handles):
+        """handles: the nranks exported handles in rank order (one process per rank)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * nranks
+        check(lib().smplb_comm_p2p_attach(self.handle, nranks, rank, C.c_char_p(blob)))
+
+    def p2p_attach_local(self, rank, contexts):
+        """Ranks that are contexts of this process: contexts[rank] is self."""
+        arr = (C.c_void_p * len(contexts))(*[x.handle for x in contexts])
+        check(lib().smplb_comm_p2p_attach_local(self.handle, len(contexts), rank, arr))
+
+    def comm_status(self):
+        st = C.c_int()
+        check(lib().smplb_comm_status(self.handle, C.byref(st)))
+        return st.value
+
+    def comm_destroy(self):
+        check(lib().smplb_comm_destroy(self.handle))
+
     def allreduce_sum(self, dev_array, count=None):
         n = int(np.prod(dev_array.shape)) if count is None else count
         check(lib().smplb_comm_allreduce_sum(self.handle, dev_array.ptr, n))

@@ -9,6 +9,7 @@ import pickle
 import numpy as np
 
 from .. import runtime
+from .. import _lib
 from .._lib import check, lib
 
 
@@ -85,7 +86,7 @@ class SMPL(object):
         joints, pj = a.out((N, K, 3))
         Rs, pR = a.out((N, 24, 3, 3), want=get_skin)
         Jtr, pJ = a.out((N, 24, 3))
-        check(lib().smplb_smpl_forward(self.ctx.handle, N, pb, pt, pv, pj, pR, pJ, a.mem))
+        check(lib().smplb_smpl_forward(self.ctx.handle, N, pb, pt, pv, pj, pR, pJ, 0, a.mem))
         self.J_transformed = Jtr
         if get_skin:
             return verts, joints, Rs
@@ -99,7 +100,7 @@ class SMPL(object):
         pb, pt = a.inp(beta, (N, self.num_betas)), a.inp(theta, (N, 72))
         joints, pj = a.out((N, self.num_keypoints, 3))
         Rs, pR = a.out((N, 24, 3, 3))
-        check(lib().smplb_smpl_forward(self.ctx.handle, N, pb, pt, None, pj, pR, None, a.mem))
+        check(lib().smplb_smpl_forward(self.ctx.handle, N, pb, pt, None, pj, pR, None, 0, a.mem))
         return joints, Rs
 
     # -- backward (TF autodiff in the reference, src/trainer.py:383,502) ----
@@ -166,15 +167,10 @@ class SMPL(object):
         _, pdb = o("d_beta", (N, self.num_betas), backward)
         _, pdt = o("d_theta", (N, 72), backward)
         _, pdc = o("d_cam", (N, 3), backward)
-        if want_verts == "device":
-            self.ctx.debug_set("keep_verts", 1)
-        try:
-            check(lib().smplb_step(self.ctx.handle, N, pb, pt, pc, pk, pp, po, P, float(w_kp), float(w_mesh),
-                                   float(img_size), int(kp_count_override), pv, pj, pR, pkp, pl, pdb, pdt, pdc,
-                                   2 if (nowait and a.mem == runtime.HOST) else a.mem))
-        finally:
-            if want_verts == "device":
-                self.ctx.debug_set("keep_verts", 0)
+        flags = _lib.STEP_KEEP_VERTS if want_verts == "device" else 0
+        check(lib().smplb_step(self.ctx.handle, N, pb, pt, pc, pk, pp, po, P, float(w_kp), float(w_mesh),
+                               float(img_size), int(kp_count_override), pv, pj, pR, pkp, pl, pdb, pdt, pdc, flags,
+                               2 if (nowait and a.mem == runtime.HOST) else a.mem))
         if want_verts == "device":
             out["verts_device_ptr"] = self.last_verts_ptr()
         return out

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SMPLB_VERSION 1
+#define SMPLB_VERSION 2
 
 #define SMPLB_HOST 0
 #define SMPLB_DEVICE 1
@@ -52,6 +52,12 @@ extern "C" {
 #define SMPLB_EDEVICE (-3)  /* no sm_100 device                     */
 #define SMPLB_ESTATE (-4)   /* backward without a matching forward  */
 #define SMPLB_ENCCL (-5)    /* NCCL unavailable or failed           */
+
+/* flags of smplb_smpl_forward / smplb_step */
+#define SMPLB_STEP_KEEP_VERTS 1 /* compute verts even when the verts pointer is NULL and keep them in a
+                                   device workspace of the context (smplb_last_verts): what a trainer
+                                   wants -- the 339 MB stay in HBM for the renderer / mesh loss and only
+                                   the small results cross PCIe */
 
 #define SMPLB_NUM_JOINTS 24
 #define SMPLB_NUM_POSE_BASIS 207
@@ -107,17 +113,15 @@ int smplb_launch_count(smplb_ctx *ctx, int64_t *count);
  * enabled (debug/bench breakdown only; serialises nothing but adds event overhead). */
 int smplb_profile_enable(smplb_ctx *ctx, int on);   /* 1: per-kernel times (serialised streams); 2: timeline trace */
 int smplb_profile_read(smplb_ctx *ctx, char *buf, size_t buflen); /* "name ms count\n" lines (mode 2: "name start_ms end_ms" per launch); resets */
-/* Test hook: key "blend_tc" = 0 routes the blend contraction through the FP32 CUDA-core GEMM
- * that cross-checks the tcgen05 kernel (default 1); "skin_tc", "fold", "compact_bwd",
- * "overlap" likewise select cross-check paths; "keep_verts" see smplb_last_verts. */
-int smplb_debug_set(smplb_ctx *ctx, const char *key, int value);
+/* (test / tuning hooks live in the private header csrc/smplb_debug.h) */
 
 /* ---- SMPL.__call__(beta, theta, get_skin) (batch_smpl.py:88-160) ------------------ *
  * beta [B,10], theta [B,72] -> verts [B,V,3] (may be NULL == get_skin False),
  * joints [B,K,3], Rs [B,24,3,3] (may be NULL), J_transformed [B,24,3] (may be NULL;
- * the attribute batch_smpl.py:135 sets).  Saves what smplb_smpl_backward needs.     */
+ * the attribute batch_smpl.py:135 sets).  Saves what smplb_smpl_backward needs.
+ * flags: 0 or SMPLB_STEP_KEEP_VERTS.                                                  */
 int smplb_smpl_forward(smplb_ctx *ctx, int B, const float *beta, const float *theta, float *verts,
-                       float *joints, float *Rs, float *J_transformed, int mem);
+                       float *joints, float *Rs, float *J_transformed, int flags, int mem);
 
 /* Backward of the last smplb_smpl_forward on this context (same B).  Replaces TF
  * autodiff through batch_smpl.py:88-160 (src/trainer.py:383,502).  Upstream gradients
@@ -128,10 +132,8 @@ int smplb_smpl_backward(smplb_ctx *ctx, int B, const float *d_verts, const float
 
 /* Device pointer to the verts [B,V,3] of the last forward / step (the caller's buffer in
  * device mode, else a workspace of the context that stays valid until the next call); NULL if
- * the last call did not compute verts.  With smplb_debug_set(ctx, "keep_verts", 1) host-mode
- * calls that pass verts == NULL still compute them and keep them on the device -- what a
- * trainer wants: the 339 MB stay in HBM for the renderer / mesh loss, only the small
- * results cross PCIe.                                                                 */
+ * the last call did not compute verts.  With SMPLB_STEP_KEEP_VERTS in the call's flags a call
+ * that passes verts == NULL still computes them and keeps them on the device.          */
 int smplb_last_verts(smplb_ctx *ctx, const float **dptr);
 
 /* ---- src/tf_smpl/batch_lbs.py stand-alone entry points ---------------------------- */
@@ -222,19 +224,36 @@ int smplb_interpolate(smplb_ctx *ctx, int N, int row, const float *fake, const f
  *   out: verts [B,V,3] (may be NULL only if no mesh loss), joints [B,K,3], Rs [B,24,3,3]
  *        (may be NULL), kp_pred [B,K,2] (may be NULL),
  *        loss_parts [4] = {kp abs_sum, kp num_present, mesh loss sum, total weighted loss};
- *        with a communicator attached (smplb_comm_init, nranks > 1) the first three are
- *        all-reduced over the ranks inside the call and the gradients use the global count
- *        d_beta [B,10], d_theta [B,72], d_cam [B,3] (all three may be NULL == forward only) */
+ *        with the batch sharded over ranks (smplb_comm_p2p_attach* or smplb_comm_init) the
+ *        first three are summed over the ranks inside the call -- the visibility count at
+ *        the start of the step, the numerators next to the backward -- and the gradients use
+ *        the global count
+ *        d_beta [B,10], d_theta [B,72], d_cam [B,3] (all three may be NULL == forward only)
+ *   flags: 0 or SMPLB_STEP_KEEP_VERTS                                                      */
 int smplb_step(smplb_ctx *ctx, int B, const float *beta, const float *theta, const float *cam,
                const float *kp_gt, const float *points_xy, const int32_t *offsets, int P, float w_kp,
                float w_mesh, float img_size, int64_t kp_count_override, float *verts, float *joints, float *Rs,
-               float *kp_pred, float *loss_parts, float *d_beta, float *d_theta, float *d_cam, int mem);
+               float *kp_pred, float *loss_parts, float *d_beta, float *d_theta, float *d_cam, int flags,
+               int mem);
 
-/* ---- multi-GPU: one process per GPU, the only exchange is a <=512-float sum -------- */
+/* ---- multi-GPU: one process per GPU; the batch shards over the ranks and the only exchange is
+ * the sum of the visibility count and of the loss numerators (the
+ * reference is single-device, src/trainer.py:352).  Two transports:
+ *  (1) mailboxes in peer GPU memory, written / polled by the loss kernels themselves over
+ *      NVLink (no collective launch): every rank exports the handle of its context's mailbox,
+ *      the host exchanges the 64-byte handles by any means (torch.distributed, MPI, a file) and
+ *      attaches them.  All ranks must issue the steps of their contexts in the same order.   */
+int smplb_comm_p2p_export(smplb_ctx *ctx, void *handle64);            /* CUDA IPC handle, 64 bytes */
+int smplb_comm_p2p_attach(smplb_ctx *ctx, int nranks, int rank, const void *handles /* nranks x 64 B */);
+/* the same when the ranks are contexts of ONE process (peers[rank] == ctx)              */
+int smplb_comm_p2p_attach_local(smplb_ctx *ctx, int nranks, int rank, smplb_ctx *const *peers);
+/* 0, or 1 once a rank waited longer than the timeout for a peer (that step's loss is NaN) */
+int smplb_comm_status(smplb_ctx *ctx, int *status);
+/* (2) NCCL (dlopen'ed, not a link-time dependency): used when no mailboxes are attached.   */
 int smplb_comm_unique_id(void *id128);                 /* 128-byte NCCL unique id (rank 0)   */
 int smplb_comm_init(smplb_ctx *ctx, int nranks, int rank, const void *id128);
 int smplb_comm_allreduce_sum(smplb_ctx *ctx, float *dev_buf, int count); /* in place, ctx stream */
-int smplb_comm_destroy(smplb_ctx *ctx);
+int smplb_comm_destroy(smplb_ctx *ctx);               /* detaches both transports            */
 
 #ifdef __cplusplus
 }

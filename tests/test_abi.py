@@ -26,6 +26,10 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "libsmplb.so does not export %s" % n
     # the ctypes table binds exactly the header's functions (minus the two untyped getters)
     assert set(_lib.SIGNATURES) | {"smplb_last_error", "smplb_version"} == set(names)
+    # test / tuning hooks are exported but live in the private header, not in the public ABI
+    priv = open(os.path.join(ROOT, "human-pose-estimation_b200", "csrc", "smplb_debug.h")).read()
+    for n in _lib.PRIVATE_SIGNATURES:
+        assert n not in names and n in priv and hasattr(lib, n)
 
 
 def test_no_cpu_fallback_create_fails_loudly_without_gpu():
