@@ -185,6 +185,17 @@ __global__ void k_finalize_den(float w_kp, float w_mesh, int have_mesh, const fl
   out[3] = w_kp * kp + w_mesh * ml;
 }
 
+// With lazy module loading the first launch of a kernel loads it, which can wait for the device to
+// drain -- fatal when the kernel running is a rank of the SAME process waiting for that very launch.
+// Attaching therefore loads the exchange kernels up front.
+int exchange_preload() {
+  cudaFuncAttributes a;
+  CUDA_TRY(cudaFuncGetAttributes(&a, k_count_exchange));
+  CUDA_TRY(cudaFuncGetAttributes(&a, k_reduce_exchange_finalize));
+  CUDA_TRY(cudaFuncGetAttributes(&a, k_finalize_den));
+  return 0;
+}
+
 static XArgs make_xargs(smplb_ctx *c) {
   XArgs x;
   for (int r = 0; r < X_MAXR; ++r) x.peers[r] = r < c->nranks ? c->x_peers[r] : nullptr;

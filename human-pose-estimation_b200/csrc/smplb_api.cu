@@ -1405,6 +1405,7 @@ extern "C" int smplb_comm_allreduce_sum(smplb_ctx *c, float *dev_buf, int count)
 // ---- mailbox exchange (k_exchange.cu): the peers' mailboxes mapped into this process -----------
 static int x_ensure_mbox(smplb_ctx *c) {
   if (c->x_mbox) return 0;
+  TRY(exchange_preload());
   CUDA_TRY(cudaMalloc((void **)&c->x_mbox, X_MBOX_ENTRIES * sizeof(XEntry)));
   CUDA_TRY(cudaMemset(c->x_mbox, 0, X_MBOX_ENTRIES * sizeof(XEntry)));
   return 0;

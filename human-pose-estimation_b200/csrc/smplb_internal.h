@@ -342,6 +342,7 @@ int launch_gp_final(smplb_ctx *c, long long M_total, const float *col_sums, floa
 int launch_gp_bwd(smplb_ctx *c, int M, long long M_total, const float *col_sums, float *d0, float *d1, float *d2,
                   float *d3);
 // k_exchange.cu
+int exchange_preload();
 int launch_count_exchange(smplb_ctx *c, int B, const float *kp_gt, long long count_override, int mode, long long *den);
 int launch_reduce_exchange_finalize(smplb_ctx *c, int B, const float *part, float w_kp, float w_mesh, int have_mesh,
                                     const long long *den, float *loss_parts);
