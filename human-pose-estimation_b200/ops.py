@@ -173,6 +173,26 @@ def compute_gradient_penalty(gradients, debug=False, want_sums=False):
     return (np.float32(pv), sums) if want_sums else np.float32(pv)
 
 
+def gradient_penalty_step(gradients, out=None, m_total=None):
+    """Device-resident penalty + its gradient in one asynchronous call pair (what the critic stage of
+    src/trainer.py:566-578 needs every step): gradients = four DeviceArrays; `out` keeps the preallocated
+    outputs {"penalty" [1], "col_sums" [428], "d0".."d3"} across calls.  No host synchronisation."""
+    g0, g1, g2, g3 = gradients
+    ctx = _ctx_for(g0)
+    M = int(g0.shape[0])
+    out = {} if out is None else out
+    if "penalty" not in out:
+        out["penalty"] = ctx.empty((1,))
+        out["col_sums"] = ctx.empty((GP_FLOATS,))
+        for i, shp in enumerate([(M, 13, 13), (M, 14, 3), (M, 10), (M, 23, 3, 3)]):
+            out["d%d" % i] = ctx.empty(shp)
+    check(lib().smplb_gradient_penalty(ctx.handle, M, g0.ptr, g1.ptr, g2.ptr, g3.ptr, out["penalty"].ptr, out["col_sums"].ptr,
+                                       runtime.DEVICE))
+    check(lib().smplb_gradient_penalty_backward(ctx.handle, M, int(m_total or M), out["col_sums"].ptr, out["d0"].ptr,
+                                                out["d1"].ptr, out["d2"].ptr, out["d3"].ptr, runtime.DEVICE))
+    return out
+
+
 def gradient_penalty_from_sums(col_sums, m_total):
     ctx = _ctx_for(col_sums)
     a = runtime.Args(ctx)

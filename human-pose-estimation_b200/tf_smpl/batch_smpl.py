@@ -103,6 +103,13 @@ class SMPL(object):
         check(lib().smplb_smpl_forward(self.ctx.handle, N, pb, pt, None, pj, pR, None, 0, a.mem))
         return joints, Rs
 
+    def forward_into(self, beta, theta, n, verts=None, joints=None, Rs=None):
+        """Device-resident serving call (src/predictor.py:141): the first `n` rows of the DeviceArrays
+        beta / theta -> preallocated DeviceArrays (verts and Rs optional); asynchronous, no allocation."""
+        ptr = lambda x: None if x is None else x.ptr   # noqa: E731
+        check(lib().smplb_smpl_forward(self.ctx.handle, int(n), beta.ptr, theta.ptr, ptr(verts), joints.ptr, ptr(Rs), None, 0,
+                                       runtime.DEVICE))
+
     # -- backward (TF autodiff in the reference, src/trainer.py:383,502) ----
     def backward(self, d_verts=None, d_joints=None, d_Rs=None, batch=None):
         """Gradients of the last call w.r.t. (beta, theta) for upstream gradients on

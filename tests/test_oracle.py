@@ -175,3 +175,23 @@ def test_kcs_oracle_matches_reference_source():
     up = rng.normal(size=(5, 13, 13))
     g = ref.torch.autograd.grad((k_ref * ref.tensor(up)).sum(), [jt])[0].numpy()
     assert rel_err(onp.get_kcs_backward(joints, C_ref, up), g) < 1e-12
+
+
+def test_torch_port_matches_numpy_oracle(small_model):
+    """oracle/smpl_torch.py (the CPU baseline bench.py times on the GPU box) == oracle/smpl_numpy.py:
+    forward, loss and autograd gradients vs the hand-derived backward, fp64."""
+    import torch
+    from hpe_b200 import synthetic
+    from oracle import smpl_numpy as onp
+    from oracle import smpl_torch as ot
+    inp = synthetic.make_inputs(5, seed=11, dtype=np.float64)
+    ts = ot.SMPL(small_model, dtype=torch.float64)
+    verts, joints, Rs, kp, loss, db, dth, dc = ot.step(ts, inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"])
+    o = onp.SMPL(small_model, dtype=np.float64)
+    v, j, R = o(inp["beta"], inp["theta"], get_skin=True)
+    kpo = onp.batch_orth_proj_idrot(j, inp["cam"])
+    assert np.max(np.abs(verts - v)) < 1e-12 and np.max(np.abs(joints - j)) < 1e-12 and np.max(np.abs(Rs - R)) < 1e-12
+    assert abs(loss - onp.kp_reprojection_loss(inp["kp_gt"], kpo)) < 1e-12
+    dj, dcam = onp.orth_proj_backward(j, inp["cam"], onp.kp_loss_backward(inp["kp_gt"], kpo))
+    dbo, dtho = onp.smpl_backward(o, inp["beta"], inp["theta"], None, dj, None)
+    assert np.max(np.abs(db - dbo)) < 1e-10 and np.max(np.abs(dth - dtho)) < 1e-10 and np.max(np.abs(dc - dcam)) < 1e-10
