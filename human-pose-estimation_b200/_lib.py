@@ -8,7 +8,8 @@ GP_FLOATS = 428
 NUM_JOINTS = 24
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmplb.so")
+# (SMPLB_LIB: an instrumented build of the same library, e.g. -DFB_TIMING, for the tools/)
+LIB_PATH = os.environ.get("SMPLB_LIB") or os.path.join(_HERE, "libsmplb.so")
 
 
 class SmplbError(RuntimeError):

@@ -21,6 +21,9 @@ static __device__ __noinline__ void store_rows4(float *dst, int row_stride, int 
                                          float b0, float b1, float b2, float c0, float c1, float c2, float d0, float d1,
                                          float d2) {
   if (!v_ok) return;
+#if FB_ABLATE == 3
+  return;   // tuning build: no stores at all (everything but the store path)
+#endif
 #if FB_ABLATE == 5
   // tuning build: same stores and bytes, but a warp's three stores of a row each cover 128 contiguous
   // bytes (WRONG element order) -- what fully coalesced store requests would buy

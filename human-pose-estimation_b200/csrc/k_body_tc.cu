@@ -849,6 +849,7 @@ int body_tc_init(smplb_ctx *c) {
   CUDA_TRY(cudaFuncSetAttribute(k_body_wt, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyW::SM_TOTAL));
   CUDA_TRY(cudaFuncSetAttribute(k_body_tc<BodyP>, cudaFuncAttributeMaxDynamicSharedMemorySize, BodyP::SM_TOTAL));
   TRY(body_pair_init(c));
+  TRY(body_res_init(c));
   c->body_tc_ok = true;
   return 0;
 }
@@ -915,9 +916,10 @@ static int launch_body_wt(smplb_ctx *c, int B, const void *x16, const void *A16,
 }
 
 // verts [B][V][3] from the operand rows pose_fwd wrote (x16 [B][256], A16 [12 B][64]).
-// Default: the CTA-pair kernel of k_body_pair.cu (it needs an even number of 128-vertex tiles; SMPL
-// has 54).  smplb_debug_set("fused", 2 .. 6) selects the single-CTA configurations of this file
-// (tuning / validation; 4 = the best of them, which is also the fallback).
+// Default: the CTA-pair kernel with the resident Dt16 tile of k_body_res.cu (it needs an even number
+// of 128-vertex tiles; SMPL has 54).  smplb_debug_set("fused", 9) selects its sixteen-epilogue-warp
+// configuration, 7 the streaming CTA-pair kernel of k_body_pair.cu, 2 .. 6 the single-CTA
+// configurations of this file (tuning / validation; 4 = the best of them, which is also the fallback).
 int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts) {
   RET_IF(!c->body_tc_ok, SMPLB_ESTATE, "fused tcgen05 blend+skinning path is not initialised");
   switch (c->use_fused) {
@@ -926,8 +928,12 @@ int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, fl
     case 4: return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
     case 5: return launch_body_wt(c, B, x16, A16, verts);
     case 6: return launch_body_pair(c, B, x16, A16, verts);
-    default:
+    case 7:
       if ((c->Vp / FB_VT) % 2 == 0) return launch_body_fwd_pair(c, B, x16, A16, verts);
+      return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
+    case 9:
+    default:
+      if ((c->Vp / FB_VT) % 2 == 0) return launch_body_fwd_res(c, B, x16, A16, verts, c->use_fused);
       return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
   }
 }

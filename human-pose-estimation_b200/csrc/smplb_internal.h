@@ -310,6 +310,9 @@ int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, fl
 // k_body_pair.cu (cta_group::2 variant; needs an even number of 128-vertex tiles)
 int body_pair_init(smplb_ctx *c);
 int launch_body_fwd_pair(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts);
+// k_body_res.cu (cta_group::2 with the Dt16 tile resident in shared memory and W16 in tensor memory)
+int body_res_init(smplb_ctx *c);
+int launch_body_fwd_res(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts, int variant);
 // k_skin.cu
 int launch_skin_fwd(smplb_ctx *c, int B, const float *A, const float *v_posed, float *verts);
 int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, const float *kp_gt, float *joints,

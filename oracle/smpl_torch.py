@@ -121,7 +121,7 @@ def step(smpl, beta, theta, cam, kp_gt):
     verts, joints, Rs = smpl(b, th, get_skin=True)
     kp = batch_orth_proj_idrot(joints, c)
     loss = kp_reprojection_loss(g, kp)
-    if loss.requires_grad and float(loss) != 0.0:
+    if loss.requires_grad and float(loss.detach()) != 0.0:
         db, dth, dc = torch.autograd.grad(loss, [b, th, c])
     else:
         db, dth, dc = torch.zeros_like(b), torch.zeros_like(th), torch.zeros_like(c)

@@ -370,21 +370,22 @@ def test_tcgen05_skinning_matches_fp32_kernel(smpl_full):
 
 
 def test_fused_blend_skinning_matches_two_kernel_path(smpl_full, full_model):
-    """k_body_pair / k_body_tc (blend + skinning in one kernel, v_posed stays in TMEM) against k_blend_tc +
+    """k_body_res / k_body_pair / k_body_tc (blend + skinning in one kernel, v_posed stays in TMEM) against k_blend_tc +
     k_skin_tc: the same fp16 operands and fp32 accumulation, so the two may differ only by fp32
     summation order; and against the fp64 oracle at the stated tolerance.  Batch sizes straddle
     the 96-sample super-tile and the 8-sample skinning tile (ragged tails)."""
     ctx = smpl_full.ctx
     o = onp.SMPL(full_model, dtype=np.float64)
-    for B in (1, 7, 96, 203):
+    for B in (1, 7, 96, 203, 1700):     # 1700: 18 sample blocks x 27 vertex-tile pairs, pairs straddle vertex tiles
         inp = synthetic.make_inputs(B, seed=500 + B)
         try:
             ctx.debug_set("fused", 0)
             v0, j0, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
-            # 1: the default (CTA pairs with cta_group::2 MMAs, k_body_pair); 4: the best single-CTA
-            # configuration; 2, 3: tuning variants; 5: W16 as a TMEM-resident operand; 6: CTA pairs
-            # with the Dt16 tiles multicast
-            for variant in (1, 2, 3, 4, 5, 6):
+            # 1: the default (CTA pairs, Dt16 tile resident in shared memory, W16 in tensor memory, k_body_res); 9: the same
+            # with sixteen epilogue warps;
+            # 7: CTA pairs streaming Dt16 (k_body_pair); 4: the best single-CTA configuration; 2, 3: tuning
+            # variants; 5: W16 as a TMEM-resident operand; 6: CTA pairs with the Dt16 tiles multicast
+            for variant in (1, 9, 7, 2, 3, 4, 5, 6):
                 ctx.debug_set("fused", variant)
                 v1, j1, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
                 assert np.isfinite(v1).all()
