@@ -80,6 +80,7 @@ SIGNATURES = {
 # private hooks (csrc/smplb_debug.h), not part of include/smplb.h
 PRIVATE_SIGNATURES = {
     "smplb_debug_set": [_P, C.c_char_p, _I],
+    "smplb_debug_p2p_inject": [_P, _I, C.c_uint, _I, _F, _F, C.c_longlong],
 }
 STEP_KEEP_VERTS = 1
 

@@ -1498,6 +1498,24 @@ extern "C" int smplb_comm_p2p_attach_local(smplb_ctx *c, int nranks, int rank, s
   return 0;
 }
 
+// Test hook (csrc/smplb_debug.h): writes rank `from_rank`'s entry of `epoch` into THIS context's mailbox, as that
+// rank's push would.  Lets a single-GPU test run the ranks one after the other: no kernel ever waits for a kernel
+// that has not been launched yet (two spinning kernels of one GPU are not guaranteed to run concurrently).
+extern "C" int smplb_debug_p2p_inject(smplb_ctx *c, int kind, unsigned epoch, int from_rank, float v0, float v1,
+                                      long long cnt) {
+  CHECK_CTX(c);
+  RET_IF(!c->x_mbox || kind < 0 || kind > 1 || from_rank < 0 || from_rank >= X_MAXR, SMPLB_EINVAL, "no mailbox / bad arguments");
+  XEntry e = {};
+  e.v[0] = v0;
+  e.v[1] = v1;
+  e.cnt = cnt;
+  e.flag = epoch;
+  XEntry *dst = c->x_mbox + ((size_t)kind * X_SLOTS + (epoch % X_SLOTS)) * X_MAXR + from_rank;
+  CUDA_TRY(cudaMemcpyAsync(dst, &e, sizeof(e), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 // 0 = every exchange so far completed; 1 = a pull timed out (a peer never arrived): the step that
 // saw it returned a NaN loss and zero gradients' denominator.
 extern "C" int smplb_comm_status(smplb_ctx *c, int *status) {

@@ -183,6 +183,10 @@ class Context(object):
         arr = (C.c_void_p * len(contexts))(*[x.handle for x in contexts])
         check(lib().smplb_comm_p2p_attach_local(self.handle, len(contexts), rank, arr))
 
+    def p2p_inject(self, kind, epoch, from_rank, v0=0.0, v1=0.0, cnt=0):
+        """Test hook: rank `from_rank`'s push of exchange `epoch` written into this context's mailbox."""
+        check(lib().smplb_debug_p2p_inject(self.handle, int(kind), int(epoch), int(from_rank), float(v0), float(v1), int(cnt)))
+
     def comm_status(self):
         st = C.c_int()
         check(lib().smplb_comm_status(self.handle, C.byref(st)))

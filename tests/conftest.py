@@ -4,10 +4,6 @@ import sys
 import numpy as np
 import pytest
 
-# the single-GPU exchange tests run several "ranks" as contexts of one process: give every stream its own
-# hardware queue so a waiting kernel of one rank can never sit in front of another rank's push
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

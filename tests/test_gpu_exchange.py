@@ -5,8 +5,9 @@ count exchanged at the start of the step and the loss numerators next to the bac
 numbers: the loss of kp_reprojection_loss (src/ops.py:35-47) over the WHOLE batch and gradients that
 divide by the GLOBAL num_present.
 
-On one GPU the ranks are contexts of this process (smplb_comm_p2p_attach_local); the 2-GPU torchrun
-test exercises CUDA IPC + NVLink and is skipped on a single-GPU box.
+On one GPU the ranks are contexts of this process (smplb_comm_p2p_attach_local) that step ONE AFTER THE OTHER
+(B200_PROFILING.md: kernels that wait for one another must not be separate launches on one GPU); the concurrent
+exchange over CUDA IPC + NVLink is the 2-GPU torchrun test, skipped on a single-GPU box (logs in profiles/r02).
 """
 import os
 import subprocess
@@ -38,6 +39,26 @@ def _single_device_reference(model, inp, B, w_kp):
     return s, full
 
 
+def _run_ranks_in_turn(ranks, epoch, order, calls, local_parts):
+    """One sharded step on every rank of a single GPU WITHOUT two kernels ever waiting for each other (nothing
+    guarantees that two spinning kernels of one GPU run at the same time): the ranks step one after the other in
+    `order`; what a rank needs from ranks that have not stepped yet is written into its mailbox with the test hook
+    (their visibility count and numerators, computed beforehand without a communicator), what it needs from ranks
+    that already stepped are those ranks' real pushes."""
+    outs = [None] * len(ranks)
+    done = set()
+    for r in order:
+        for peer in range(len(ranks)):
+            if peer != r and peer not in done:
+                cnt, num, mesh = local_parts[peer]
+                ranks[r].ctx.p2p_inject(0, epoch, peer, cnt=cnt)
+                ranks[r].ctx.p2p_inject(1, epoch, peer, v0=num, v1=mesh)
+        outs[r] = calls[r]()
+        ranks[r].ctx.sync()
+        done.add(r)
+    return outs
+
+
 @pytest.mark.parametrize("nranks,B", [(2, 512), (3, 389)])
 def test_mailbox_exchange_equals_single_device(full_model, nranks, B):
     """nranks contexts of one GPU act as ranks: every rank's loss is the whole batch's loss bit for bit
@@ -51,16 +72,22 @@ def test_mailbox_exchange_equals_single_device(full_model, nranks, B):
     ranks = [SMPL(full_model, max_batch=B) for _ in range(nranks)]
     ctxs = [r.ctx for r in ranks]
     for i, r in enumerate(ranks):
-        r.ctx.debug_set("comm_timeout_ms", 5000)
+        r.ctx.debug_set("comm_timeout_ms", 3000)
         r.ctx.p2p_attach_local(i, ctxs)
     rng = [sharding.shard_range(B, nranks, i) for i in range(nranks)]
     dev = [_dev(r.ctx, inp, *rng[i]) for i, r in enumerate(ranks)]
-    for rep in range(3):                      # several epochs: slots are reused
-        outs = []
-        for i, r in enumerate(ranks):         # device-mode calls are asynchronous: rank 0 waits on the GPU
-            d = dev[i]                        # for rank 1's push while the host goes on to enqueue rank 1
-            outs.append(r.step(d["beta"], d["theta"], d["cam"], d["kp_gt"], w_kp=w_kp, want_verts=False))
-        got = [_np(o) for o in outs]
+    # what every shard contributes, and the single-device per-sample results with the global count
+    want, local_parts = [], []
+    for lo, hi in rng:
+        w = ref_ctx.step(inp["beta"][lo:hi], inp["theta"][lo:hi], inp["cam"][lo:hi], inp["kp_gt"][lo:hi], w_kp=w_kp,
+                         want_verts=False, kp_count_override=tot)
+        want.append({k: np.array(w[k]) for k in KEYS})
+        local_parts.append((2 * int(np.count_nonzero(inp["kp_gt"][lo:hi, :, 2])), float(w["loss_parts"][0]), 0.0))
+    calls = [lambda i=i: ranks[i].step(dev[i]["beta"], dev[i]["theta"], dev[i]["cam"], dev[i]["kp_gt"], w_kp=w_kp,
+                                       want_verts=False) for i in range(nranks)]
+    for epoch in (1, 2, 3, 4, 5, 6):          # more epochs than mailbox slots; the order the ranks step in rotates
+        order = [(epoch + j) % nranks for j in range(nranks)]
+        got = [_np(o) for o in _run_ranks_in_turn(ranks, epoch, order, calls, local_parts)]
         assert all(r.ctx.comm_status() == 0 for r in ranks)
         for g in got[1:]:
             assert np.array_equal(g["loss_parts"], got[0]["loss_parts"]), "ranks disagree on the global loss"
@@ -69,11 +96,8 @@ def test_mailbox_exchange_equals_single_device(full_model, nranks, B):
         assert abs(lp[0] - full["loss_parts"][0]) <= 2e-6 * full["loss_parts"][0]
         assert abs(lp[3] - full["loss_parts"][3]) <= 2e-6 * abs(full["loss_parts"][3])
         for i in range(nranks):
-            lo, hi = rng[i]
-            want = ref_ctx.step(inp["beta"][lo:hi], inp["theta"][lo:hi], inp["cam"][lo:hi], inp["kp_gt"][lo:hi], w_kp=w_kp,
-                                want_verts=False, kp_count_override=tot)
             for k in KEYS:
-                assert np.array_equal(got[i][k], want[k]), "rank %d: %s differs from the single-device result" % (i, k)
+                assert np.array_equal(got[i][k], want[i][k]), "rank %d: %s differs from the single-device result" % (i, k)
     for r in ranks:
         r.ctx.comm_destroy()
 
@@ -90,24 +114,28 @@ def test_mailbox_exchange_mesh_step(full_model):
     full = {k: np.array(v) for k, v in full.items()}
     ranks = [SMPL(full_model, max_batch=B) for _ in range(2)]
     for i, r in enumerate(ranks):
-        r.ctx.debug_set("comm_timeout_ms", 5000)
+        r.ctx.debug_set("comm_timeout_ms", 3000)
         r.ctx.p2p_attach_local(i, [x.ctx for x in ranks])
-    outs = []
+    calls, local_parts = [], []
     for i, r in enumerate(ranks):
         lo, hi = sharding.shard_range(B, 2, i)
         rows = pts3[(pts3[:, 0] >= lo) & (pts3[:, 0] < hi)].copy()
         rows[:, 0] -= lo
         pts, offs = ops.silhouette_csr(rows, hi - lo)
         d = _dev(r.ctx, inp, lo, hi)
-        outs.append(r.step(d["beta"], d["theta"], d["cam"], d["kp_gt"],
-                           silhouette=(r.ctx.to_device(pts), r.ctx.to_device(offs, dtype=np.int32))))
-    got = [_np(o, ("loss_parts", "d_beta", "d_theta", "d_cam")) for o in outs]
-    assert np.array_equal(got[0]["loss_parts"], got[1]["loss_parts"])
-    for j in range(4):
-        assert abs(got[0]["loss_parts"][j] - full["loss_parts"][j]) <= 1e-5 * abs(full["loss_parts"][j])
-    for k in ("d_beta", "d_theta", "d_cam"):
-        cat = np.concatenate([got[0][k], got[1][k]])
-        assert np.max(np.abs(cat - full[k])) <= 1e-5 * np.max(np.abs(full[k])), k
+        sil = (r.ctx.to_device(pts), r.ctx.to_device(offs, dtype=np.int32))
+        calls.append(lambda r=r, d=d, sil=sil: r.step(d["beta"], d["theta"], d["cam"], d["kp_gt"], silhouette=sil))
+        w = s.step(inp["beta"][lo:hi], inp["theta"][lo:hi], inp["cam"][lo:hi], inp["kp_gt"][lo:hi], silhouette=(pts, offs))
+        local_parts.append((int(w["loss_parts"][1]), float(w["loss_parts"][0]), float(w["loss_parts"][2])))
+    for epoch, order in ((1, [0, 1]), (2, [1, 0])):
+        got = [_np(o, ("loss_parts", "d_beta", "d_theta", "d_cam")) for o in _run_ranks_in_turn(ranks, epoch, order, calls, local_parts)]
+        assert all(r.ctx.comm_status() == 0 for r in ranks)
+        assert np.array_equal(got[0]["loss_parts"], got[1]["loss_parts"])
+        for j in range(4):
+            assert abs(got[0]["loss_parts"][j] - full["loss_parts"][j]) <= 1e-5 * abs(full["loss_parts"][j])
+        for k in ("d_beta", "d_theta", "d_cam"):
+            cat = np.concatenate([got[0][k], got[1][k]])
+            assert np.max(np.abs(cat - full[k])) <= 1e-5 * np.max(np.abs(full[k])), k
 
 
 def _three_context_stress(engines, B, steps, ref_engine=None):
