@@ -299,3 +299,59 @@ class _Compat:
 
 
 compat = _Compat()
+
+
+# ---- the two symbols hpe_b200/tf_adapter.py needs ----------------
+def _set_shape(self, shape):
+    """tf.Tensor.set_shape: a static-shape assertion; here it only checks."""
+    want = [int(s) if s is not None else None for s in list(shape)]
+    have = list(self.shape)
+    assert len(want) == len(have) and all(w is None or w == h for w, h in zip(want, have)), (want, have)
+
+
+Tensor.set_shape = _set_shape
+
+
+def numpy_function(func, inp, Tout, name=None):
+    """tf.numpy_function: call `func` on numpy copies of the inputs; outputs come back as tensors of
+    dtypes Tout (outside the autograd graph, as in TensorFlow)."""
+    args = [x.detach().as_subclass(torch.Tensor).numpy() if isinstance(x, torch.Tensor) else np.asarray(x) for x in inp]
+    out = func(*args)
+    single = not isinstance(Tout, (list, tuple))
+    outs = [out] if single else list(out)
+    touts = [Tout] if single else list(Tout)
+    res = [_t(np.asarray(o), dt) for o, dt in zip(outs, touts)]
+    return res[0] if single else res
+
+
+def custom_gradient(f):
+    """tf.custom_gradient: f(*args) -> (outputs, grad_fn); grad_fn(*upstream) -> gradients w.r.t. args.
+    Implemented as a torch.autograd.Function; outputs that receive no gradient get None upstream is
+    NOT TensorFlow's behaviour (it passes zeros), so zeros are materialised."""
+
+    def wrapped(*args):
+        targs = [_t(a) for a in args]
+        holder = {}
+
+        class _Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, *xs):
+                outs, grad_fn = f(*[x.as_subclass(Tensor) for x in xs])
+                holder["grad"] = grad_fn
+                holder["single"] = not isinstance(outs, (list, tuple))
+                outs = [outs] if holder["single"] else list(outs)
+                holder["like"] = [o.detach() for o in outs]
+                return tuple(o.detach().as_subclass(torch.Tensor) for o in outs)
+
+            @staticmethod
+            def backward(ctx, *ups):
+                ups = [(_t(u) if u is not None else _t(torch.zeros_like(l))) for u, l in zip(ups, holder["like"])]
+                g = holder["grad"](*ups)
+                g = list(g) if isinstance(g, (list, tuple)) else [g]
+                return tuple(None if x is None else x.as_subclass(torch.Tensor) for x in g)
+
+        outs = _Fn.apply(*[a.as_subclass(torch.Tensor) for a in targs])
+        outs = [o.as_subclass(Tensor) for o in outs]
+        return outs[0] if holder["single"] else tuple(outs)
+
+    return wrapped
