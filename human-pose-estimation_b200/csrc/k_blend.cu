@@ -6,6 +6,8 @@
 //       Dext rows = posedirs (207) | shapedirs (NB) | v_template (1) | zero padding
 //   backward (TF autodiff of the same two matmuls):
 //       dx[b,k] = sum_n dp[b,n] * Dext[k,n]   (split-K partial sums, reduced in k_pose_bwd)
+#include <cuda_bf16.h>
+
 #include "smplb_internal.h"
 
 #define BM 128
@@ -113,4 +115,42 @@ int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part, bool 
   LAUNCH(c, compact ? "blend_bwd_sgemm_active" : "blend_bwd_sgemm", grid, 256, 0, k_sgemm<true>, B, KX, pitch, kchunk, dp,
          pitch, D, pitch, dx_part, KX);
   return 0;
+}
+
+// ---- dense blend backward on the tensor cores ------------------------------------------------------
+// dx[b, k] = sum_n dp[b, n] Dext[k, n] is a [B x 62208] x [62208 x 224] contraction once the operands are split
+// (dp = hi + lo and Dext = hi + lo in bf16; hi.hi + lo.hi + hi.lo keeps ~16 significand bits, the dropped lo.lo
+// term is 2^-16 relative): k_gemm_tc with bf16 operands, split-K over the SMs, partials summed by k_pose_bwd.
+__global__ void k_build_dbf(int pitch, const float *__restrict__ Dext, __nv_bfloat16 *__restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (n >= pitch) return;
+  const float v = Dext[(size_t)k * pitch + n];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  __nv_bfloat16 *row = out + (size_t)k * 3 * pitch;
+  row[n] = hi;
+  row[pitch + n] = hi;
+  row[2 * (size_t)pitch + n] = lo;
+}
+
+int blend_bwd_tc_init(smplb_ctx *c) {
+  if (c->blend_bwd_tc_ok) return 0;
+  RET_IF(c->pitch % 64 != 0, SMPLB_ESTATE, "pitch is not a multiple of the GEMM's k-block");
+  CUDA_TRY(cudaMalloc(&c->d_Dbf, (size_t)KX * 3 * c->pitch * 2));
+  k_build_dbf<<<dim3(cdiv(c->pitch, 256), KX), 256, 0, c->cur>>>(c->pitch, c->d_Dext, (__nv_bfloat16 *)c->d_Dbf);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  TRY(tc_make_map(c->map_dbf, 0, c->d_Dbf, (uint64_t)3 * c->pitch, (uint64_t)KX, (uint64_t)3 * c->pitch * 2, 64, 128));
+  c->blend_bwd_tc_ok = true;
+  return 0;
+}
+
+int launch_blend_bwd_tc(smplb_ctx *c, int B, const void *dp16, float *dx_part, int *ksplit, int *dx_rows) {
+  TRY(blend_bwd_tc_init(c));
+  const int n_mblk = cdiv(B, 128), n_nblk = cdiv(KX, 128);
+  int ks = c->num_sms / (n_mblk * n_nblk);
+  ks = ks < 1 ? 1 : (ks > 16 ? 16 : ks);
+  *ksplit = ks;
+  *dx_rows = n_mblk * 128;
+  return launch_gemm_tc(c, "blend_bwd_tc", B, KX, 3 * c->pitch, dp16, c->map_dbf, dx_part, KX, ks, 1.0f, /*bf16=*/1);
 }

@@ -1,8 +1,9 @@
-// Generic fp16 x fp16 -> fp32 GEMM on tcgen05/TMEM, TMA-fed:
+// Generic fp16 x fp16 (or bf16 x bf16) -> fp32 GEMM on tcgen05/TMEM, TMA-fed:
 //
 //   C[z][m, n] = scale * sum_{k in split z} A[m, k] * B[n, k]        (both operands K-major)
 //
-// Used for the two contractions of the folded keypoint path (k_fold.cu).  Split-precision is
+// Used for the two contractions of the folded keypoint path (k_fold.cu) and, with bf16 operands, for the
+// blend-transpose contraction of the dense backward (d pose_feature = dp . posedirs^T, K = 3 * 20736).  Split-precision is
 // expressed by the caller along K (operands concatenated as hi|hi|lo against hi|lo|hi), so this
 // kernel is a plain GEMM.  Persistent, warp-specialised (TMA producer / MMA issuer / 4 epilogue
 // warps), 128 x 128 output tiles, a 4-deep ring of 64-wide k-blocks, two TMEM accumulator
@@ -27,7 +28,7 @@
 __global__ void __launch_bounds__(G_THREADS, 1)
     k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               const __grid_constant__ CUtensorMap map_c, int n_mblk, int n_nblk, int n_kblk, int ksplit, int c_rows_per_split,
-              float scale) {
+              float scale, uint32_t idesc) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + G_SM_BAR;
@@ -83,7 +84,6 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   } else if (warp == 1) {
     // all 32 lanes run the loop, the elected lane issues (tc_ptx.cuh: elect_one)
     {
-      constexpr uint32_t idesc = umma_idesc_f16(G_BM, G_BN);
       const uint64_t desc0 = umma_desc_sw128(sbase);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -200,8 +200,9 @@ int tc_make_map(void *map, int is_f32, const void *ptr, uint64_t inner, uint64_t
 
 // C [ksplit][c_rows_per_split][ldc] fp32 = scale * A16 [M][K] * B16 [N][K]^T.  K is a multiple of
 // 64; N is padded by the tensor map's zero fill; c_rows_per_split is M rounded up to 128.
+// bf16 != 0: both operands are bfloat16 (same bytes per element, same rate; the TMA descriptor only moves bytes).
 int launch_gemm_tc(smplb_ctx *c, const char *name, int M, int N, int K, const void *A16, const void *map_b, float *C,
-                   int ldc, int ksplit, float scale) {
+                   int ldc, int ksplit, float scale, int bf16) {
   if (!(c->attr_done & 2u)) {
     CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SM_TOTAL));
     c->attr_done |= 2u;
@@ -215,7 +216,9 @@ int launch_gemm_tc(smplb_ctx *c, const char *name, int M, int N, int K, const vo
   TRY(tc_make_map(&map_c, 1, (void *)C, (uint64_t)ldc, c_rows, (uint64_t)ldc * 4, 32, 32));
   int total = n_mblk * n_nblk * ksplit;
   int grid = total < c->num_sms ? total : c->num_sms;
+  // instruction descriptor (tc_ptx.cuh); a_format / b_format = 1 (bits 7, 10) selects bf16 operands
+  const uint32_t idesc = umma_idesc_f16(G_BM, G_BN) | (bf16 ? ((1u << 7) | (1u << 10)) : 0u);
   LAUNCH(c, name, grid, G_THREADS, G_SM_TOTAL, k_gemm_tc, map_a, *(const CUtensorMap *)map_b, map_c, n_mblk, n_nblk, n_kblk,
-         ksplit, rows_per, scale);
+         ksplit, rows_per, scale, idesc);
   return 0;
 }

@@ -7,6 +7,8 @@
 //   batch_orth_proj_idrot    src/tf_smpl/projection.py:23-33
 //   reproject_vertices       src/tf_smpl/projection.py:45-56
 //   kp_reprojection_loss     src/ops.py:35-47 (per-body partial sums)
+#include <cuda_bf16.h>
+
 #include "smplb_internal.h"
 
 #define FULL 0xffffffffu
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(SB_THREADS)
                const float *__restrict__ W, const float *__restrict__ A, const float *__restrict__ v_posed,
                const float *__restrict__ d_verts, const float *__restrict__ d_joints, const int *__restrict__ voff,
                const int *__restrict__ vk, const float *__restrict__ vval, float *__restrict__ dp,
-               float *__restrict__ dA_part) {
+               float *__restrict__ dA_part, __nv_bfloat16 *__restrict__ dp16) {
   // V counts the vertices this launch walks: all of them, or (vmap != NULL) only the rows of
   // joint_regressor with a non-zero entry -- when no d_verts is given every other vertex has
   // g == 0 and contributes nothing.  W, voff are indexed by the walked index, v_posed /
@@ -237,10 +239,29 @@ __global__ void __launch_bounds__(SB_THREADS)
         p1 = pp[Vp_vp];
         p2 = pp[2 * (size_t)Vp_vp];
         one = 1.0f;
-        float *o = dp + b * (3 * (size_t)Vp_dp) + v;
-        o[0] = TR[0] * g0 + TR[3] * g1 + TR[6] * g2;   // dp = T_R^T g
-        o[Vp_dp] = TR[1] * g0 + TR[4] * g1 + TR[7] * g2;
-        o[2 * (size_t)Vp_dp] = TR[2] * g0 + TR[5] * g1 + TR[8] * g2;
+        const float d0 = TR[0] * g0 + TR[3] * g1 + TR[6] * g2;   // dp = T_R^T g
+        const float d1 = TR[1] * g0 + TR[4] * g1 + TR[7] * g2;
+        const float d2 = TR[2] * g0 + TR[5] * g1 + TR[8] * g2;
+        if (dp16) {
+          // operand row of the tcgen05 blend-transpose GEMM: [hi | lo | hi], each 3 * Vp_dp wide, bf16 (16
+          // significand bits between hi and lo, fp32's exponent range: no scaling needed)
+          const size_t P3 = 3 * (size_t)Vp_dp;
+          __nv_bfloat16 *o = dp16 + b * (3 * P3) + v;
+          const float dd[3] = {d0, d1, d2};
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(dd[cc]);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(dd[cc] - __bfloat162float(hi));
+            o[cc * (size_t)Vp_dp] = hi;
+            o[P3 + cc * (size_t)Vp_dp] = lo;
+            o[2 * P3 + cc * (size_t)Vp_dp] = hi;
+          }
+        } else {
+          float *o = dp + b * (3 * (size_t)Vp_dp) + v;
+          o[0] = d0;
+          o[Vp_dp] = d1;
+          o[2 * (size_t)Vp_dp] = d2;
+        }
       }
       float4 *dst = reinterpret_cast<float4 *>(S.GP[vl][sl]);
       dst[0] = make_float4(g0, g1, g2, 0.f);
@@ -362,7 +383,7 @@ int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, con
 }
 
 int launch_skin_bwd(smplb_ctx *c, int B, const float *A, const float *v_posed, const float *d_verts,
-                    const float *d_joints, float *dp, float *dA_part, int mode) {
+                    const float *d_joints, float *dp, float *dA_part, int mode, void *dp16) {
   // mode 0: every vertex.  mode 1: active vertices, v_posed gathered from the full tensor.
   // mode 2: active vertices, v_posed is the compact v_posed_act (no gather).
   if (!(c->attr_done & 1u)) {
@@ -373,15 +394,15 @@ int launch_skin_bwd(smplb_ctx *c, int B, const float *A, const float *v_posed, c
   if (mode == 2) {
     LAUNCH(c, "skin_bwd_active", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->n_act, c->n_act, c->K, c->Vpa,
            c->Vpa, (const int *)nullptr, c->d_act_W, A, v_posed, (const float *)nullptr, d_joints, c->d_acsr_off,
-           c->d_acsr_k, c->d_acsr_val, dp, dA_part);
+           c->d_acsr_k, c->d_acsr_val, dp, dA_part, (__nv_bfloat16 *)nullptr);
   } else if (mode == 1) {
     LAUNCH(c, "skin_bwd_active_gather", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->n_act, c->V, c->K, c->Vp,
            c->Vpa, c->d_act_idx, c->d_act_W, A, v_posed, (const float *)nullptr, d_joints, c->d_acsr_off,
-           c->d_acsr_k, c->d_acsr_val, dp, dA_part);
+           c->d_acsr_k, c->d_acsr_val, dp, dA_part, (__nv_bfloat16 *)nullptr);
   } else {
     LAUNCH(c, "skin_bwd", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->V, c->V, c->K, c->Vp, c->Vp,
            (const int *)nullptr, c->d_W, A, v_posed, d_verts, d_joints, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val, dp,
-           dA_part);
+           dA_part, (__nv_bfloat16 *)dp16);
   }
   return 0;
 }

@@ -182,7 +182,7 @@ static void free_ws(smplb_ctx *c) {
                    (void **)&c->ws_dkp, (void **)&c->ws_djoints, (void **)&c->ws_dverts, (void **)&c->ws_dp, (void **)&c->ws_dA,
                    (void **)&c->ws_dx, (void **)&c->ws_part, (void **)&c->ws_cnt, (void **)&c->ws_theta,
                    (void **)&c->ws_beta, (void **)&c->ws_gp, (void **)&c->ws_x16, (void **)&c->ws_dp_act, (void **)&c->ws_A16, (void **)&c->ws_vposed_act, (void **)&c->ws_verts_act, (void **)&c->ws_U, (void **)&c->ws_du16,
-                   (void **)&c->ws_rowscale, (void **)&c->ws_x16b};
+                   (void **)&c->ws_rowscale, (void **)&c->ws_x16b, (void **)&c->ws_dp16};
   for (void **p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -225,7 +225,7 @@ static int ensure_ws(smplb_ctx *c, int B) {
   WS_ALLOC(ws_dkp, nb * c->K * 2);
   WS_ALLOC(ws_djoints, nb * c->K * 3);
   WS_ALLOC(ws_dA, (size_t)VSPLIT * nb * NJ * 12);
-  WS_ALLOC(ws_dx, std::max((size_t)c->ksplit * nb, (size_t)2 * (nb + 128)) * KX);
+  WS_ALLOC(ws_dx, (size_t)c->ksplit * (nb + 128) * KX);   // split-K partials: up to 16 x (B rounded up to 128) rows
   WS_ALLOC(ws_part, nb);
   WS_ALLOC(ws_cnt, nb);
   WS_ALLOC(ws_theta, nb * 72);
@@ -435,7 +435,7 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
                   c->d_Jdirs,    c->d_kcsr_off,  c->d_kcsr_idx, c->d_kcsr_val, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val,
                   c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_W16,      c->d_G,        c->d_cc,       c->d_G16,      c->d_Gt16,     c->d_Dt16_act, c->d_W16_act,  c->d_kcsr_slot, c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
                   c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part, c->ws_grid,  c->ws_vdist,
-                  c->x_mbox,     c->x_status};
+                  c->x_mbox,     c->x_status,    c->d_Dbf};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 16; ++i) {
@@ -568,6 +568,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
   RET_IF(!c || !key, SMPLB_EINVAL, "null argument");
   if (!strcmp(key, "blend_tc")) {
     c->use_tc = value;
+    return 0;
+  }
+  if (!strcmp(key, "blend_bwd_tc")) {
+    c->use_blend_bwd_tc = value;
     return 0;
   }
   if (!strcmp(key, "comm_backend")) {
@@ -841,13 +845,21 @@ static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const fl
   // No upstream gradient on verts: only vertices the keypoint regressor touches carry a
   // gradient, so walk just those (exact: the skipped terms are zeros).
   bool compact = (d_verts == nullptr) && c->use_compact && c->n_act < c->V;
-  float *dp;
+  float *dp = nullptr;
+  const bool bwd_tc = !compact && c->tc_ok && c->use_blend_bwd_tc;
   if (compact) {
     TRY(ensure_buf(c, &c->ws_dp_act, (size_t)c->ws_batch * c->pitch_act, true));
     dp = c->ws_dp_act;
-  } else {
+  } else if (!bwd_tc) {
     TRY(ensure_buf(c, &c->ws_dp, (size_t)c->ws_batch * c->pitch, true));
     dp = c->ws_dp;
+  }
+  if (bwd_tc) {
+    // k_skin_bwd writes the bf16 operand rows of the tcgen05 blend-transpose GEMM instead of fp32 dp
+    if (!c->ws_dp16) {
+      CUDA_TRY(cudaMalloc(&c->ws_dp16, (size_t)c->ws_batch * 3 * c->pitch * 2));
+      CUDA_TRY(cudaMemsetAsync(c->ws_dp16, 0, (size_t)c->ws_batch * 3 * c->pitch * 2, c->cur));   // padding columns stay 0
+    }
   }
   if ((!compact || !c->saved_compact) && !c->saved_full) {
     // the forward skipped the 6890-vertex tensors (no verts requested): rebuild v_posed now
@@ -858,11 +870,13 @@ static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const fl
   if (compact && c->saved_compact)
     TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed_act, nullptr, d_joints, dp, c->ws_dA, 2));
   else
-    TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed, d_verts, d_joints, dp, c->ws_dA, compact ? 1 : 0));
+    TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed, d_verts, d_joints, dp, c->ws_dA, compact ? 1 : 0, bwd_tc ? c->ws_dp16 : nullptr));
   int ks = compact ? 4 : c->ksplit;   // the compact contraction is 11x shorter: fewer split-K partials
-  TRY(launch_blend_bwd(c, B, dp, c->ws_dx, compact, ks));
-  TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, VSPLIT, c->ws_dx, ks, B, nullptr, d_Rs, d_beta,
-                      d_theta));
+  int dx_rows = B;
+  if (bwd_tc) TRY(launch_blend_bwd_tc(c, B, c->ws_dp16, c->ws_dx, &ks, &dx_rows));
+  else TRY(launch_blend_bwd(c, B, dp, c->ws_dx, compact, ks));
+  TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, VSPLIT, c->ws_dx, ks, dx_rows, nullptr, d_Rs,
+                      d_beta, d_theta));
   return 0;
 }
 

@@ -161,6 +161,11 @@ struct smplb_ctx {
   float *ws_dsil = nullptr;    // [B][V][2]
   int *ws_silcnt = nullptr;    // [B][V][2] integer sign sums of the pixel->vertex term
   float *ws_dp = nullptr;      // [B][pitch]
+  void *ws_dp16 = nullptr;     // [B][3 * pitch] bf16: hi | lo | hi (operand of the tcgen05 blend-transpose GEMM)
+  void *d_Dbf = nullptr;       // [KX][3 * pitch] bf16: Dext hi | hi | lo
+  alignas(64) unsigned char map_dbf[128];
+  bool blend_bwd_tc_ok = false;
+  int use_blend_bwd_tc = 1;    // smplb_debug_set("blend_bwd_tc", 0): FP32 CUDA-core GEMM (cross-check)
   float *ws_dA = nullptr;      // [VSPLIT][B][288]
   float *ws_dx = nullptr;      // [ksplit][B][KX]
   float *ws_part = nullptr;    // per-body / per-block float partials
@@ -281,6 +286,10 @@ int launch_lrotmin(smplb_ctx *c, int B, const float *theta, float *out);
 // k_blend.cu
 int launch_blend_fwd(smplb_ctx *c, int B, const float *x, float *v_posed);
 int launch_blend_bwd(smplb_ctx *c, int B, const float *dp, float *dx_part, bool compact, int ksplit);
+// tcgen05 version of the dense one: dp16 = [B][3 * pitch] bf16 (hi | lo | hi, written by k_skin_bwd) against
+// Dext as bf16 (hi | hi | lo); returns the split-K factor and row pitch of dx_part through the pointers
+int blend_bwd_tc_init(smplb_ctx *c);
+int launch_blend_bwd_tc(smplb_ctx *c, int B, const void *dp16, float *dx_part, int *ksplit, int *dx_rows);
 // k_blend_tc.cu
 int blend_tc_init(smplb_ctx *c);
 int launch_blend_fwd_tc(smplb_ctx *c, int B, const void *x16, float *v_posed, bool act);
@@ -299,7 +308,7 @@ int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long l
 int tc_make_map(void *map, int is_f32, const void *ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                 uint32_t box_inner, uint32_t box_outer, int swizzle = 1);
 int launch_gemm_tc(smplb_ctx *c, const char *name, int M, int N, int K, const void *A16, const void *map_b, float *C,
-                   int ldc, int ksplit, float scale);
+                   int ldc, int ksplit, float scale, int bf16 = 0);
 // k_skin_tc.cu
 int skin_tc_init(smplb_ctx *c);
 int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts, bool act);
@@ -318,7 +327,7 @@ int launch_skin_fwd(smplb_ctx *c, int B, const float *A, const float *v_posed, f
 int launch_joints(smplb_ctx *c, int B, const float *verts, const float *cam, const float *kp_gt, float *joints,
                   float *kp_pred, float *dkp, float *part, int *cnt, bool act);
 int launch_skin_bwd(smplb_ctx *c, int B, const float *A, const float *v_posed, const float *d_verts,
-                    const float *d_joints, float *dp, float *dA_part, int mode);
+                    const float *d_joints, float *dp, float *dA_part, int mode, void *dp16 = nullptr);
 int launch_proj(smplb_ctx *c, int B, int N, const float *X, const float *cam, int pixel, float im_w, float im_h,
                 float *out);
 int launch_proj_bwd(smplb_ctx *c, int B, int N, const float *X, const float *cam, const float *d_out, int pixel,

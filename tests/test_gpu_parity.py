@@ -354,6 +354,38 @@ def test_compact_backward_equals_dense_walk(smpl_full):
         assert rel_err(a[k], b[k]) < 2e-6, k
 
 
+def test_tcgen05_blend_transpose_gemm_matches_fp32_gemm(smpl_full, full_model):
+    """Dense backward (an upstream gradient on every vertex, src/trainer.py:502 with the mesh loss on):
+    d pose_feature / d beta = dp . [posedirs | shapedirs]^T over K = 20670 as a bf16 split-precision tcgen05 GEMM
+    (dp and the basis as hi + lo) against the FP32 CUDA-core GEMM of the same contraction and the fp64 oracle.
+    Batch sizes straddle the 128-row M tile; the gradients span 8 orders of magnitude between samples."""
+    ctx = smpl_full.ctx
+    o = onp.SMPL(full_model, dtype=np.float64)
+    V = full_model["v_template"].shape[0]
+    for B in (3, 130):
+        inp = synthetic.make_inputs(B, seed=900 + B)
+        rng = np.random.default_rng(B)
+        d_verts = (rng.standard_normal((B, V, 3)) * 10.0 ** rng.uniform(-6, 2, size=(B, 1, 1))).astype(np.float32)
+        d_joints = rng.standard_normal((B, 19, 3)).astype(np.float32)
+        smpl_full(inp["beta"], inp["theta"], get_skin=True)
+        g1 = smpl_full.backward(d_verts=d_verts, d_joints=d_joints)
+        try:
+            ctx.debug_set("blend_bwd_tc", 0)
+            smpl_full(inp["beta"], inp["theta"], get_skin=True)
+            g0 = smpl_full.backward(d_verts=d_verts, d_joints=d_joints)
+        finally:
+            ctx.debug_set("blend_bwd_tc", 1)
+        n = min(B, 6)
+        b64 = {k: v[:n].astype(np.float64) for k, v in inp.items()}
+        db, dth = onp.smpl_backward(o, b64["beta"], b64["theta"], d_verts[:n].astype(np.float64), d_joints[:n].astype(np.float64), None)
+        for a, b, w in zip(g1, g0, (db, dth)):
+            # per sample: the scales differ by orders of magnitude between samples
+            for i in range(B):
+                assert rel_err(a[i], b[i]) < 2e-5, (B, i)
+            for i in range(n):
+                assert rel_err(a[i], w[i]) < TOL, (B, i)
+
+
 def test_tcgen05_skinning_matches_fp32_kernel(smpl_full):
     """T = W.A on the tensor cores (fp16 operands split into hi/lo so the product keeps
     fp32-grade accuracy) against the FP32 CUDA-core skinning kernel."""
