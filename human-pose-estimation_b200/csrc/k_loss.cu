@@ -148,15 +148,26 @@ __device__ __forceinline__ float d2_expand(float ax, float ay, float a2, float b
 #define GRID_G 64
 #define GRID_NC (GRID_G * GRID_G)
 #define GP_STRIDE 8   // x0, y0, x1, y1, inv_h, h, max |p|^2, -
+// Most of a far query's ring walk crosses EMPTY cells (a vertex 50 px outside the silhouette walks ~17 rings,
+// ~600 cell ranges, before it meets the first pixel).  Per (image, set) the build kernel therefore also writes
+//   occ [y]  : bit x set if cell (x, y) holds a point          (64 x 64 cells = one 64-bit word per row)
+//   occT[x]  : the same by column
+//   cdist[c] : Chebyshev distance in cells from cell c to the nearest non-empty cell
+// and the walk (a) starts at ring cdist[c] -- every ring before it is empty -- and (b) visits only the
+// non-empty cells of a ring: two row masks and two column masks per ring.  The set of points compared
+// is unchanged, so the result stays bit-identical to the full scan.
+#define GRID_AUX_BYTES (2 * GRID_G * 8 + GRID_NC)   // occ, occT, cdist
 
 // One CTA per (set, image): set 0 = projected vertices, set 1 = silhouette pixels.
 __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restrict__ pts, const int *__restrict__ offsets,
                                                     const float *__restrict__ sil_pred, float *__restrict__ gparam,
                                                     int *__restrict__ gstart, float4 *__restrict__ sortedB,
-                                                    float4 *__restrict__ sortedA) {
+                                                    float4 *__restrict__ sortedA, unsigned char *__restrict__ gaux) {
   __shared__ float red[4][256];
   __shared__ int hist[GRID_NC];
   __shared__ int scan[256];
+  __shared__ unsigned long long s_occ[GRID_G];
+  __shared__ unsigned char s_hx[GRID_NC];
   int sel = blockIdx.x, i = blockIdx.y, t = threadIdx.x;
   int p0 = offsets[i];
   int n = sel == 0 ? V : offsets[i + 1] - p0;
@@ -199,6 +210,46 @@ __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restri
     int cx = min(GRID_G - 1, max(0, (int)((x - x0) * inv_h)));
     int cy = min(GRID_G - 1, max(0, (int)((y - y0) * inv_h)));
     atomicAdd(&hist[cy * GRID_G + cx], 1);
+  }
+  __syncthreads();
+  // occupancy masks and the cell distance transform (see GRID_AUX_BYTES)
+  {
+    unsigned char *aux = gaux + ((size_t)i * 2 + sel) * GRID_AUX_BYTES;
+    unsigned long long *occ = reinterpret_cast<unsigned long long *>(aux), *occT = occ + GRID_G;
+    unsigned char *cdist = aux + 2 * GRID_G * 8;
+    if (t < GRID_G) {
+      unsigned long long m = 0;
+      for (int x = 0; x < GRID_G; ++x) m |= (unsigned long long)(hist[t * GRID_G + x] > 0) << x;
+      s_occ[t] = m;
+      occ[t] = m;
+    } else if (t < 2 * GRID_G) {
+      const int x = t - GRID_G;
+      unsigned long long m = 0;
+      for (int y = 0; y < GRID_G; ++y) m |= (unsigned long long)(hist[y * GRID_G + x] > 0) << y;
+      occT[x] = m;
+    }
+    __syncthreads();
+    // hx[y][x]: distance along the row to the nearest non-empty cell (GRID_G if the row is empty)
+    for (int k = t; k < GRID_NC; k += 256) {
+      const int y = k / GRID_G, x = k % GRID_G;
+      const unsigned long long m = s_occ[y];
+      const unsigned long long left = m & (~0ull >> (63 - x)), right = m >> x;
+      int d = GRID_G;
+      if (left) d = x - (63 - __clzll((long long)left));
+      if (right) d = min(d, __ffsll((long long)right) - 1);
+      s_hx[k] = (unsigned char)d;
+    }
+    __syncthreads();
+    // cdist[y][x] = min over rows y' of max(|y - y'|, hx[y'][x]), walked outwards with early exit
+    for (int k = t; k < GRID_NC; k += 256) {
+      const int y = k / GRID_G, x = k % GRID_G;
+      int best = s_hx[k];
+      for (int dy = 1; dy < best; ++dy) {
+        if (y - dy >= 0) best = min(best, max(dy, (int)s_hx[(y - dy) * GRID_G + x]));
+        if (y + dy < GRID_G) best = min(best, max(dy, (int)s_hx[(y + dy) * GRID_G + x]));
+      }
+      cdist[k] = (unsigned char)min(best, GRID_G);
+    }
   }
   __syncthreads();
   // exclusive scan of the cell counts: GRID_NC / 256 cells per thread + block scan
@@ -248,7 +299,8 @@ __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restri
 template <bool QUERY_IS_A>
 __device__ __forceinline__ void grid_search(float qx, float qy, float q2, const float4 *__restrict__ sorted,
                                             const int *__restrict__ gs, const float *__restrict__ gp, float margin,
-                                            float &best, int &bi) {
+                                            const unsigned long long *s_occ, const unsigned long long *s_occT,
+                                            const unsigned char *s_cdist, float &best, int &bi) {
   float x0 = gp[0], y0 = gp[1], x1 = gp[2], y1 = gp[3], inv_h = gp[4], h = gp[5];
   float qcx = fminf(fmaxf(qx, x0), x1), qcy = fminf(fmaxf(qy, y0), y1);   // projection onto the bounding box
   float outside2 = (qx - qcx) * (qx - qcx) + (qy - qcy) * (qy - qcy);
@@ -267,11 +319,34 @@ __device__ __forceinline__ void grid_search(float qx, float qy, float q2, const 
       }
     }
   };
-  int rmax = max(max(cx, GRID_G - 1 - cx), max(cy, GRID_G - 1 - cy));
-  // Rings 0 and 1 together: ring 0 alone can never satisfy the stopping rule (0 * h), and the 3 x 3
-  // block is three contiguous cell ranges whose six range bounds load independently (the ring
-  // walk below needs five ranges and a dependent pair of loads for each).
-  {
+  // the non-empty cells of row y between columns xa..xb, as runs of consecutive cells (contiguous point ranges)
+  auto scan_row = [&](int y, int xa, int xb) {
+    unsigned long long m = s_occ[y] & ((~0ull >> (63 - xb)) & (~0ull << xa));
+    while (m) {
+      const int xs = __ffsll((long long)m) - 1;
+      const unsigned long long run = ~(m >> xs);                          // first zero above xs ends the run
+      const int len = run ? __ffsll((long long)run) - 1 : 64 - xs;
+      scan(gs[y * GRID_G + xs], gs[y * GRID_G + xs + len]);
+      m = (xs + len >= 64) ? 0ull : (m & (~0ull << (xs + len)));
+    }
+  };
+  // the non-empty cells of column x between rows ya..yb
+  auto scan_col = [&](int x, int ya, int yb) {
+    if (ya > yb) return;
+    unsigned long long m = s_occT[x] & ((~0ull >> (63 - yb)) & (~0ull << ya));
+    while (m) {
+      const int y = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      scan(gs[y * GRID_G + x], gs[y * GRID_G + x + 1]);
+    }
+  };
+  const int rmax = max(max(cx, GRID_G - 1 - cx), max(cy, GRID_G - 1 - cy));
+  const int r0 = s_cdist[cy * GRID_G + cx];      // every ring before r0 is empty
+  if (r0 > rmax) return;                          // an empty set
+  int r = r0;
+  if (r0 <= 1) {
+    // Rings 0 and 1 together: ring 0 alone can never satisfy the stopping rule (0 * h), and the 3 x 3
+    // block is three contiguous cell ranges whose six range bounds load independently.
     int xa = max(cx - 1, 0), xb = min(cx + 1, GRID_G - 1);
     int ya = max(cy - 1, 0), yb = min(cy + 1, GRID_G - 1);
     int lo[3], hi[3];
@@ -283,33 +358,22 @@ __device__ __forceinline__ void grid_search(float qx, float qy, float q2, const 
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) scan(lo[j], hi[j]);
+    r = 1;
+  } else {
+    --r;   // the loop below visits ring r + 1 first
   }
-  for (int r = 1; r <= rmax; ++r) {
-    if (r >= 2) {
-      int ylo = cy - r, yhi = cy + r;
-      for (int y = max(ylo, 0); y <= min(yhi, GRID_G - 1); ++y) {
-        bool full_row = (y == ylo) || (y == yhi);
-        int xa = max(cx - r, 0), xb = min(cx + r, GRID_G - 1);
-        // full rows of the ring are one contiguous cell range; inner rows contribute their two end cells
-        int nseg = full_row ? 1 : 2;
-        for (int sgi = 0; sgi < nseg; ++sgi) {
-          int c_lo, c_hi;
-          if (full_row) {
-            c_lo = y * GRID_G + xa;
-            c_hi = y * GRID_G + xb;
-          } else {
-            int x = sgi == 0 ? cx - r : cx + r;
-            if (x < 0 || x > GRID_G - 1) continue;
-            c_lo = c_hi = y * GRID_G + x;
-          }
-          scan(gs[c_lo], gs[c_hi + 1]);
-        }
-      }
-    }
+  for (;;) {
     // every unvisited cell is at Chebyshev ring >= r + 1: its points are >= r * h from the
     // projected query (0.9999 covers the rounding of the cell assignment)
-    float rh = (float)r * h;
+    const float rh = (float)r * h;
     if (rh * rh * 0.9999f + outside2 > best + margin) break;
+    if (++r > rmax) break;
+    const int xa = max(cx - r, 0), xb = min(cx + r, GRID_G - 1);
+    if (cy - r >= 0) scan_row(cy - r, xa, xb);
+    if (cy + r < GRID_G) scan_row(cy + r, xa, xb);
+    const int ya = max(cy - r + 1, 0), yb = min(cy + r - 1, GRID_G - 1);
+    if (cx - r >= 0) scan_col(cx - r, ya, yb);
+    if (cx + r < GRID_G) scan_col(cx + r, ya, yb);
   }
 }
 
@@ -322,10 +386,16 @@ __global__ void __launch_bounds__(MT) k_mesh_ab(int V, const float *__restrict__
                                                 const float *__restrict__ sil_pred, float *__restrict__ part,
                                                 int *__restrict__ cnt, int *__restrict__ ind_ab,
                                                 const float *__restrict__ gparam, const int *__restrict__ gstart,
-                                                const float4 *__restrict__ sortedB) {
+                                                const float4 *__restrict__ sortedB, const unsigned char *__restrict__ gaux) {
   __shared__ float4 s4[GRID ? 1 : MTILE];   // (x, y, |.|^2, -) of the staged vertices: one broadcast LDS.128 per pair
   __shared__ float red[MT];
+  __shared__ __align__(16) unsigned char s_aux[GRID ? GRID_AUX_BYTES : 16];
   int i = blockIdx.y;
+  if (GRID) {   // occupancy masks + cell distances of this image's VERTEX grid
+    const uint4 *src = reinterpret_cast<const uint4 *>(gaux + ((size_t)i * 2 + 0) * GRID_AUX_BYTES);
+    for (int k = threadIdx.x; k < GRID_AUX_BYTES / 16; k += MT) reinterpret_cast<uint4 *>(s_aux)[k] = src[k];
+    __syncthreads();
+  }
   int p0 = offsets[i], np = offsets[i + 1] - p0;
   const float *Bv = sil_pred + (size_t)i * V * 2;
   float total = 0.f;
@@ -344,7 +414,10 @@ __global__ void __launch_bounds__(MT) k_mesh_ab(int V, const float *__restrict__
     if (GRID) {
       const float *gpB = gparam + ((size_t)i * 2 + 0) * GP_STRIDE, *gpA = gparam + ((size_t)i * 2 + 1) * GP_STRIDE;
       float margin = 32.0f * 5.9604645e-8f * fmaxf(gpA[6], gpB[6]);
-      if (ok) grid_search<true>(ax, ay, a2, sortedB + (size_t)i * V, gstart + ((size_t)i * 2 + 0) * (GRID_NC + 1), gpB, margin, best, bi);
+      if (ok)
+        grid_search<true>(ax, ay, a2, sortedB + (size_t)i * V, gstart + ((size_t)i * 2 + 0) * (GRID_NC + 1), gpB, margin,
+                          reinterpret_cast<const unsigned long long *>(s_aux),
+                          reinterpret_cast<const unsigned long long *>(s_aux) + GRID_G, s_aux + 2 * GRID_G * 8, best, bi);
     } else
     for (int v0 = 0; v0 < V; v0 += MTILE) {
       int nv = min(MTILE, V - v0);
@@ -388,9 +461,16 @@ __global__ void __launch_bounds__(MT) k_mesh_ba(int V, const float *__restrict__
                                                 const float *__restrict__ sil_pred, float *__restrict__ vdist,
                                                 float *__restrict__ d_sil, int *__restrict__ ind_ba,
                                                 const float *__restrict__ gparam, const int *__restrict__ gstart,
-                                                const float4 *__restrict__ sortedA, const float4 *__restrict__ sortedB) {
+                                                const float4 *__restrict__ sortedA, const float4 *__restrict__ sortedB,
+                                                const unsigned char *__restrict__ gaux) {
   __shared__ float4 s4[GRID ? 1 : MTILE];
+  __shared__ __align__(16) unsigned char s_aux[GRID ? GRID_AUX_BYTES : 16];
   int i = blockIdx.y;
+  if (GRID) {   // occupancy masks + cell distances of this image's PIXEL grid
+    const uint4 *src = reinterpret_cast<const uint4 *>(gaux + ((size_t)i * 2 + 1) * GRID_AUX_BYTES);
+    for (int k = threadIdx.x; k < GRID_AUX_BYTES / 16; k += MT) reinterpret_cast<uint4 *>(s_aux)[k] = src[k];
+    __syncthreads();
+  }
   int p0 = offsets[i], np = offsets[i + 1] - p0;
   int slot = blockIdx.x * MT + threadIdx.x;
   bool ok = slot < V;
@@ -412,7 +492,9 @@ __global__ void __launch_bounds__(MT) k_mesh_ba(int V, const float *__restrict__
     if (ok && np > 0) {
       const float *gpB = gparam + ((size_t)i * 2 + 0) * GP_STRIDE, *gpA = gparam + ((size_t)i * 2 + 1) * GP_STRIDE;
       float margin = 32.0f * 5.9604645e-8f * fmaxf(gpA[6], gpB[6]);
-      grid_search<false>(bx, by, b2, sortedA + p0, gstart + ((size_t)i * 2 + 1) * (GRID_NC + 1), gpA, margin, best, ai);
+      grid_search<false>(bx, by, b2, sortedA + p0, gstart + ((size_t)i * 2 + 1) * (GRID_NC + 1), gpA, margin,
+                         reinterpret_cast<const unsigned long long *>(s_aux),
+                         reinterpret_cast<const unsigned long long *>(s_aux) + GRID_G, s_aux + 2 * GRID_G * 8, best, ai);
     }
   } else
   for (int a0 = 0; a0 < np; a0 += MTILE) {
@@ -604,7 +686,8 @@ int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *of
   if (d_sil_pred) CUDA_TRY(cudaMemsetAsync(cnt_scratch, 0, (size_t)B * V * 2 * sizeof(int), c->cur));
   if (c->use_mesh_grid) {
     // grid workspace: per image and set 8 floats + GRID_NC + 1 ints, sorted copies of both point sets
-    size_t need = (size_t)B * 2 * GP_STRIDE * 4 + (size_t)B * 2 * (GRID_NC + 1) * 4 + ((size_t)B * V + (size_t)P + 16) * 16 + 256;
+    size_t need = (size_t)B * 2 * GP_STRIDE * 4 + (size_t)B * 2 * (GRID_NC + 1) * 4 + ((size_t)B * V + (size_t)P + 16) * 16 + 256 +
+                  (size_t)B * 2 * GRID_AUX_BYTES + 64;
     if (need > c->ws_grid_cap) {
       CUDA_TRY(cudaStreamSynchronize(c->stream));
       if (c->ws_grid) CUDA_TRY(cudaFree(c->ws_grid));
@@ -617,18 +700,20 @@ int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *of
     float4 *sortedA = sortedB + (size_t)B * V;
     float *gparam = (float *)(sortedA + P + 16);
     int *gstart = (int *)(gparam + (size_t)B * 2 * GP_STRIDE);
-    LAUNCH(c, "mesh_grid_build", dim3(2, B), 256, 0, k_grid_build, V, pts, offsets, sil_pred, gparam, gstart, sortedB, sortedA);
+    unsigned char *gaux = (unsigned char *)(((uintptr_t)(gstart + (size_t)B * 2 * (GRID_NC + 1)) + 63) & ~(uintptr_t)63);
+    LAUNCH(c, "mesh_grid_build", dim3(2, B), 256, 0, k_grid_build, V, pts, offsets, sil_pred, gparam, gstart, sortedB, sortedA,
+           gaux);
     LAUNCH(c, "mesh_nn_pixel_to_vertex_grid", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab<true>, V, pts, offsets, sil_pred,
-           part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, gparam, gstart, sortedB);
+           part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, gparam, gstart, sortedB, gaux);
     LAUNCH(c, "mesh_nn_vertex_to_pixel_grid", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba<true>, V, pts, offsets, sil_pred,
-           c->ws_vdist, d_sil_pred, ind_ba, gparam, gstart, sortedA, sortedB);
+           c->ws_vdist, d_sil_pred, ind_ba, gparam, gstart, sortedA, sortedB, gaux);
   } else {
     LAUNCH(c, "mesh_nn_pixel_to_vertex", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab<false>, V, pts, offsets, sil_pred,
            part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, (const float *)nullptr, (const int *)nullptr,
-           (const float4 *)nullptr);
+           (const float4 *)nullptr, (const unsigned char *)nullptr);
     LAUNCH(c, "mesh_nn_vertex_to_pixel", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba<false>, V, pts, offsets, sil_pred,
            c->ws_vdist, d_sil_pred, ind_ba, (const float *)nullptr, (const int *)nullptr, (const float4 *)nullptr,
-           (const float4 *)nullptr);
+           (const float4 *)nullptr, (const unsigned char *)nullptr);
   }
   LAUNCH(c, "mesh_rowsum", B, 256, 0, k_mesh_rowsum, V, c->ws_vdist, part_ba);
   float denom = (float)(3 + V);
