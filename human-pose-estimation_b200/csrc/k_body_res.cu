@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (kb == 3 && k == 3) continue;      // K = 240: the last 16 columns are zero padding
-                tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_p, (kb | k) != 0);
+                if (FB_ABLATE != 7) tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_p, (kb | k) != 0);
               }
             }
             __syncwarp();
@@ -338,11 +338,13 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           const uint64_t a_desc = umma_desc_add(desc_a0, stage * C::A_BYTES);
           if (elect_one()) {
             // (W window, A window) pairs of the table in k_skin_tc.cu; an A window is 32 B = 2 descriptor units
-            tc_mma_f16_ts_pair(d_tmem, w_tmem + 0, a_desc + 0, idesc_t, 0);
-            tc_mma_f16_ts_pair(d_tmem, w_tmem + 8, a_desc + 2, idesc_t, 1);
-            tc_mma_f16_ts_pair(d_tmem, w_tmem + 0, a_desc + 4, idesc_t, 1);
-            tc_mma_f16_ts_pair(d_tmem, w_tmem + 16, a_desc + 0, idesc_t, 1);
-            tc_mma_f16_ts_pair(d_tmem, w_tmem + 24, a_desc + 2, idesc_t, 1);
+            if (FB_ABLATE != 7) {   // (7: tuning build without MMAs -- hand-shakes, TMA traffic and stores only)
+              tc_mma_f16_ts_pair(d_tmem, w_tmem + 0, a_desc + 0, idesc_t, 0);
+              tc_mma_f16_ts_pair(d_tmem, w_tmem + 8, a_desc + 2, idesc_t, 1);
+              tc_mma_f16_ts_pair(d_tmem, w_tmem + 0, a_desc + 4, idesc_t, 1);
+              tc_mma_f16_ts_pair(d_tmem, w_tmem + 16, a_desc + 0, idesc_t, 1);
+              tc_mma_f16_ts_pair(d_tmem, w_tmem + 24, a_desc + 2, idesc_t, 1);
+            }
             tc_commit_pair(empty_a + 8 * stage);
             tc_commit_pair(t_full + 8 * tb);
           }
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
         tc_fence_after();
         const int s_loc = st * C::ST + part * HS;   // first sample (within the super-tile) of this warp
         uint32_t r[12 * HS], pc[3][HS];
-#if FB_ABLATE == 6
+#if FB_ABLATE == 6 || FB_ABLATE == 7
         // tuning build: no TMEM loads (hand-shakes and stores only)
 #pragma unroll
         for (int i = 0; i < 12 * HS; ++i) r[i] = tcol0 + i;
