@@ -296,16 +296,16 @@ def single_gpu_configs(smpl, model, peaks, sampler):
     inp = synthetic.make_inputs(B3, seed=3000)
     seg = synthetic.make_silhouettes(B3, seed=3001)
     d_seg = ctx.to_device(seg.reshape(B3, 224, 224))
-    pts, offs = ops.silhouette_csr_device(d_seg, cap=int(seg.sum()) + 16)        # where(seg > 0) on the device
+    pts, offs = ops.silhouette_csr_device(d_seg, cap=int(seg.sum()) + 16)        # (for the brute-force comparison below)
     offs_h = offs.numpy()
     P = int(offs_h[-1])
-    d_seg.free()
     d = {k: ctx.to_device(v) for k, v in inp.items()}
     gp_in = [ctx.to_device(g) for g in synthetic.make_gp_inputs(3 * B3, seed=3002)]
     o3, ogp = {}, {}
 
     def c3_step():
-        smpl.step(d["beta"], d["theta"], d["cam"], d["kp_gt"], silhouette=(pts, offs), w_kp=60.0, w_mesh=0.001, out=o3)
+        # the dense mask goes in as the trainer holds it: where(seg > 0) runs on the device inside the call, every step
+        smpl.step(d["beta"], d["theta"], d["cam"], d["kp_gt"], seg=d_seg, w_kp=60.0, w_mesh=0.001, out=o3)
         ops.gradient_penalty_step(gp_in, out=ogp)
 
     for _ in range(3):
@@ -334,8 +334,9 @@ def single_gpu_configs(smpl, model, peaks, sampler):
     ctx.debug_set("mesh_grid", 1)
     pairs_bf = 2.0 * int(offs_h[sub]) * V
     gp_bytes = 3 * B3 * 428 * 4
-    out["c3"] = {"workload": "BASELINE config 3: kp + mesh-reprojection loss + backward at B=1024 (P=%d silhouette pixels, %.0f per "
-                             "image) + critic gradient penalty (forward + backward) over M=%d rows" % (P, P / B3, 3 * B3),
+    out["c3"] = {"workload": "BASELINE config 3: kp + mesh-reprojection loss + backward at B=1024 from the dense masks [B,224,224] "
+                             "(where(seg > 0) on the device inside the step: P=%d silhouette pixels, %.0f per image) + critic "
+                             "gradient penalty (forward + backward) over M=%d rows" % (P, P / B3, 3 * B3),
                  "ms_per_step": ms3, "value": B3 / (ms3 * 1e-3), "unit": UNIT, "iterations": n3, "clocks": ck,
                  "kernels_ms_per_step": kms,
                  "mesh_search": {"ms": mesh_ms, "reference_pairs_per_step": pairs,
@@ -347,7 +348,7 @@ def single_gpu_configs(smpl, model, peaks, sampler):
                                       "frac_of_fma_issue_peak_at_7_instr_per_pair": 7 * pairs_bf / (ms_bf * 1e-3) / fma_peak},
                  "gradient_penalty": {"ms": gp_ms, "bytes": gp_bytes, "gbs": gp_bytes / (gp_ms * 1e-3) / 1e9 if gp_ms else None,
                                       "frac_of_hbm": gp_bytes / (gp_ms * 1e-3) / 1e9 / peaks["hbm"] if gp_ms else None}}
-    for x in list(d.values()) + gp_in + [pts, offs, sp, d_pts, d_offs]:
+    for x in list(d.values()) + gp_in + [pts, offs, sp, d_pts, d_offs, d_seg]:
         x.free()
     # ---- config 5: inference sweep, SMPL forward (verts + joints + Rs), device-resident I/O
     sweep = []

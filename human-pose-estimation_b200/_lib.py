@@ -66,7 +66,10 @@ SIGNATURES = {
     "smplb_kcs": [_P, _I, _I, _P, _P, _P, _I],
     "smplb_kcs_backward": [_P, _I, _I, _P, _P, _P, _P, _I],
     "smplb_interpolate": [_P, _I, _I, _P, _P, _P, _P, _I],
+    "smplb_critic_inputs": [_P, _I, _I] + [_P] * 14 + [_I],
+    "smplb_critic_gradient_penalty": [_P, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I],
     "smplb_step": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I],
+    "smplb_step_seg": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I],
     "smplb_comm_p2p_export": [_P, _P],
     "smplb_comm_p2p_attach": [_P, _I, _I, _P],
     "smplb_comm_p2p_attach_local": [_P, _I, _I, C.POINTER(_P)],

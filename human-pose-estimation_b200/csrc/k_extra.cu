@@ -147,10 +147,162 @@ __global__ void k_interp(size_t total, int row, const float *__restrict__ fake, 
   out[i] = fake[i] + a * (real[i] - fake[i]);
 }
 
+// ---- the critic's inputs and its gradient penalty, fused -------------------------
+// (1) k_critic_inputs: everything src/trainer.py:548-557 builds for the interpolated forward pass in one launch:
+//     x_hat = fake + alpha * (real - fake) with ELEMENT-wise alpha (tf.random.uniform(x.shape)) for the 3-D joints
+//     [N,14,3], shapes [N,10] and rotations [N,23,3,3], and get_kcs(x_hat_joints) (src/models.py:123-139; the
+//     reference forms an N x 13 x 13 x N intermediate to take its diagonal).  One CTA per sample.
+__global__ void __launch_bounds__(256) k_critic_inputs(int K, const float *__restrict__ fj, const float *__restrict__ rj,
+                                                       const float *__restrict__ aj, const float *__restrict__ fs,
+                                                       const float *__restrict__ rs, const float *__restrict__ as_,
+                                                       const float *__restrict__ fR, const float *__restrict__ rR,
+                                                       const float *__restrict__ aR, const float *__restrict__ Cm,
+                                                       float *__restrict__ oj, float *__restrict__ okcs,
+                                                       float *__restrict__ os, float *__restrict__ oR) {
+  __shared__ float sB[3][KB];
+  __shared__ float sJ[KJ][3];
+  const int n = blockIdx.x, t = threadIdx.x;
+  for (int i = t; i < K * 3; i += 256) {
+    const size_t g = (size_t)n * K * 3 + i;
+    const float v = fj[g] + aj[g] * (rj[g] - fj[g]);
+    oj[g] = v;
+    if (i < KJ * 3) sJ[i / 3][i % 3] = v;
+  }
+  for (int i = t; i < 10 + 207; i += 256) {
+    if (i < 10) {
+      const size_t g = (size_t)n * 10 + i;
+      os[g] = fs[g] + as_[g] * (rs[g] - fs[g]);
+    } else {
+      const size_t g = (size_t)n * 207 + (i - 10);
+      oR[g] = fR[g] + aR[g] * (rR[g] - fR[g]);
+    }
+  }
+  __syncthreads();
+  if (t < 3 * KB) {
+    const int c = t / KB, a = t % KB;
+    float acc = 0.f;
+    for (int j = 0; j < KJ; ++j) acc = fmaf(sJ[j][c], Cm[j * KB + a], acc);
+    sB[c][a] = acc;
+  }
+  __syncthreads();
+  if (t < KB * KB) {
+    const int a = t / KB, b = t % KB;
+    okcs[(size_t)n * KB * KB + t] = sB[0][a] * sB[0][b] + sB[1][a] * sB[1][b] + sB[2][a] * sB[2][b];
+  }
+}
+
+// (2) k_critic_gp: what tf.gradients(out, [kcs, joints, shapes, Rs]) + compute_gradient_penalty (src/trainer.py:566-572,
+//     src/ops.py:153-172) amount to once the critic has returned its partial derivatives: the gradient w.r.t. the
+//     joints is the direct part plus the part through get_kcs (its backward, formed here per row), and the penalty
+//     needs the column sums of all four gradients.  One pass over the inputs: a CTA walks 64 rows, per row forms
+//     d_joints_total (optionally stored) and adds every column into its partial sums; the last CTA to finish (ticket)
+//     adds the partials in chunk order (deterministic) and forms the penalty.
+#define CG_ROWS 64
+__global__ void __launch_bounds__(448) k_critic_gp(int M, int K, long long M_total, const float *__restrict__ joints,
+                                                   const float *__restrict__ Cm, const float *__restrict__ g_kcs,
+                                                   const float *__restrict__ g_j, const float *__restrict__ g_s,
+                                                   const float *__restrict__ g_R, float *__restrict__ gj_total,
+                                                   float *__restrict__ part, unsigned int *__restrict__ ticket,
+                                                   float *__restrict__ col_sums, float *__restrict__ penalty) {
+  __shared__ float sK[KB][KB], sJ[KJ][3], sB[3][KB], sdB[3][KB], sC[KJ * KB];
+  __shared__ float sq[448], norms[4];
+  __shared__ bool last;
+  const int t = threadIdx.x;
+  const int m0 = blockIdx.x * CG_ROWS, m1 = min(M, m0 + CG_ROWS);
+  if (t < KJ * KB) sC[t] = Cm[t];
+  float acc = 0.f;   // this thread's column of the 428
+  for (int m = m0; m < m1; ++m) {
+    __syncthreads();
+    if (t < KB * KB) {
+      const float v = g_kcs[(size_t)m * KB * KB + t];
+      sK[t / KB][t % KB] = v;
+      acc += v;
+    } else if (t >= 211 && t < 221) {
+      acc += g_s[(size_t)m * 10 + (t - 211)];
+    } else if (t >= 221 && t < 428) {
+      acc += g_R[(size_t)m * 207 + (t - 221)];
+    } else if (t >= 169 && t < 169 + KJ * 3) {
+      const int i = t - 169;
+      sJ[i / 3][i % 3] = joints[((size_t)m * K + i / 3) * 3 + i % 3];
+    }
+    __syncthreads();
+    if (t < 3 * KB) {
+      const int c = t / KB, a = t % KB;
+      float b = 0.f;
+      for (int j = 0; j < KJ; ++j) b = fmaf(sJ[j][c], sC[j * KB + a], b);
+      sB[c][a] = b;
+    }
+    __syncthreads();
+    if (t < 3 * KB) {
+      const int c = t / KB, a = t % KB;
+      float d = 0.f;
+      for (int b = 0; b < KB; ++b) d = fmaf(sK[a][b] + sK[b][a], sB[c][b], d);
+      sdB[c][a] = d;
+    }
+    __syncthreads();
+    if (t >= 169 && t < 169 + KJ * 3) {
+      const int i = t - 169, j = i / 3, c = i % 3;
+      float d = g_j[(size_t)m * KJ * 3 + i];
+      for (int a = 0; a < KB; ++a) d = fmaf(sC[j * KB + a], sdB[c][a], d);
+      if (gj_total) gj_total[(size_t)m * KJ * 3 + i] = d;
+      acc += d;
+    }
+  }
+  if (t < SMPLB_GP_FLOATS) part[(size_t)blockIdx.x * SMPLB_GP_FLOATS + t] = acc;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float s = 0.f;
+  if (t < SMPLB_GP_FLOATS) {
+    for (int c = 0; c < (int)gridDim.x; ++c) s += __ldcg(part + (size_t)c * SMPLB_GP_FLOATS + t);
+    col_sums[t] = s;
+    const float mean = s / (float)M_total;
+    sq[t] = mean * mean;
+  }
+  __syncthreads();
+  if (t < 4) {
+    const int beg[5] = {0, 169, 211, 221, 428};
+    float q = 0.f;
+    for (int i = beg[t]; i < beg[t + 1]; ++i) q += sq[i];
+    norms[t] = sqrtf(q);
+  }
+  __syncthreads();
+  if (t == 0) {
+    float p = 0.f;
+    for (int q = 0; q < 4; ++q) p += (1.0f - norms[q]) * (1.0f - norms[q]);
+    *penalty = p;
+    *ticket = 0;   // ready for the next call on this stream
+  }
+}
+
+int launch_critic_inputs(smplb_ctx *c, int N, int K, const float *fj, const float *rj, const float *aj, const float *fs,
+                         const float *rs, const float *as_, const float *fR, const float *rR, const float *aR,
+                         const float *Cm, float *oj, float *okcs, float *os, float *oR) {
+  LAUNCH(c, "critic_inputs_interp_kcs", N, 256, 0, k_critic_inputs, K, fj, rj, aj, fs, rs, as_, fR, rR, aR, Cm, oj, okcs, os, oR);
+  return 0;
+}
+
+int launch_critic_gp(smplb_ctx *c, int M, int K, long long M_total, const float *joints, const float *Cm, const float *g_kcs,
+                     const float *g_j, const float *g_s, const float *g_R, float *gj_total, float *part,
+                     unsigned int *ticket, float *col_sums, float *penalty) {
+  LAUNCH(c, "critic_gp_kcsbwd_colsum_penalty", cdiv(M, CG_ROWS), 448, 0, k_critic_gp, M, K, M_total, joints, Cm, g_kcs, g_j, g_s,
+         g_R, gj_total, part, ticket, col_sums, penalty);
+  return 0;
+}
+
 int launch_silhouette_csr(smplb_ctx *c, int B, int H, int W, const float *seg, float *points, int cap, int *offsets,
                           int *counts_scratch) {
   LAUNCH(c, "sil_count", B, 256, 0, k_sil_count, H * W, seg, counts_scratch);
   LAUNCH(c, "sil_scan", 1, 1024, 0, k_sil_scan, B, counts_scratch, offsets);
+  if (cap > 0) LAUNCH(c, "sil_fill", B, 256, 0, k_sil_fill, H, W, seg, offsets, cap, points);
+  return 0;
+}
+
+// the fill alone, once the offsets (and the total) are known
+int launch_silhouette_fill(smplb_ctx *c, int B, int H, int W, const float *seg, float *points, int cap, const int *offsets) {
   LAUNCH(c, "sil_fill", B, 256, 0, k_sil_fill, H, W, seg, offsets, cap, points);
   return 0;
 }

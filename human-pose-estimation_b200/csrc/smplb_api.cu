@@ -434,7 +434,7 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
   void *ptrs[] = {c->d_vt,       c->d_shapedirs, c->d_posedirs, c->d_W,        c->d_JR,       c->d_Dext,   c->d_J0,
                   c->d_Jdirs,    c->d_kcsr_off,  c->d_kcsr_idx, c->d_kcsr_val, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val,
                   c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_W16,      c->d_G,        c->d_cc,       c->d_G16,      c->d_Gt16,     c->d_Dt16_act, c->d_W16_act,  c->d_kcsr_slot, c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
-                  c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part, c->ws_grid,  c->ws_vdist,
+                  c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part, c->ws_grid,  c->ws_vdist, c->ws_segpts, c->ws_segoff, c->ws_ticket,
                   c->x_mbox,     c->x_status,    c->d_Dbf};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -1181,23 +1181,74 @@ extern "C" int smplb_interpolate(smplb_ctx *c, int N, int row, const float *fake
   return st.finish();
 }
 
+// trainer.py:548-557 in one launch: element-wise interpolation of the critic's three inputs + get_kcs of the result
+extern "C" int smplb_critic_inputs(smplb_ctx *c, int N, int K, const float *fake_joints, const float *real_joints,
+                                   const float *alpha_joints, const float *fake_shapes, const float *real_shapes,
+                                   const float *alpha_shapes, const float *fake_Rs, const float *real_Rs,
+                                   const float *alpha_Rs, const float *Cm, float *joints, float *kcs, float *shapes,
+                                   float *Rs, int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(N < 1 || K < 14 || !fake_joints || !real_joints || !alpha_joints || !fake_shapes || !real_shapes || !alpha_shapes ||
+             !fake_Rs || !real_Rs || !alpha_Rs || !Cm || !joints || !kcs || !shapes || !Rs,
+         SMPLB_EINVAL, "N >= 1, K >= 14 and non-null pointers required");
+  NvtxRange nvtx("critic_inputs");
+  Stager st(c, mem);
+  const size_t nj = (size_t)N * K * 3, ns = (size_t)N * 10, nR = (size_t)N * 207;
+  const float *fj = st.in(fake_joints, nj), *rj = st.in(real_joints, nj), *aj = st.in(alpha_joints, nj);
+  const float *fs = st.in(fake_shapes, ns), *rs = st.in(real_shapes, ns), *as_ = st.in(alpha_shapes, ns);
+  const float *fR = st.in(fake_Rs, nR), *rR = st.in(real_Rs, nR), *aR = st.in(alpha_Rs, nR);
+  const float *dc = st.in(Cm, (size_t)14 * 13);
+  float *oj = st.out(joints, nj), *ok = st.out(kcs, (size_t)N * 169), *os = st.out(shapes, ns), *oR = st.out(Rs, nR);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  TRY(launch_critic_inputs(c, N, K, fj, rj, aj, fs, rs, as_, fR, rR, aR, dc, oj, ok, os, oR));
+  return st.finish();
+}
+
+// trainer.py:566-572 + ops.py:153-172 in one launch, given the critic's partial derivatives
+extern "C" int smplb_critic_gradient_penalty(smplb_ctx *c, int M, int K, int64_t M_total, const float *joints, const float *Cm,
+                                             const float *g_kcs, const float *g_joints, const float *g_shapes,
+                                             const float *g_Rs, float *penalty, float *col_sums, float *g_joints_total,
+                                             int mem) {
+  CHECK_CTX(c);
+  CHECK_MEM(mem);
+  RET_IF(M < 1 || K < 14 || M_total < M || !joints || !Cm || !g_kcs || !g_joints || !g_shapes || !g_Rs || !penalty, SMPLB_EINVAL,
+         "M >= 1, K >= 14, M_total >= M and non-null joints, C, gradients, penalty required");
+  NvtxRange nvtx("compute_gradient_penalty");
+  TRY(ensure_gp_ws(c, M));
+  if (!c->ws_ticket) {
+    CUDA_TRY(cudaMalloc((void **)&c->ws_ticket, 4));
+    CUDA_TRY(cudaMemsetAsync(c->ws_ticket, 0, 4, c->stream));
+  }
+  Stager st(c, mem);
+  const float *dj = st.in(joints, (size_t)M * K * 3), *dc = st.in(Cm, (size_t)14 * 13), *gk = st.in(g_kcs, (size_t)M * 169);
+  const float *gj = st.in(g_joints, (size_t)M * 42), *gs = st.in(g_shapes, (size_t)M * 10), *gR = st.in(g_Rs, (size_t)M * 207);
+  float *dp = st.out(penalty, 1), *dcs = st.out(col_sums, SMPLB_GP_FLOATS), *dgt = st.out(g_joints_total, (size_t)M * 42);
+  RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  float *sums = dcs ? dcs : c->ws_gp + (size_t)cdiv(M, 64) * SMPLB_GP_FLOATS;
+  TRY(launch_critic_gp(c, M, K, (long long)M_total, dj, dc, gk, gj, gs, gR, dgt, c->ws_gp, c->ws_ticket, sums, dp));
+  return st.finish();
+}
+
 // ---------------------------------------------------------------------------------- fused step
 static int allreduce_on(smplb_ctx *c, void *dev_buf, size_t count, int nccl_dtype, cudaStream_t stream);
 
-extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *theta, const float *cam,
-                          const float *kp_gt, const float *points_xy, const int32_t *offsets, int P, float w_kp,
-                          float w_mesh, float img_size, int64_t kp_count_override, float *verts, float *joints, float *Rs,
-                          float *kp_pred, float *loss_parts, float *d_beta, float *d_theta, float *d_cam, int flags,
-                          int mem) {
+// seg != NULL: the silhouettes arrive as the dense mask seg [B,H,W] (src/trainer.py:443: where(seg > 0)) and are
+// compacted on the device into the context's workspace; else points_xy / offsets / P as documented in smplb.h.
+static int step_core(smplb_ctx *c, int B, const float *beta, const float *theta, const float *cam, const float *kp_gt,
+                     const float *points_xy, const int32_t *offsets, int P, const float *seg, int H, int W, float w_kp,
+                     float w_mesh, float img_size, int64_t kp_count_override, float *verts, float *joints, float *Rs,
+                     float *kp_pred, float *loss_parts, float *d_beta, float *d_theta, float *d_cam, int flags, int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
   RET_IF(B < 1 || !beta || !theta || !cam || !kp_gt || !loss_parts, SMPLB_EINVAL,
          "B >= 1 and non-null beta, theta, cam, kp_gt, loss_parts required");
   RET_IF(flags & ~SMPLB_STEP_KEEP_VERTS, SMPLB_EINVAL, "unknown bits in flags");
-  bool have_mesh = offsets != nullptr;
+  RET_IF(seg && (H < 1 || W < 1), SMPLB_EINVAL, "H, W >= 1 required with a dense mask");
+  bool have_mesh = offsets != nullptr || seg != nullptr;
   bool bwd = d_beta || d_theta || d_cam;
   RET_IF(bwd && !(d_beta && d_theta && d_cam), SMPLB_EINVAL, "d_beta, d_theta, d_cam must be all set or all NULL");
-  RET_IF(have_mesh && P > 0 && !points_xy, SMPLB_EINVAL, "points_xy is NULL but P > 0");
+  RET_IF(!seg && have_mesh && P > 0 && !points_xy, SMPLB_EINVAL, "points_xy is NULL but P > 0");
   TRY(ensure_ws(c, B));
   if (have_mesh) TRY(ensure_mesh_ws(c, B, c->V));
   int K = c->K;
@@ -1206,13 +1257,39 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
   StepGuard guard{c};
   const float *dbeta = st.in(beta, (size_t)B * c->NB), *dtheta = st.in(theta, (size_t)B * 72);
   const float *dcam = st.in(cam, (size_t)B * 3), *dkpgt = st.in(kp_gt, (size_t)B * K * 3);
-  const float *dpts = have_mesh ? st.in(points_xy, (size_t)P * 2) : nullptr;
-  const int32_t *doff = have_mesh ? st.in(offsets, (size_t)B + 1) : nullptr;
+  const float *dpts = (have_mesh && !seg) ? st.in(points_xy, (size_t)P * 2) : nullptr;
+  const int32_t *doff = (have_mesh && !seg) ? st.in(offsets, (size_t)B + 1) : nullptr;
+  const float *dseg = seg ? st.in(seg, (size_t)B * H * W) : nullptr;
   float *overts = st.out(verts, (size_t)B * c->V3), *ojoints = st.out(joints, (size_t)B * K * 3);
   float *oRs = st.out(Rs, (size_t)B * NJ * 9), *okp = st.out(kp_pred, (size_t)B * K * 2);
   float *oloss = st.out(loss_parts, 4);
   float *odb = st.out(d_beta, (size_t)B * c->NB), *odt = st.out(d_theta, (size_t)B * 72), *odc = st.out(d_cam, (size_t)B * 3);
   RET_IF(st.failed, SMPLB_ECUDA, "device staging allocation failed");
+  if (seg) {
+    // where(seg > 0) -> CSR point lists, on the device (k_extra.cu): counts and offsets first, one 4-byte read-back
+    // of the total so the point buffer is sized exactly, then the ordered fill
+    if ((size_t)B + 1 > c->ws_segoff_cap) {
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      if (c->ws_segoff) CUDA_TRY(cudaFree(c->ws_segoff));
+      c->ws_segoff = nullptr;
+      CUDA_TRY(cudaMalloc((void **)&c->ws_segoff, ((size_t)B + 1) * 4));
+      c->ws_segoff_cap = (size_t)B + 1;
+    }
+    TRY(launch_silhouette_csr(c, B, H, W, dseg, c->ws_scal /* unused: cap 0 */, 0, c->ws_segoff, c->ws_cnt));
+    int total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, c->ws_segoff + B, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    P = total;
+    if ((size_t)P > c->ws_segpts_cap) {
+      if (c->ws_segpts) CUDA_TRY(cudaFree(c->ws_segpts));
+      c->ws_segpts = nullptr;
+      CUDA_TRY(cudaMalloc((void **)&c->ws_segpts, std::max<size_t>((size_t)P, 1) * 8));
+      c->ws_segpts_cap = (size_t)P;
+    }
+    if (P > 0) TRY(launch_silhouette_fill(c, B, H, W, dseg, c->ws_segpts, P, c->ws_segoff));
+    dpts = c->ws_segpts;
+    doff = c->ws_segoff;
+  }
   if (have_mesh && !dpts) dpts = c->ws_scal;
 
   // ---- batch shards: the visibility count is exchanged first (it depends on kp_gt alone, SURVEY
@@ -1333,6 +1410,24 @@ extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *t
   int rc = st.finish();
   guard.ok = rc == 0;
   return rc;
+}
+
+extern "C" int smplb_step(smplb_ctx *c, int B, const float *beta, const float *theta, const float *cam,
+                          const float *kp_gt, const float *points_xy, const int32_t *offsets, int P, float w_kp,
+                          float w_mesh, float img_size, int64_t kp_count_override, float *verts, float *joints, float *Rs,
+                          float *kp_pred, float *loss_parts, float *d_beta, float *d_theta, float *d_cam, int flags,
+                          int mem) {
+  return step_core(c, B, beta, theta, cam, kp_gt, points_xy, offsets, P, nullptr, 0, 0, w_kp, w_mesh, img_size, kp_count_override,
+                   verts, joints, Rs, kp_pred, loss_parts, d_beta, d_theta, d_cam, flags, mem);
+}
+
+extern "C" int smplb_step_seg(smplb_ctx *c, int B, const float *beta, const float *theta, const float *cam,
+                              const float *kp_gt, const float *seg, int H, int W, float w_kp, float w_mesh, float img_size,
+                              int64_t kp_count_override, float *verts, float *joints, float *Rs, float *kp_pred,
+                              float *loss_parts, float *d_beta, float *d_theta, float *d_cam, int flags, int mem) {
+  RET_IF(!seg, SMPLB_EINVAL, "seg is NULL");
+  return step_core(c, B, beta, theta, cam, kp_gt, nullptr, nullptr, 0, seg, H, W, w_kp, w_mesh, img_size, kp_count_override, verts,
+                   joints, Rs, kp_pred, loss_parts, d_beta, d_theta, d_cam, flags, mem);
 }
 
 // ------------------------------------------------------------------------------ NCCL (dlopen)

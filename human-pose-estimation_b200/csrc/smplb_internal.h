@@ -174,12 +174,16 @@ struct smplb_ctx {
   long long *ws_cnt64 = nullptr;  // [0] = kp num_present
   float *ws_theta = nullptr, *ws_beta = nullptr;   // copies kept for backward
   float *ws_gp = nullptr;      // gradient-penalty partials
+  unsigned int *ws_ticket = nullptr;   // last-CTA-done counter of k_critic_gp
   size_t ws_gp_cap = 0;        // floats
   float *ws_mesh_part = nullptr;   // mesh-loss per-CTA partials
   float *ws_vdist = nullptr;       // [B][V] vertex->pixel distances (summed per image in index order)
   size_t ws_vdist_cap = 0;
   void *ws_grid = nullptr;         // uniform-grid search workspace (k_loss.cu)
   size_t ws_grid_cap = 0;
+  float *ws_segpts = nullptr;      // smplb_step_seg: the compacted silhouette points [P][2] ...
+  int *ws_segoff = nullptr;        // ... and their offsets [B + 1]
+  size_t ws_segpts_cap = 0, ws_segoff_cap = 0;
   int use_mesh_grid = 1;           // smplb_debug_set("mesh_grid", 0): brute-force scan (the reference's own algorithm)
   size_t ws_mesh_part_cap = 0;
   size_t ws_mesh_cap = 0;      // elements of ws_silpred / ws_dsil / ws_silcnt
@@ -336,9 +340,16 @@ int launch_proj_bwd(smplb_ctx *c, int B, int N, const float *X, const float *cam
 // k_extra.cu
 int launch_silhouette_csr(smplb_ctx *c, int B, int H, int W, const float *seg, float *points, int cap, int *offsets,
                           int *counts_scratch);
+int launch_silhouette_fill(smplb_ctx *c, int B, int H, int W, const float *seg, float *points, int cap, const int *offsets);
 int launch_kcs(smplb_ctx *c, int N, int K, const float *joints, const float *Cm, float *kcs);
 int launch_kcs_bwd(smplb_ctx *c, int N, int K, const float *joints, const float *Cm, const float *dK, float *d_joints);
 int launch_interp(smplb_ctx *c, size_t total, int row, const float *fake, const float *real, const float *alpha, float *out);
+int launch_critic_inputs(smplb_ctx *c, int N, int K, const float *fj, const float *rj, const float *aj, const float *fs,
+                         const float *rs, const float *as_, const float *fR, const float *rR, const float *aR,
+                         const float *Cm, float *oj, float *okcs, float *os, float *oR);
+int launch_critic_gp(smplb_ctx *c, int M, int K, long long M_total, const float *joints, const float *Cm, const float *g_kcs,
+                     const float *g_j, const float *g_s, const float *g_R, float *gj_total, float *part,
+                     unsigned int *ticket, float *col_sums, float *penalty);
 // k_loss.cu
 int launch_kp_loss(smplb_ctx *c, int B, int K, const float *kp_gt, const float *kp_pred, float *dkp, float *part,
                    int *cnt);

@@ -130,11 +130,12 @@ class SMPL(object):
 
     # -- one generator stage of Trainer.train_step + its backward -----------
     def step(self, beta, theta, cam, kp_gt, silhouette=None, w_kp=60.0, w_mesh=0.001, img_size=224.0,
-             backward=True, want_verts=True, kp_count_override=0, out=None, skip=(), nowait=False):
+             backward=True, want_verts=True, kp_count_override=0, out=None, skip=(), nowait=False, seg=None):
         """src/trainer.py:404-450 + :502 for one stage: SMPL forward, keypoint
         projection and loss, optional mesh-reprojection loss, and gradients
         w.r.t. beta/theta/cam.  `silhouette` = (points_xy [P,2], offsets [B+1])
-        from ops.silhouette_csr.  Returns a dict.  `out` may hold preallocated
+        from ops.silhouette_csr, or `seg` = the dense mask [B,H,W(,1)] itself (compacted on the
+        device inside the call, trainer.py:443).  Returns a dict.  `out` may hold preallocated
         outputs of the right kind to avoid allocations in a timed loop;
         want_verts="device" (host-buffer calls) computes verts but leaves them in
         device memory (out["verts_device_ptr"]) instead of copying 339 MB back; names in
@@ -148,6 +149,11 @@ class SMPL(object):
         pc, pk = a.inp(cam, (N, 3)), a.inp(kp_gt, (N, K, 3))
         pp = po = None
         P = 0
+        pseg = None
+        if seg is not None:
+            assert silhouette is None, "pass either silhouette= (CSR points) or seg= (dense mask)"
+            H, W = int(seg.shape[1]), int(seg.shape[2])
+            pseg = a.inp(seg, (N, H, W))
         if silhouette is not None:
             pts, offs = silhouette
             P = int(pts.shape[0])
@@ -175,9 +181,13 @@ class SMPL(object):
         _, pdt = o("d_theta", (N, 72), backward)
         _, pdc = o("d_cam", (N, 3), backward)
         flags = _lib.STEP_KEEP_VERTS if want_verts == "device" else 0
-        check(lib().smplb_step(self.ctx.handle, N, pb, pt, pc, pk, pp, po, P, float(w_kp), float(w_mesh),
-                               float(img_size), int(kp_count_override), pv, pj, pR, pkp, pl, pdb, pdt, pdc, flags,
-                               2 if (nowait and a.mem == runtime.HOST) else a.mem))
+        mem = 2 if (nowait and a.mem == runtime.HOST) else a.mem
+        if pseg is not None:
+            check(lib().smplb_step_seg(self.ctx.handle, N, pb, pt, pc, pk, pseg, H, W, float(w_kp), float(w_mesh),
+                                       float(img_size), int(kp_count_override), pv, pj, pR, pkp, pl, pdb, pdt, pdc, flags, mem))
+        else:
+            check(lib().smplb_step(self.ctx.handle, N, pb, pt, pc, pk, pp, po, P, float(w_kp), float(w_mesh),
+                                   float(img_size), int(kp_count_override), pv, pj, pR, pkp, pl, pdb, pdt, pdc, flags, mem))
         if want_verts == "device":
             out["verts_device_ptr"] = self.last_verts_ptr()
         return out

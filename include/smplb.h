@@ -212,6 +212,22 @@ int smplb_kcs_backward(smplb_ctx *ctx, int N, int K, const float *joints, const 
 int smplb_interpolate(smplb_ctx *ctx, int N, int row, const float *fake, const float *real, const float *alpha,
                       float *out, int mem);
 
+/* The critic's interpolated inputs in one launch (src/trainer.py:548-557): x_hat = fake + alpha * (real - fake) with
+ * ELEMENT-wise alpha (tf.random.uniform(x.shape)) for the 3-D joints [N,K,3] (K >= 14), the shapes [N,10] and the
+ * rotations [N,23,3,3], plus kcs [N,13,13] = get_kcs(x_hat joints, C) (src/models.py:123-139).                   */
+int smplb_critic_inputs(smplb_ctx *ctx, int N, int K, const float *fake_joints, const float *real_joints,
+                        const float *alpha_joints, const float *fake_shapes, const float *real_shapes,
+                        const float *alpha_shapes, const float *fake_Rs, const float *real_Rs, const float *alpha_Rs,
+                        const float *C, float *joints, float *kcs, float *shapes, float *Rs, int mem);
+/* tf.gradients(out, [kcs, joints, shapes, Rs]) + compute_gradient_penalty (src/trainer.py:566-572, src/ops.py:153-172)
+ * in one launch, given the critic's PARTIAL derivatives g_kcs [M,13,13], g_joints [M,14,3] (direct path only),
+ * g_shapes [M,10], g_Rs [M,23,3,3] and the interpolated joints [M,K,3]: the joints gradient gains the path through
+ * get_kcs (its backward, per row), col_sums [428] (may be NULL) and penalty as smplb_gradient_penalty;
+ * g_joints_total [M,14,3] (may be NULL) receives the total joints gradient.  M_total: rows over all ranks.      */
+int smplb_critic_gradient_penalty(smplb_ctx *ctx, int M, int K, int64_t M_total, const float *joints, const float *C,
+                                  const float *g_kcs, const float *g_joints, const float *g_shapes, const float *g_Rs,
+                                  float *penalty, float *col_sums, float *g_joints_total, int mem);
+
 /* ---- the benchmarked fused call: what one generator stage of Trainer.train_step does
  * with SMPL, projection and losses (src/trainer.py:404-450) plus its backward
  * (src/trainer.py:502).
@@ -235,6 +251,14 @@ int smplb_step(smplb_ctx *ctx, int B, const float *beta, const float *theta, con
                float w_mesh, float img_size, int64_t kp_count_override, float *verts, float *joints, float *Rs,
                float *kp_pred, float *loss_parts, float *d_beta, float *d_theta, float *d_cam, int flags,
                int mem);
+
+/* The same step with the silhouettes given as the dense mask the trainer holds, seg [B,H,W] (NHWC with C = 1;
+ * src/trainer.py:443 builds the point list with tf.where(seg > 0) before every mesh_reprojection_loss): the
+ * compaction runs on the device inside the call, nothing passes through the host but one 4-byte count.       */
+int smplb_step_seg(smplb_ctx *ctx, int B, const float *beta, const float *theta, const float *cam,
+                   const float *kp_gt, const float *seg, int H, int W, float w_kp, float w_mesh, float img_size,
+                   int64_t kp_count_override, float *verts, float *joints, float *Rs, float *kp_pred,
+                   float *loss_parts, float *d_beta, float *d_theta, float *d_cam, int flags, int mem);
 
 /* ---- multi-GPU: one process per GPU; the batch shards over the ranks and the only exchange is
  * the sum of the visibility count and of the loss numerators (the

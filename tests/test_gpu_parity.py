@@ -354,6 +354,25 @@ def test_compact_backward_equals_dense_walk(smpl_full):
         assert rel_err(a[k], b[k]) < 2e-6, k
 
 
+def test_step_with_dense_mask_equals_step_with_point_lists(smpl_full):
+    """smplb_step_seg: the dense mask seg [B,H,W,1] of src/trainer.py:443 compacted on the device inside the step ==
+    the step fed with the host-side where(seg > 0) point lists, bit for bit (same points, same order)."""
+    B = 5
+    inp = synthetic.make_inputs(B, seed=71)
+    seg = synthetic.make_silhouettes(B, seed=72, a_range=(6, 10), b_range=(9, 14))
+    pts3 = synthetic.silhouette_points(seg)
+    a = smpl_full.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"], silhouette=ops.silhouette_csr(pts3, B))
+    a = {k: np.array(v) for k, v in a.items()}
+    b = smpl_full.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"], seg=seg)
+    ctx = smpl_full.ctx
+    d = smpl_full.step(ctx.to_device(inp["beta"]), ctx.to_device(inp["theta"]), ctx.to_device(inp["cam"]),
+                       ctx.to_device(inp["kp_gt"]), seg=ctx.to_device(seg.reshape(B, 224, 224)))
+    for k in ("verts", "loss_parts", "d_beta", "d_theta", "d_cam"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], d[k].numpy()), k
+    assert a["loss_parts"][2] > 0
+
+
 def test_tcgen05_blend_transpose_gemm_matches_fp32_gemm(smpl_full, full_model):
     """Dense backward (an upstream gradient on every vertex, src/trainer.py:502 with the mesh loss on):
     d pose_feature / d beta = dp . [posedirs | shapedirs]^T over K = 20670 as a bf16 split-precision tcgen05 GEMM
@@ -613,6 +632,40 @@ def test_section_8f_rows():
     fake, real = rng.normal(size=(9, 23, 3, 3)).astype(np.float32), rng.normal(size=(9, 23, 3, 3)).astype(np.float32)
     alpha = rng.uniform(size=9).astype(np.float32)
     assert rel_err(models.interpolate(fake, real, alpha), fake + alpha[:, None, None, None] * (real - fake)) < 1e-6
+    alpha_e = rng.uniform(size=fake.shape).astype(np.float32)     # element-wise, as trainer.py:548-550 draws it
+    assert rel_err(models.interpolate(fake, real, alpha_e), fake + alpha_e * (real - fake)) < 1e-6
+
+
+def test_fused_critic_inputs_and_gradient_penalty():
+    """SURVEY section 8f rank 1, fused: (1) the interpolated critic inputs + get_kcs of the interpolated joints in one
+    launch (trainer.py:548-557, models.py:123-139); (2) the gradient w.r.t. the joints completed with the path
+    through get_kcs and the gradient penalty over all four gradients in one launch (trainer.py:566-572,
+    ops.py:153-172) -- against the oracle and against the separate calls."""
+    from hpe_b200 import models
+    rng = np.random.default_rng(17)
+    M = 333                                                          # 6 chunks of 64 rows, the last one ragged
+    C = models.precompute_C_matrix()
+    mk = lambda *shape: rng.normal(size=shape).astype(np.float32)    # noqa: E731
+    un = lambda *shape: rng.uniform(size=shape).astype(np.float32)   # noqa: E731
+    fj, rj, aj = mk(M, 14, 3), mk(M, 14, 3), un(M, 14, 3)
+    fs, rs, as_ = mk(M, 10), mk(M, 10), un(M, 10)
+    fR, rR, aR = mk(M, 23, 3, 3), mk(M, 23, 3, 3), un(M, 23, 3, 3)
+    jh, kh, sh, Rh = models.critic_inputs(fj, rj, aj, fs, rs, as_, fR, rR, aR, C)
+    jw = fj.astype(np.float64) + aj * (rj.astype(np.float64) - fj)
+    assert rel_err(jh, jw) < 1e-6 and rel_err(sh, fs + as_ * (rs - fs)) < 1e-6 and rel_err(Rh, fR + aR * (rR - fR)) < 1e-6
+    assert rel_err(kh, onp.get_kcs(jw, C.astype(np.float64))) < 1e-5
+    # the critic's partial derivatives (any values: the critic itself is out of scope)
+    g_kcs, g_j, g_s, g_R = mk(M, 13, 13) + 0.1, mk(M, 14, 3) + 0.1, mk(M, 10) + 0.1, mk(M, 23, 3, 3) + 0.1
+    res = models.critic_gradient_penalty(jh, C, g_kcs, g_j, g_s, g_R, want=("col_sums", "g_joints_total"))
+    gj_total = g_j.astype(np.float64) + onp.get_kcs_backward(jh.astype(np.float64), C.astype(np.float64), g_kcs.astype(np.float64))
+    assert rel_err(res["g_joints_total"], gj_total) < 1e-5
+    want = onp.compute_gradient_penalty([g_kcs.astype(np.float64), gj_total, g_s.astype(np.float64), g_R.astype(np.float64)])
+    assert abs(res["penalty"] - want) < 1e-5 * want
+    # == the separate calls (kcs backward, add, penalty), and repeatable bit for bit (fixed-order partial sums)
+    sep = ops.compute_gradient_penalty([g_kcs, g_j + models.get_kcs_backward(jh, C, g_kcs), g_s, g_R])
+    assert abs(res["penalty"] - sep) < 1e-5 * sep
+    again = models.critic_gradient_penalty(jh, C, g_kcs, g_j, g_s, g_R, want=("col_sums",))
+    assert again["penalty"] == res["penalty"] and np.array_equal(again["col_sums"], res["col_sums"])
 
 
 def test_mocap_preprocessing_batched(smpl_full, full_model):
