@@ -923,6 +923,7 @@ extern "C" int smplb_last_verts(smplb_ctx *c, const float **dptr) {
 extern "C" int smplb_rodrigues(smplb_ctx *c, int N, const float *theta, float *R, int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
+  NvtxRange nvtx("batch_rodrigues");   // the reference's tf.name_scope of this function
   RET_IF(N < 1 || !theta || !R, SMPLB_EINVAL, "N >= 1 and non-null pointers required");
   Stager st(c, mem);
   const float *dt = st.in(theta, (size_t)N * 3);
@@ -936,6 +937,7 @@ extern "C" int smplb_global_rigid(smplb_ctx *c, int B, const float *Rs, const fl
                                   int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
+  NvtxRange nvtx("batch_forward_kinematics");   // the reference's tf.name_scope of this function
   RET_IF(B < 1 || !Rs || !Js || !new_J || !A, SMPLB_EINVAL, "B >= 1 and non-null pointers required");
   Stager st(c, mem);
   const float *dR = st.in(Rs, (size_t)B * NJ * 9), *dJ = st.in(Js, (size_t)B * NJ * 3);
@@ -949,6 +951,7 @@ extern "C" int smplb_global_rigid(smplb_ctx *c, int B, const float *Rs, const fl
 extern "C" int smplb_orth_proj(smplb_ctx *c, int B, int N, const float *X, const float *cam, float *out, int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
+  NvtxRange nvtx("batch_orth_proj_idrot");   // the reference's tf.name_scope of this function
   RET_IF(B < 1 || N < 1 || !X || !cam || !out, SMPLB_EINVAL, "B, N >= 1 and non-null pointers required");
   Stager st(c, mem);
   const float *dX = st.in(X, (size_t)B * N * 3), *dc = st.in(cam, (size_t)B * 3);
@@ -962,6 +965,7 @@ extern "C" int smplb_reproject_vertices(smplb_ctx *c, int B, int N, const float 
                                         float im_h, float *out, int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
+  NvtxRange nvtx("mesh_reproject");   // the reference's tf.name_scope of this function
   RET_IF(B < 1 || N < 1 || !verts || !cam || !out, SMPLB_EINVAL, "B, N >= 1 and non-null pointers required");
   Stager st(c, mem);
   const float *dX = st.in(verts, (size_t)B * N * 3), *dc = st.in(cam, (size_t)B * 3);
@@ -989,6 +993,7 @@ extern "C" int smplb_kp_loss(smplb_ctx *c, int B, int K, const float *kp_gt, con
                              int64_t *num_present, float *d_kp_pred, int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
+  NvtxRange nvtx("kp_reprojection_loss");   // the reference's tf.name_scope of this function
   RET_IF(B < 1 || K < 1 || !kp_gt || !kp_pred || !abs_sum || !num_present, SMPLB_EINVAL,
          "B, K >= 1 and non-null kp_gt, kp_pred, abs_sum, num_present required");
   TRY(ensure_ws(c, B));
@@ -1030,6 +1035,7 @@ extern "C" int smplb_mesh_reproj_loss(smplb_ctx *c, int B, int V, const float *p
                                       int32_t *ind_ba, int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
+  NvtxRange nvtx("mesh_reprojection_loss");   // the reference's tf.name_scope of this function
   RET_IF(B < 1 || V < 1 || P < 0 || !offsets || !sil_pred || !loss || (P > 0 && !points_xy), SMPLB_EINVAL,
          "B, V >= 1, P >= 0 and non-null offsets, sil_pred, loss required");
   TRY(ensure_mesh_ws(c, B, V));
@@ -1048,6 +1054,7 @@ extern "C" int smplb_mesh_reproj_loss(smplb_ctx *c, int B, int V, const float *p
 extern "C" int smplb_skew(smplb_ctx *c, int N, const float *vec, float *out, int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
+  NvtxRange nvtx("batch_skew");   // the reference's tf.name_scope of this function
   RET_IF(N < 1 || !vec || !out, SMPLB_EINVAL, "N >= 1 and non-null pointers required");
   Stager st(c, mem);
   const float *dv = st.in(vec, (size_t)N * 3);
@@ -1060,6 +1067,7 @@ extern "C" int smplb_skew(smplb_ctx *c, int N, const float *vec, float *out, int
 extern "C" int smplb_lrotmin(smplb_ctx *c, int B, const float *theta, float *out, int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
+  NvtxRange nvtx("batch_lrotmin");   // the reference's tf.name_scope of this function
   RET_IF(B < 1 || !theta || !out, SMPLB_EINVAL, "B >= 1 and non-null pointers required");
   Stager st(c, mem);
   const float *dt = st.in(theta, (size_t)B * 72);
@@ -1084,6 +1092,7 @@ extern "C" int smplb_gradient_penalty(smplb_ctx *c, int M, const float *g0, cons
                                       const float *g3, float *penalty, float *col_sums, int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
+  NvtxRange nvtx("compute_gradient_penalty");   // the reference's tf.name_scope of this function
   RET_IF(M < 1 || !g0 || !g1 || !g2 || !g3 || !penalty, SMPLB_EINVAL, "M >= 1 and non-null g0..g3, penalty required");
   TRY(ensure_gp_ws(c, M));
   Stager st(c, mem);
@@ -1145,6 +1154,7 @@ extern "C" int smplb_silhouette_csr(smplb_ctx *c, int B, int H, int W, const flo
 extern "C" int smplb_kcs(smplb_ctx *c, int N, int K, const float *joints, const float *Cm, float *kcs, int mem) {
   CHECK_CTX(c);
   CHECK_MEM(mem);
+  NvtxRange nvtx("get_kcs");   // the reference's tf.name_scope of this function
   RET_IF(N < 1 || K < 14 || !joints || !Cm || !kcs, SMPLB_EINVAL, "N >= 1, K >= 14 and non-null pointers required");
   Stager st(c, mem);
   const float *dj = st.in(joints, (size_t)N * K * 3), *dc = st.in(Cm, (size_t)14 * 13);
