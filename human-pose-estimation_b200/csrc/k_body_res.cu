@@ -32,6 +32,11 @@
 #include "tc_ptx.cuh"
 #include "body_common.cuh"
 
+// Tuning builds of this kernel (tools/build_variant.sh <name> -DFB_ABL2=<bits>): 1 no MMAs, 2 no TMEM loads, 4 no stores,
+// 8 stores go to the rows of sample block 0 (they stay in L2), 16 no TMA loads into the x16 / A16 rings.
+#ifndef FB_ABL2
+#define FB_ABL2 0
+#endif
 #ifdef FB_TIMING
 #define TCLK() clock64()
 #define TADD(acc, t) acc += clock64() - (t)
@@ -186,9 +191,13 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 #pragma unroll 1
         for (int st = 0; st < C::NT; ++st) {
           mbar_wait(empty_a + 8 * stage, phase ^ 1);
-          if (leader) mbar_expect_tx(full_a + 8 * stage, 2 * C::A_BYTES);
-          tma_load_2d_pair(sbase + C::SM_A + stage * C::A_BYTES, &map_a, 0, (m * C::NS + st * C::ST) * 12 + crank * (C::TN / 2),
-                           l_full_a + 8 * stage);
+          if (FB_ABL2 & 16) {
+            if (leader) mbar_arrive(full_a + 8 * stage);
+          } else {
+            if (leader) mbar_expect_tx(full_a + 8 * stage, 2 * C::A_BYTES);
+            tma_load_2d_pair(sbase + C::SM_A + stage * C::A_BYTES, &map_a, 0, (m * C::NS + st * C::ST) * 12 + crank * (C::TN / 2),
+                             l_full_a + 8 * stage);
+          }
           if (++stage == C::ASTAGES) {
             stage = 0;
             phase ^= 1;
@@ -226,9 +235,13 @@ __global__ void __launch_bounds__(C::THREADS, 1)
         }
         for (int kb = 0; kb < 4; ++kb) {
           mbar_wait(empty_x + 8 * stage, phase ^ 1);
-          if (leader) mbar_expect_tx(full_x + 8 * stage, 2 * C::X_BYTES);
-          tma_load_2d_pair(sbase + C::SM_X + stage * C::X_BYTES, &map_x, kb * 64, m * C::NS + crank * (C::NS / 2),
-                           l_full_x + 8 * stage);
+          if (FB_ABL2 & 16) {
+            if (leader) mbar_arrive(full_x + 8 * stage);
+          } else {
+            if (leader) mbar_expect_tx(full_x + 8 * stage, 2 * C::X_BYTES);
+            tma_load_2d_pair(sbase + C::SM_X + stage * C::X_BYTES, &map_x, kb * 64, m * C::NS + crank * (C::NS / 2),
+                             l_full_x + 8 * stage);
+          }
           if (++stage == C::XSTAGES) {
             stage = 0;
             phase ^= 1;
@@ -283,7 +296,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (kb == 3 && k == 3) continue;      // K = 240: the last 16 columns are zero padding
-                if (FB_ABLATE != 7) tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_p, (kb | k) != 0);
+                if (FB_ABLATE != 7 && !(FB_ABL2 & 1)) tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_p, (kb | k) != 0);
               }
             }
             __syncwarp();
@@ -338,7 +351,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           const uint64_t a_desc = umma_desc_add(desc_a0, stage * C::A_BYTES);
           if (elect_one()) {
             // (W window, A window) pairs of the table in k_skin_tc.cu; an A window is 32 B = 2 descriptor units
-            if (FB_ABLATE != 7) {   // (7: tuning build without MMAs -- hand-shakes, TMA traffic and stores only)
+            if (FB_ABLATE != 7 && !(FB_ABL2 & 1)) {   // (tuning builds without MMAs: hand-shakes, TMA traffic and stores only)
               tc_mma_f16_ts_pair(d_tmem, w_tmem + 0, a_desc + 0, idesc_t, 0);
               tc_mma_f16_ts_pair(d_tmem, w_tmem + 8, a_desc + 2, idesc_t, 1);
               tc_mma_f16_ts_pair(d_tmem, w_tmem + 0, a_desc + 4, idesc_t, 1);
@@ -385,8 +398,8 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       const bool v_ok = v0 + lane < V;
       // (FB_ABLATE == 4, tuning build: every super-tile writes the rows of sample block 0 -- the same store
       // instructions and bytes, but the lines stay in L2: no HBM write traffic)
-      float *const vbase = verts + ((size_t)((FB_ABLATE == 4 ? 0 : m) * C::NS) * V + v0 + lane) * 3;
-      const int b_left = FB_ABLATE == 4 ? C::NS : B - m * C::NS;   // samples of this super-tile inside the batch
+      float *const vbase = verts + ((size_t)(((FB_ABLATE == 4 || (FB_ABL2 & 8)) ? 0 : m) * C::NS) * V + v0 + lane) * 3;
+      const int b_left = (FB_ABLATE == 4 || (FB_ABL2 & 8)) ? C::NS : B - m * C::NS;   // samples of this super-tile inside the batch
       if (vp != cur_vp && grp == C::EG - 1) {
         // Every skinning MMA of the previous vertex tile has completed (this warp's group has waited for the
         // T of the super-tile's LAST tile): copy this thread's half of its W16 row (rows >= V are zero) to
@@ -422,7 +435,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
         tc_fence_after();
         const int s_loc = st * C::ST + part * HS;   // first sample (within the super-tile) of this warp
         uint32_t r[12 * HS], pc[3][HS];
-#if FB_ABLATE == 6 || FB_ABLATE == 7
+#if FB_ABLATE == 6 || FB_ABLATE == 7 || (FB_ABL2 & 2)
         // tuning build: no TMEM loads (hand-shakes and stores only)
 #pragma unroll
         for (int i = 0; i < 12 * HS; ++i) r[i] = tcol0 + i;
@@ -465,6 +478,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
                                   fmaf(__uint_as_float(T[4 * rr + 2]), pz, __uint_as_float(T[4 * rr + 3]))));
         }
         tq = TCLK();
+        if (!(FB_ABL2 & 4) || o[0][0] == 1.2345e-30f)
         store_rows4(vbase + s_loc * (V * 3), V * 3, b_left - s_loc, v_ok, o[0][0], o[0][1], o[0][2], o[1][0], o[1][1], o[1][2],
                     o[2][0], o[2][1], o[2][2], o[3][0], o[3][1], o[3][2]);
         TADD(w_st, tq);
