@@ -15,12 +15,19 @@
 //     vertex tile changes;
 //   * the "B" operands of both contractions -- the four k-blocks of the x16 tile and the twelve A16
 //     tiles of a super-tile, all [48 rows x 128 B] halves of a cta_group::2 operand -- stream through
-//     two small rings of 6 KB stages (x16: 2, A16: 3); the blend MMAs run k-block major so that an
+//     two small rings of 6 KB stages (x16: 3, A16: 4); the blend MMAs run k-block major so that an
 //     x16 stage is free again after its three planes.  (One ring shared by the two MMA issuers does
 //     not work: an issuer that skips the other's items can get two ring revolutions away from the
 //     producer, where an mbarrier's phase parity is ambiguous -- measured as wrong vertices.)
 //
-// Shared memory: 192 KB + 30 KB + barriers.  Per launch at B = 4096 a CTA now reads ~1.9 MB instead of
+//   * K = 240 (207 pose + 30 split shape + 3 split template columns), so the last 64-column k-block is only 3/4 used:
+//     it is loaded as three [128 rows x 16 columns] SWIZZLE_32B slabs (one K = 16 step each) instead of one
+//     SWIZZLE_128B block, which frees 12 KB for two more ring stages (x16: 3, A16: 4): the latency of the ring loads
+//     under the kernel's own store traffic is what the hand-shake chain waits for (112.6 -> 105.5 us on one box; verts
+//     stores through staging buffers and the TMA engine with those 12 KB instead were measured equal to st.global,
+//     profiles/r02/vertex_kernel_ablations.md).
+//
+// Shared memory: 180 KB + 42 KB of rings + barriers.  Per launch at B = 4096 a CTA reads ~1.9 MB instead of
 // 4.5 MB from L2.  Roles per CTA: warp 0 ring producer, warp 2 Dt16-tile producer (both CTAs load
 // their own halves; complete_tx goes to the leader's barriers), warps 1 / 3 blend / skinning MMA
 // issuers (leader only, commits multicast to both CTAs), warps 4-11 epilogue.
@@ -67,6 +74,17 @@ __device__ __forceinline__ void tc_st_32x16_r(uint32_t taddr, const uint32_t *r)
       : "memory");
 }
 
+// K-major SWIZZLE_32B operand ([rows x 32 B], 8-row groups 256 B apart): one K = 16 step per descriptor
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
+
 // EG = epilogue warp groups: 1 = eight warps walk every skinning tile; 2 = sixteen warps, group g takes the
 // tiles (and the T stage) of parity g, so one group's stores overlap the other's TMEM loads and FMAs.
 // PRE = tiles per group whose v_posed is fetched early (P is handed back before the super-tile ends).
@@ -77,7 +95,9 @@ struct ResCfg {
   static constexpr int NT = NS / ST;                 // skinning tiles per super-tile
   static constexpr int X_BYTES = (NS / 2) * 128;     // one stage of the x16 ring: this CTA's rows of one k-block
   static constexpr int A_BYTES = (TN / 2) * 128;     // one stage of the A16 ring: this CTA's rows of one skinning tile
-  static constexpr int D_TILE = 12 * FB_D_BYTES;     // 3 planes x 4 k-blocks of this CTA's vertex tile
+  static constexpr int D_MAIN = 9 * FB_D_BYTES;      // 3 planes x k-blocks 0..2 of this CTA's vertex tile, SWIZZLE_128B
+  static constexpr int D_SLAB = FB_VT * 32;          // one K = 16 step of the last k-block: [128 rows x 32 B], SWIZZLE_32B
+  static constexpr int D_TILE = D_MAIN + 9 * D_SLAB; // 180 KB: the zero padding of K = 240 to 256 never enters shared memory
   static constexpr int SM_D = 0;
   static constexpr int SM_X = SM_D + D_TILE;
   static constexpr int SM_A = SM_X + XSTAGES * X_BYTES;
@@ -88,6 +108,8 @@ struct ResCfg {
   static constexpr int HS = ST / EW;                 // samples per epilogue warp and tile
   static constexpr int THREADS = 32 * (4 + 4 * EW * EG);
   static constexpr int GT = NT / EG;                 // tiles per group and super-tile
+  // shared-memory offset of (plane cc, k-block kb) of the resident tile; kb = 3: the first of the plane's three slabs
+  __host__ __device__ static constexpr int d_off(int cc, int kb) { return kb < 3 ? (cc * 3 + kb) * FB_D_BYTES : D_MAIN + cc * 3 * D_SLAB; }
   static_assert(EG == 1 || EG == 2, "one or two epilogue groups");
   static_assert(NT % TBUF == 0 && PRE < GT, "tile counts");
   static_assert(HS == 4, "the epilogue is written for 4 samples per warp");
@@ -95,13 +117,13 @@ struct ResCfg {
   static_assert(WCOL + 32 <= 512, "TMEM budget");
   static_assert(X_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "swizzle atoms need 1024 B alignment");
   static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
-  static_assert(XSTAGES <= 4 && ASTAGES <= 4, "barrier slots");
+  static_assert(XSTAGES <= 4 && ASTAGES <= 8, "barrier slots");
 };
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1)
     k_body_res(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_d,
-               const __grid_constant__ CUtensorMap map_a, const uint4 *__restrict__ W16, int B, int V, int Vp, int n_vp,
+               const __grid_constant__ CUtensorMap map_d32, const __grid_constant__ CUtensorMap map_a, const uint4 *__restrict__ W16, int B, int V, int Vp, int n_vp,
                int n_m, float inv_scale, float *__restrict__ verts) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -110,8 +132,8 @@ __global__ void __launch_bounds__(C::THREADS, 1)
   const uint32_t d_empty = bar0 + 96;                          // the blend MMAs of a vertex tile are done
   const uint32_t p_full = bar0 + 104, p_empty = bar0 + 112, w_ready = bar0 + 120;
   const uint32_t full_x = bar0 + 128, empty_x = bar0 + 160;    // C::XSTAGES (<= 4) each
-  const uint32_t full_a = bar0 + 192, empty_a = bar0 + 224;    // C::ASTAGES (<= 4) each
-  const uint32_t t_full = bar0 + 256, t_empty = bar0 + 272;    // C::TBUF (2) each
+  const uint32_t t_full = bar0 + 192, t_empty = bar0 + 208;    // C::TBUF (2) each
+  const uint32_t full_a = bar0 + 320, empty_a = bar0 + 384;    // C::ASTAGES (<= 8) each
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + C::SM_BAR + 288);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -228,8 +250,15 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           for (int kb = 0; kb < 4; ++kb)                         // k-block major, the order the blend consumes them in
             for (int cc = 0; cc < 3; ++cc) {
               const int i = cc * 4 + kb;
-              if (leader) mbar_expect_tx(full_d + 8 * i, 2 * FB_D_BYTES);
-              tma_load_2d_pair(sbase + C::SM_D + i * FB_D_BYTES, &map_d, kb * 64, cc * Vp + vt * FB_VT, l_full_d + 8 * i);
+              if (kb < 3) {
+                if (leader) mbar_expect_tx(full_d + 8 * i, 2 * FB_D_BYTES);
+                tma_load_2d_pair(sbase + C::SM_D + C::d_off(cc, kb), &map_d, kb * 64, cc * Vp + vt * FB_VT, l_full_d + 8 * i);
+              } else {
+                if (leader) mbar_expect_tx(full_d + 8 * i, 2 * 3 * C::D_SLAB);
+                for (int k = 0; k < 3; ++k)
+                  tma_load_2d_pair(sbase + C::SM_D + C::d_off(cc, 3) + k * C::D_SLAB, &map_d32, 192 + 16 * k, cc * Vp + vt * FB_VT,
+                                   l_full_d + 8 * i);
+              }
             }
           ++loads;
         }
@@ -262,6 +291,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     if (leader) {
       constexpr uint32_t idesc_p = umma_idesc_f16(2 * FB_VT, C::NS);
       const uint64_t desc_d0 = umma_desc_sw128(sbase + C::SM_D), desc_x0 = umma_desc_sw128(sbase + C::SM_X);
+      const uint64_t desc_d32 = umma_desc_sw32(sbase + C::SM_D + C::D_MAIN);
       int cur_vp = -1, d_loads = 0, stage = 0, phase = 0, n_tiles = 0;
       [[maybe_unused]] long long w_pe = 0, w_fr = 0, w_fd = 0, w_tot = TCLK(), tq;
       for (int ti = 0; ti < n_t; ++ti, ++n_tiles) {
@@ -291,12 +321,14 @@ __global__ void __launch_bounds__(C::THREADS, 1)
             }
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + cc * C::NS;
-            const uint64_t a_desc = umma_desc_add(desc_d0, (cc * 4 + kb) * FB_D_BYTES);
+            // k-blocks 0..2: K steps 32 B apart inside a 128-byte swizzle atom; k-block 3: one 4 KB slab per K step
+            const uint64_t a_desc = kb < 3 ? umma_desc_add(desc_d0, (cc * 3 + kb) * FB_D_BYTES) : umma_desc_add(desc_d32, cc * 3 * C::D_SLAB);
+            const uint32_t a_step = kb < 3 ? 2 : (C::D_SLAB >> 4);
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                if (kb == 3 && k == 3) continue;      // K = 240: the last 16 columns are zero padding
-                if (FB_ABLATE != 7 && !(FB_ABL2 & 1)) tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_p, (kb | k) != 0);
+                if (kb == 3 && k == 3) continue;      // K = 240
+                if (FB_ABLATE != 7 && !(FB_ABL2 & 1)) tc_mma_f16_pair(d_tmem, a_desc + a_step * k, b_desc + 2 * k, idesc_p, (kb | k) != 0);
               }
             }
             __syncwarp();
@@ -479,8 +511,8 @@ __global__ void __launch_bounds__(C::THREADS, 1)
         }
         tq = TCLK();
         if (!(FB_ABL2 & 4) || o[0][0] == 1.2345e-30f)
-        store_rows4(vbase + s_loc * (V * 3), V * 3, b_left - s_loc, v_ok, o[0][0], o[0][1], o[0][2], o[1][0], o[1][1], o[1][2],
-                    o[2][0], o[2][1], o[2][2], o[3][0], o[3][1], o[3][2]);
+          store_rows4(vbase + s_loc * (V * 3), V * 3, b_left - s_loc, v_ok, o[0][0], o[0][1], o[0][2], o[1][0], o[1][1], o[1][2],
+                      o[2][0], o[2][1], o[2][2], o[3][0], o[3][1], o[3][2]);
         TADD(w_st, tq);
         if (C::EG == 1) {
           if (++tb == C::TBUF) {
@@ -527,12 +559,16 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------ host side
-using ResA = ResCfg<96, 8, 2, 3, 2, 1>;   // eight epilogue warps
+using ResA = ResCfg<96, 8, 3, 4, 2, 1>;   // eight epilogue warps; rings: x16 3 stages, A16 4 (the default)
 using ResB = ResCfg<96, 8, 2, 3, 1, 2>;   // sixteen epilogue warps in two groups
+using ResC = ResCfg<96, 8, 2, 3, 2, 1>;   // round 2's first ring depths (2 / 3), for comparison
 
 int body_res_init(smplb_ctx *c) {
   CUDA_TRY(cudaFuncSetAttribute(k_body_res<ResA>, cudaFuncAttributeMaxDynamicSharedMemorySize, ResA::SM_TOTAL));
   CUDA_TRY(cudaFuncSetAttribute(k_body_res<ResB>, cudaFuncAttributeMaxDynamicSharedMemorySize, ResB::SM_TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(k_body_res<ResC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ResC::SM_TOTAL));
+  // the last k-block of the resident tile as 16-column SWIZZLE_32B boxes (same rows as map_d)
+  TRY(tc_make_map(c->map_d32, 0, c->d_Dt16, 256, (uint64_t)c->pitch, 512, 16, FB_VT, /*swizzle=*/32));
   return 0;
 }
 
@@ -557,13 +593,13 @@ static int launch_res_cfg(smplb_ctx *c, int B, const void *x16, const void *A16,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const CUtensorMap map_d = *(const CUtensorMap *)c->map_d;
+  const CUtensorMap map_d = *(const CUtensorMap *)c->map_d, map_d32 = *(const CUtensorMap *)c->map_d32;
   const uint4 *W16 = (const uint4 *)c->d_W16;
   int Vv = c->V, Vp = c->Vp;
   float inv = c->tc_inv_scale;
   {
     ProfScope ps(c, "body_fwd_tc");
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_body_res<C>, map_x, map_d, map_a, W16, B, Vv, Vp, n_vp, n_m, inv, verts);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_body_res<C>, map_x, map_d, map_d32, map_a, W16, B, Vv, Vp, n_vp, n_m, inv, verts);
     if (e != cudaSuccess) {
       smplb_set_error("launch body_fwd_tc (resident Dt16 tile) failed: %s", cudaGetErrorString(e));
       return SMPLB_ECUDA;
@@ -573,10 +609,10 @@ static int launch_res_cfg(smplb_ctx *c, int B, const void *x16, const void *A16,
   return 0;
 }
 
-// verts [B][V][3]; needs an even number of 128-vertex tiles (the caller checks).  variant 9: sixteen epilogue
-// warps in two groups (measured equal alone, 1.5 % slower in the three-context step: the store path, not the
-// warps, is what the epilogue waits for -- DESIGN.md section 4).
+// verts [B][V][3]; needs an even number of 128-vertex tiles (the caller checks).  variant 9: sixteen epilogue warps in
+// two groups; variant 10: the 2 / 3 ring depths.
 int launch_body_fwd_res(smplb_ctx *c, int B, const void *x16, const void *A16, float *verts, int variant) {
   if (variant == 9) return launch_res_cfg<ResB>(c, B, x16, A16, verts);
+  if (variant == 10) return launch_res_cfg<ResC>(c, B, x16, A16, verts);
   return launch_res_cfg<ResA>(c, B, x16, A16, verts);
 }

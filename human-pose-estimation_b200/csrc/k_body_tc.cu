@@ -932,6 +932,7 @@ int launch_body_fwd_tc(smplb_ctx *c, int B, const void *x16, const void *A16, fl
       if ((c->Vp / FB_VT) % 2 == 0) return launch_body_fwd_pair(c, B, x16, A16, verts);
       return launch_body_cfg<BodyA>(c, B, x16, A16, verts);
     case 9:
+    case 10:
     default:
       if ((c->Vp / FB_VT) % 2 == 0) return launch_body_fwd_res(c, B, x16, A16, verts, c->use_fused);
       return launch_body_cfg<BodyA>(c, B, x16, A16, verts);

@@ -131,6 +131,7 @@ struct smplb_ctx {
   float tc_scale = 1.f, tc_inv_scale = 1.f;
   void *d_Dt16 = nullptr;      // [pitch][256] fp16, K-major
   alignas(64) unsigned char map_d[128];   // CUtensorMap of Dt16
+  alignas(64) unsigned char map_d32[128]; // the same rows as [128 x 16]-column boxes, SWIZZLE_32B (k_body_res.cu: last k-block)
   int num_sms = 148;
   void *ws_x16 = nullptr;      // [B][256] fp16 operand rows
   // ---- tcgen05 skinning path (k_skin_tc.cu)

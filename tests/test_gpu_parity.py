@@ -432,14 +432,20 @@ def test_fused_blend_skinning_matches_two_kernel_path(smpl_full, full_model):
         try:
             ctx.debug_set("fused", 0)
             v0, j0, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
-            # 1: the default (CTA pairs, Dt16 tile resident in shared memory, W16 in tensor memory, k_body_res); 9: the same
-            # with sixteen epilogue warps;
+            # 1: the default (CTA pairs, Dt16 tile resident in shared memory, W16 in tensor memory, k_body_res); 10: the
+            # same with shallower operand rings; 9: sixteen epilogue warps;
             # 7: CTA pairs streaming Dt16 (k_body_pair); 4: the best single-CTA configuration; 2, 3: tuning
             # variants; 5: W16 as a TMEM-resident operand; 6: CTA pairs with the Dt16 tiles multicast
-            for variant in (1, 9, 7, 2, 3, 4, 5, 6):
+            v_tma = None
+            for variant in (1, 10, 9, 7, 2, 3, 4, 5, 6):
                 ctx.debug_set("fused", variant)
                 v1, j1, _ = smpl_full(inp["beta"], inp["theta"], get_skin=True)
                 assert np.isfinite(v1).all()
+                # 1 and 10 differ only in the depth of the operand rings: same MMAs in the same order, same bits
+                if variant == 1:
+                    v_tma = v1
+                if variant == 10:
+                    assert np.array_equal(v1, v_tma), (B, "ring depth changed the result")
                 assert rel_err(v1, v0) < 2e-6, (B, variant)
                 assert np.array_equal(j1, j0)
                 n = min(B, 4)

@@ -16,7 +16,7 @@ ctx = smpl.ctx
 inp = synthetic.make_inputs(B, seed=1000)
 d = {k: ctx.to_device(v) for k, v in inp.items()}
 out = {}
-names = {0: "two kernels", 1: "CTA pairs, resident Dt16 tile, W16 in TMEM (default)", 7: "CTA pairs, streaming Dt16", 9: "resident Dt16 tile, sixteen epilogue warps", 2: "NS=96 ST=8 x2 PRE=0", 3: "NS=128 ST=4 x2 PRE=8",
+names = {0: "two kernels", 1: "CTA pairs, resident Dt16 tile, W16 in TMEM, rings 3 / 4 (default)", 10: "the same with rings 2 / 3", 7: "CTA pairs, streaming Dt16", 9: "resident Dt16 tile, sixteen epilogue warps", 2: "NS=96 ST=8 x2 PRE=0", 3: "NS=128 ST=4 x2 PRE=8",
          4: "NS=96 ST=8 x2 PRE=4 (best single-CTA)", 5: "W16 in TMEM, vertex-tile major", 6: "CTA pairs, Dt16 multicast"}
 for variant in ([int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else (0, 1, 9, 7, 4)):
     ctx.debug_set("fused", variant)
