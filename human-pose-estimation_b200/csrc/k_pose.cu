@@ -392,6 +392,199 @@ __global__ void __launch_bounds__(32 * PB_WARPS)
   }
 }
 
+// The same backward without the 23-step serial walk: everything the reverse chain accumulates is a SUBTREE SUM.
+// With S_i = sum over the subtree of i of dtg0 (dtg0 = dA_t), Rg_k = Rg_i * (product of the local rotations from i
+// down to k), the recursion  dRg_p += dRg_i R_i^T + dtg_i (x) (J_i - J_p),  dtg_p += dtg_i  unrolls to
+//     dRg_i = (sum over k in subtree(i) of E_k Rg_k^T) Rg_i,   E_k = dRg0_k + sum over children c of k of S_c (x) (J_c - J_k),
+// and   dR_i = Rg_p^T dRg_i,   dJ_i = dJ0_i + Rg_p^T S_i - Rg_i^T (S_i - dtg0_i)   (roots: dR = dRg, Rg_p = I).
+// One warp per body, lane = joint, state in registers; subtree sums gather children level by level with shuffles
+// (children in index order, so the sums are deterministic).  No shared memory, no local rotations.
+// ch[slot] = this lane's slot-th child (-1: none), slots[d] = the largest child count among the joints of depth d - 1
+template <int N>
+__device__ __forceinline__ void subtree_sum(float *v, const int *ch, int depth, int max_depth, unsigned slots) {
+#pragma unroll 1
+  for (int d = max_depth; d >= 1; --d) {
+    const int ns = (slots >> (2 * d)) & 3;
+#pragma unroll 1
+    for (int slot = 0; slot < ns; ++slot) {
+      const int cs = slot == 0 ? ch[0] : (slot == 1 ? ch[1] : ch[2]);
+      const bool on = depth == d - 1 && cs >= 0;
+      const int c = on ? cs : 0;
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        const float x = __shfl_sync(FULL, v[e], c);
+        v[e] += on ? x : 0.0f;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    k_pose_bwd_reg(int B, int NB, Tree tree, const float *__restrict__ theta, const float *__restrict__ Jin,
+                   const float *__restrict__ A, const float *__restrict__ dA_part, int n_dA_parts,
+                   const float *__restrict__ dx_part, int ksplit, int dx_rows, const float *__restrict__ rowscale,
+                   const float *__restrict__ d_Rs, const float *__restrict__ Jdirs, float *__restrict__ d_beta,
+                   float *__restrict__ d_theta, const long long *__restrict__ den, float gscale, float *__restrict__ d_cam) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  float osc = 1.0f;
+  if (den) {
+    long long dv = *den;
+    osc = dv > 0 ? gscale / (float)dv : 0.0f;
+    if (d_cam && lane < 3) d_cam[(size_t)b * 3 + lane] *= osc;
+  }
+  const bool act = lane < NJ;
+  const int j = act ? lane : NJ - 1;
+  const int par = act ? tree.parent[j] : -2;
+  const int depth = act ? tree.depth[j] : -1;
+  const int ch[3] = {act ? tree.child[j][0] : -1, act ? tree.child[j][1] : -1, act ? tree.child[j][2] : -1};
+  const unsigned slots = tree.level_slots;
+  // independent loads first: dx partials (pose-feature rows), theta, then dA / A / J
+  float gx[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) {
+    float acc = 0.0f;
+    if (j >= 1)
+      for (int ks = 0; ks < ksplit; ++ks) acc += dx_part[((size_t)ks * dx_rows + b) * KX + (j - 1) * 9 + e];
+    gx[e] = acc;
+  }
+  const float rs = rowscale ? rowscale[b] : 1.0f;
+  float dA[12];
+  {
+    const float4 *src = reinterpret_cast<const float4 *>(dA_part + (size_t)b * (NJ * 12) + j * 12);
+    float4 a0 = src[0], a1 = src[1], a2 = src[2];
+    for (int sp = 1; sp < n_dA_parts; ++sp) {
+      const float4 *s2 = src + (size_t)sp * B * (NJ * 3);
+      float4 b0 = s2[0], b1 = s2[1], b2 = s2[2];
+      a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+      a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+      a2.x += b2.x; a2.y += b2.y; a2.z += b2.z; a2.w += b2.w;
+    }
+    dA[0] = a0.x; dA[1] = a0.y; dA[2] = a0.z; dA[3] = a0.w;
+    dA[4] = a1.x; dA[5] = a1.y; dA[6] = a1.z; dA[7] = a1.w;
+    dA[8] = a2.x; dA[9] = a2.y; dA[10] = a2.z; dA[11] = a2.w;
+  }
+  float Rg[9], J[3];
+  {
+    const float4 *src = reinterpret_cast<const float4 *>(A + ((size_t)b * NJ + j) * 12);
+    float4 a0 = src[0], a1 = src[1], a2 = src[2];
+    Rg[0] = a0.x; Rg[1] = a0.y; Rg[2] = a0.z;
+    Rg[3] = a1.x; Rg[4] = a1.y; Rg[5] = a1.z;
+    Rg[6] = a2.x; Rg[7] = a2.y; Rg[8] = a2.z;
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) J[cc] = Jin[((size_t)b * NJ + j) * 3 + cc];
+  }
+  if (!act) {
+#pragma unroll
+    for (int e = 0; e < 12; ++e) dA[e] = 0.0f;
+  }
+  const float t0[3] = {dA[3], dA[7], dA[11]};            // dtg0 = dA_t
+  float S[3] = {t0[0], t0[1], t0[2]};
+  subtree_sum<3>(S, ch, depth, tree.max_depth, slots);
+  // Z = sum over children c of S_c (x) J_c
+  float Z[9];
+  {
+    float Y[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        Y[3 * r + cc] = S[r] * J[cc];
+        Z[3 * r + cc] = 0.0f;
+      }
+#pragma unroll
+    for (int slot = 0; slot < 3; ++slot) {
+      const bool on = ch[slot] >= 0;
+      const int c = on ? ch[slot] : 0;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) {
+        const float x = __shfl_sync(FULL, Y[e], c);
+        Z[e] += on ? x : 0.0f;
+      }
+    }
+  }
+  // E = dRg0 + Z - (S - dtg0) (x) J with dRg0 = dA_R - dA_t (x) J;  Q = subtree sum of E Rg^T
+  float Q[9];
+  {
+    float E[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) E[3 * r + cc] = (dA[4 * r + cc] - t0[r] * J[cc]) + (Z[3 * r + cc] - (S[r] - t0[r]) * J[cc]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) Q[3 * r + cc] = E[3 * r] * Rg[3 * cc] + E[3 * r + 1] * Rg[3 * cc + 1] + E[3 * r + 2] * Rg[3 * cc + 2];
+  }
+  subtree_sum<9>(Q, ch, depth, tree.max_depth, slots);
+  // dRg = Q Rg; parent's rotation by shuffle (identity for a root)
+  float dRg[9], P[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) dRg[3 * r + cc] = Q[3 * r] * Rg[cc] + Q[3 * r + 1] * Rg[3 + cc] + Q[3 * r + 2] * Rg[6 + cc];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) {
+    const float x = __shfl_sync(FULL, Rg[e], par >= 0 ? par : 0);
+    P[e] = par >= 0 ? x : ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+  }
+  // G = dR (+ blend-backward pose-feature gradient + upstream d_Rs);  dR = Rg_p^T dRg
+  float G[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      float g = P[r] * dRg[cc] + P[3 + r] * dRg[3 + cc] + P[6 + r] * dRg[6 + cc];
+      g += gx[3 * r + cc] * rs;
+      if (d_Rs) g += d_Rs[((size_t)b * NJ + j) * 9 + 3 * r + cc];
+      G[3 * r + cc] = g;
+    }
+  // dJ = dJ0 + Rg_p^T S - Rg^T (S - dtg0),  dJ0 = -Rg^T dtg0   =>   dJ = Rg_p^T S - Rg^T S
+  float dJ[3];
+#pragma unroll
+  for (int cc = 0; cc < 3; ++cc)
+    dJ[cc] = (P[cc] * S[0] + P[3 + cc] * S[1] + P[6 + cc] * S[2]) - (Rg[cc] * S[0] + Rg[3 + cc] * S[1] + Rg[6 + cc] * S[2]);
+  if (act) {
+    const float *th = theta + (size_t)b * 72 + 3 * j;
+    float dth[3];
+    rodrigues_bwd(th[0], th[1], th[2], G, dth);
+    d_theta[(size_t)b * 72 + 3 * j + 0] = dth[0] * osc;
+    d_theta[(size_t)b * 72 + 3 * j + 1] = dth[1] * osc;
+    d_theta[(size_t)b * 72 + 3 * j + 2] = dth[2] * osc;
+  } else {
+    dJ[0] = dJ[1] = dJ[2] = 0.0f;
+  }
+  // d beta = Jdirs^T dJ (+ dp . shapedirs^T from the blend backward GEMM): lane j adds its joint's three rows of
+  // Jdirs, then a fixed-order butterfly over the lanes
+  float db[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) db[k] = 0.0f;
+  if (act) {
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      const float *jd = Jdirs + (size_t)(3 * j + cc) * NB;
+#pragma unroll
+      for (int k = 0; k < 10; ++k)
+        if (k < NB) db[k] = fmaf(jd[k], dJ[cc], db[k]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 10; ++k) db[k] += __shfl_xor_sync(FULL, db[k], o);
+  if (lane < NB) {
+    float acc = 0.0f;
+    for (int ks = 0; ks < ksplit; ++ks) acc += dx_part[((size_t)ks * dx_rows + b) * KX + NPF + lane];
+    acc *= rs;
+    float mine = db[0];
+#pragma unroll
+    for (int k = 1; k < 10; ++k)
+      if (lane == k) mine = db[k];
+    d_beta[(size_t)b * NB + lane] = (acc + mine) * osc;
+  }
+}
+
 // batch_rodrigues stand-alone (batch_lbs.py:42): one thread per rotation.
 __global__ void k_rodrigues(int N, const float *__restrict__ theta, float *__restrict__ R) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -478,6 +671,12 @@ int launch_pose_bwd(smplb_ctx *c, int B, const float *theta, const float *Rs, co
                     const float *dA_part, int n_dA_parts, const float *dx_part, int ksplit, int dx_rows,
                     const float *rowscale, const float *d_Rs, float *d_beta, float *d_theta, const long long *den,
                     float gscale, float *d_cam) {
+  if (c->use_pose_bwd_reg && c->NB <= 10 && c->tree.max_children <= 3 && c->tree.max_depth < 16) {
+    // register / shuffle formulation (subtree sums); smplb_debug_set("pose_bwd_reg", 0) selects the serial walk
+    LAUNCH(c, "pose_bwd", cdiv(B, 4), 128, 0, k_pose_bwd_reg, B, c->NB, c->tree, theta, J, A, dA_part, n_dA_parts, dx_part, ksplit,
+           dx_rows, rowscale, d_Rs, c->d_Jdirs, d_beta, d_theta, den, gscale, d_cam);
+    return 0;
+  }
   LAUNCH(c, "pose_bwd", cdiv(B, PB_WARPS), 32 * PB_WARPS, 0, k_pose_bwd, B, c->NB, c->tree, theta, Rs, J, A, dA_part,
          n_dA_parts, dx_part, ksplit, dx_rows, rowscale, d_Rs, c->d_Jdirs, d_beta, d_theta, den, gscale, d_cam);
   return 0;

@@ -287,6 +287,27 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
     c->tree.depth[j] = p < 0 ? 0 : (signed char)(c->tree.depth[p] + 1);
     c->tree.max_depth = std::max(c->tree.max_depth, (int)c->tree.depth[j]);
   }
+  {
+    int nch[NJ] = {};
+    for (int j = 0; j < NJ; ++j) c->tree.child[j][0] = c->tree.child[j][1] = c->tree.child[j][2] = -1;
+    for (int j = 0; j < NJ; ++j) {
+      const int p = c->tree.parent[j];
+      if (p < 0) continue;
+      if (nch[p] < 3) c->tree.child[p][nch[p]] = (signed char)j;
+      nch[p]++;
+    }
+    c->tree.level_slots = 0;
+    c->tree.max_children = 0;
+    for (int j = 0; j < NJ; ++j) {
+      c->tree.max_children = std::max(c->tree.max_children, nch[j]);
+      const int d = c->tree.depth[j] + 1;
+      if (d < 16) {
+        const unsigned cur = (c->tree.level_slots >> (2 * d)) & 3u;
+        const unsigned want = (unsigned)std::min(nch[j], 3);
+        if (want > cur) c->tree.level_slots = (c->tree.level_slots & ~(3u << (2 * d))) | (want << (2 * d));
+      }
+    }
+  }
   int rc = 0;
   auto fail = [&](int code) {
     smplb_destroy(c);
@@ -627,6 +648,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
   }
   if (!strcmp(key, "skin_tc")) {
     c->use_skin_tc = value;
+    return 0;
+  }
+  if (!strcmp(key, "pose_bwd_reg")) {
+    c->use_pose_bwd_reg = value;
     return 0;
   }
   if (!strcmp(key, "compact_bwd")) {

@@ -21,6 +21,11 @@ struct Tree {
   signed char parent[NJ];
   signed char depth[NJ];
   int max_depth;
+  // for the subtree-sum backward (k_pose_bwd_reg): the first three children of each joint in index order (-1: none),
+  // per depth d the largest child count among the joints of depth d - 1 (2 bits each), and the largest child count
+  signed char child[NJ][3];
+  unsigned level_slots;
+  int max_children;
 };
 
 // ---- mailbox exchange between batch shards (k_exchange.cu)
@@ -124,6 +129,7 @@ struct smplb_ctx {
   bool saved_fold = false;
   bool saved_fold_step = false;    // the forward already ran the fused keypoint forward + backward (k_fold_step_w)
   int use_fold_step = 1;           // smplb_debug_set("fold_step", 0): separate forward / backward kernels
+  int use_pose_bwd_reg = 1;        // smplb_debug_set("pose_bwd_reg", 0): the serial reverse walk in shared memory (validation)
   int fold_warp_kernels = 1;       // smplb_debug_set("fold_warp", 0): CTA-per-body reference kernels
   // ---- tcgen05 blend path (k_blend_tc.cu)
   bool tc_ok = false;          // operands built, tensor map encoded

@@ -489,6 +489,32 @@ def test_fused_blend_skinning_small_vertex_counts():
             assert rel_err(v1[:3], v) < TOL
 
 
+def test_pose_backward_subtree_sum_form_matches_serial_walk(smpl_full, full_model):
+    """k_pose_bwd_reg (the reverse kinematic chain as subtree sums in registers, the default) against k_pose_bwd (the
+    23-step walk of batch_lbs.py:128-135 reversed joint by joint): the keypoint step, and the dense backward with
+    upstream d_verts / d_joints / d_Rs -- same inputs, different summation order only."""
+    ctx = smpl_full.ctx
+    inp = synthetic.make_inputs(61, seed=4242)
+    rng = np.random.default_rng(9)
+    V = full_model["v_template"].shape[0]
+    ups = dict(d_verts=rng.standard_normal((61, V, 3)).astype(np.float32) * 1e-3,
+               d_joints=rng.standard_normal((61, 19, 3)).astype(np.float32),
+               d_Rs=rng.standard_normal((61, 24, 3, 3)).astype(np.float32))
+    res = {}
+    try:
+        for mode in (1, 0):
+            ctx.debug_set("pose_bwd_reg", mode)
+            st = smpl_full.step(inp["beta"], inp["theta"], inp["cam"], inp["kp_gt"])
+            smpl_full(inp["beta"], inp["theta"], get_skin=True)
+            g = smpl_full.backward(**ups)
+            res[mode] = [np.array(st[k]) for k in ("d_beta", "d_theta", "d_cam")] + [np.array(x) for x in g]
+    finally:
+        ctx.debug_set("pose_bwd_reg", 1)
+    for a, b in zip(res[1], res[0]):
+        assert np.isfinite(a).all()
+        assert rel_err(a, b) < 5e-6
+
+
 def test_fused_keypoint_forward_backward_matches_separate_kernels(smpl_full):
     """k_fold_step_w (forward + backward of the folded keypoint path in one kernel, gradients formed
     for a unit loss scale and scaled by w_kp / num_present in k_pose_bwd) against the separate
