@@ -650,6 +650,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
     c->use_skin_tc = value;
     return 0;
   }
+  if (!strcmp(key, "mesh_lattice")) {
+    c->use_mesh_lattice = value;
+    return 0;
+  }
   if (!strcmp(key, "pose_bwd_reg")) {
     c->use_pose_bwd_reg = value;
     return 0;

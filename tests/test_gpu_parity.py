@@ -613,30 +613,43 @@ def test_folded_keypoint_path_matches_per_vertex_path(smpl_full):
 
 
 def test_mesh_grid_search_equals_brute_force():
-    """The uniform-grid nearest-neighbour search must reproduce the reference's full scan
-    bit for bit: same indices (first index on ties), same loss, same gradient."""
+    """The accelerated nearest-neighbour searches must reproduce the reference's full scan bit for bit: same indices
+    (first index on ties), same loss, same gradient.  Modes: lattice (vertex -> pixel on the pixel bitmap, the default
+    for row-major pixel lists) + binned grid, binned grid only, brute force.  Image 4's points are shuffled and image
+    5's are not integers, so those two fall back to the grid inside the lattice mode."""
     rng = np.random.default_rng(77)
     B, V = 6, 1500
     seg = synthetic.make_silhouettes(B, seed=19, a_range=(10, 30), b_range=(20, 60))
     pts3 = synthetic.silhouette_points(seg)
+    sel4 = np.flatnonzero(pts3[:, 0] == 4)
+    pts3[sel4] = pts3[rng.permutation(sel4)]           # not in row-major order: no lattice for this image
+    pts3[pts3[:, 0] == 5, 1:] += 0.25                  # not on the integer lattice
     sp = (rng.normal(size=(B, V, 2)) * np.array([25.0, 45.0]) + 112.0).astype(np.float32)
     sp[0, :200] = sp[0, 200:400]                       # exact duplicates: ties must pick the first index
+    sp[0, 400:500] = np.round(sp[0, 400:500])          # vertices exactly on lattice points: equidistant pixels
+    sp[0, 500:600] = np.round(sp[0, 500:600]) + 0.5    # ... and exactly between them
     sp[1] += 400.0                                     # a mesh projected far outside the image
     sp[3, :, 0] = 100.0                                # degenerate: all vertices on one vertical line
     ctx = ops._ctx_for(sp)
     pts, offs = ops.silhouette_csr(pts3, B)
     res = {}
-    for mode in (1, 0):
-        ctx.debug_set("mesh_grid", mode)
-        res[mode] = ops._mesh_call(ctx, pts, offs, sp, True, True)
-    ctx.debug_set("mesh_grid", 1)
-    (l1, g1, ab1, ba1), (l0, g0, ab0, ba0) = res[1], res[0]
-    assert np.array_equal(ab1, ab0) and np.array_equal(ba1, ba0)
-    assert l1[0] == l0[0]
-    assert np.array_equal(g1, g0)
-    # and both agree with the oracle's value
+    try:
+        for mode in ("lattice", "grid", "brute"):
+            ctx.debug_set("mesh_grid", 0 if mode == "brute" else 1)
+            ctx.debug_set("mesh_lattice", 1 if mode == "lattice" else 0)
+            res[mode] = ops._mesh_call(ctx, pts, offs, sp, True, True)
+    finally:
+        ctx.debug_set("mesh_grid", 1)
+        ctx.debug_set("mesh_lattice", 1)
+    l0, g0, ab0, ba0 = res["brute"]
+    for mode in ("lattice", "grid"):
+        l1, g1, ab1, ba1 = res[mode]
+        assert np.array_equal(ab1, ab0) and np.array_equal(ba1, ba0), mode
+        assert l1[0] == l0[0], mode
+        assert np.array_equal(g1, g0), mode
+    # and all agree with the oracle's value
     lo = onp.mesh_reprojection_loss(pts3.astype(np.float64), sp.astype(np.float64), B)
-    assert abs(l1[0] - lo) < TOL * lo
+    assert abs(l0[0] - lo) < TOL * lo
 
 
 def test_section_8f_rows():
