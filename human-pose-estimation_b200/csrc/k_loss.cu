@@ -7,20 +7,7 @@
 //   mesh_reprojection_loss    src/ops.py:117-137
 //   compute_gradient_penalty  src/ops.py:153-172
 #include "smplb_internal.h"
-
-// Fixed-order block sum of one float per thread (blockDim.x a power of two <= 1024).
-__device__ __forceinline__ float block_sum(float v, float *red) {
-  int t = threadIdx.x;
-  red[t] = v;
-  __syncthreads();
-  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-    if (t < o) red[t] += red[t + o];
-    __syncthreads();
-  }
-  float r = red[0];
-  __syncthreads();
-  return r;
-}
+#include "mesh_common.cuh"
 
 // ---------------------------------------------------------------------------- keypoint loss
 // Stand-alone kp loss on caller-supplied predictions: per-body partial sums.
@@ -125,13 +112,6 @@ __global__ void k_finalize_loss(float w_kp, float w_mesh, long long count_overri
 }
 
 // ------------------------------------------------------------------------------- mesh loss
-// d2(a, b) exactly as the fp32 expansion of ops.py:63-65: (-2 a.b + |a|^2) + |b|^2, each sum
-// rounded separately (-2 * x is exact, so the FMA below rounds once like the TF add does).
-__device__ __forceinline__ float d2_expand(float ax, float ay, float a2, float bx, float by, float b2) {
-  float dot = __fmaf_rn(ax, bx, __fmul_rn(ay, by));
-  return __fadd_rn(__fmaf_rn(-2.0f, dot, a2), b2);
-}
-
 #define MT 256     // threads per CTA of the NN kernels
 #define MTILE 1024 // points staged per shared-memory tile
 
@@ -158,15 +138,7 @@ __device__ __forceinline__ float d2_expand(float ax, float ay, float a2, float b
 // is unchanged, so the result stays bit-identical to the full scan.
 #define GRID_AUX_BYTES (2 * GRID_G * 8 + GRID_NC)   // occ, occT, cdist
 
-#define LAT_N 256                       // lattice extent (the reference's images are 224 x 224)
-#define LAT_W (LAT_N / 32)              // 32-bit words per row
-#define LAT_C 64                        // coarse cells per side (4 x 4 pixels each)
-#define LAT_BM_WORDS (LAT_N * LAT_W)
-#define LAT_BYTES (2 * LAT_BM_WORDS * 4 + LAT_N * 4 + LAT_C * LAT_C)   // bitmap, transposed bitmap, row prefix, coarse distances
-
-
-// One CTA per (set, image): set 0 = projected vertices, set 1 = silhouette pixels.  lat_ok[i] != 0: the pixels of
-// image i are searched on the lattice (k_mesh_ba_lat); only their bounding box is needed here.
+// One CTA per (set, image): set 0 = projected vertices, set 1 = silhouette pixels.
 __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restrict__ pts, const int *__restrict__ offsets,
                                                     const float *__restrict__ sil_pred, float *__restrict__ gparam,
                                                     int *__restrict__ gstart, float4 *__restrict__ sortedB,
@@ -178,6 +150,7 @@ __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restri
   __shared__ unsigned long long s_occ[GRID_G];
   __shared__ unsigned char s_hx[GRID_NC];
   int sel = blockIdx.x, i = blockIdx.y, t = threadIdx.x;
+  if (sel == 1 && lat_ok && lat_ok[i]) return;   // these pixels are searched on the lattice (k_mesh_lattice.cu), which also wrote their gparam
   int p0 = offsets[i];
   int n = sel == 0 ? V : offsets[i + 1] - p0;
   const float *src = sel == 0 ? sil_pred + (size_t)i * V * 2 : pts + (size_t)p0 * 2;
@@ -214,20 +187,6 @@ __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restri
   float ext = fmaxf(x1 - x0, y1 - y0);
   float h = ext > 0.f ? ext / GRID_G : 1.0f;
   float inv_h = 1.0f / h;
-  if (sel == 1 && lat_ok && lat_ok[i]) {
-    // (the pixel -> vertex search still takes max |a|^2 from here for its rounding margin)
-    if (t == 0) {
-      gp[0] = x0;
-      gp[1] = y0;
-      gp[2] = x1;
-      gp[3] = y1;
-      gp[4] = inv_h;
-      gp[5] = h;
-      gp[6] = fmaxf(x0 * x0, x1 * x1) + fmaxf(y0 * y0, y1 * y1);
-      gp[7] = 0.f;
-    }
-    return;
-  }
   for (int k = t; k < n; k += 256) {
     float x = src[2 * k], y = src[2 * k + 1];
     int cx = min(GRID_G - 1, max(0, (int)((x - x0) * inv_h)));
@@ -557,244 +516,6 @@ __global__ void __launch_bounds__(MT) k_mesh_ba(int V, const float *__restrict__
   if (ok) vdist[(size_t)i * V + b] = dist;
 }
 
-// ---- vertex -> nearest pixel on the pixel LATTICE ------------------------------------------------
-// The silhouette points of the reference are `where(seg > 0)` (src/trainer.py:443): integer (col, row) pairs in
-// row-major order.  Such a set is a BITMAP, and a nearest-pixel query needs no point list at all: candidates are
-// the set bits on square lattice rings around the query's own lattice point, their coordinates are implied by
-// the bit position, |a|^2 is an exact integer, and the index `where` gave a pixel is its rank in the bitmap
-// (row prefix + popcount).  Every candidate is compared with the SAME fp32 expansion as the full scan (smaller
-// index on equal values) and a ring is skipped only when all of its pixels are provably farther than the best
-// candidate by more than the expansion's rounding error, so the indices are those of the full scan, bit for bit.
-// Everything the walk reads sits in 20 KB of shared memory (the grid walk chased 16-byte point loads through L2).
-// k_lattice_build checks per image that the points ARE such a list (integers in [0, LAT_N)^2, strictly increasing in
-// row-major order); images that are not keep the binned-grid search.
-__global__ void __launch_bounds__(256) k_lattice_build(const float *__restrict__ pts, const int *__restrict__ offsets,
-                                                       unsigned char *__restrict__ lat, int *__restrict__ lat_ok) {
-  __shared__ unsigned bm[LAT_BM_WORDS], bmT[LAT_BM_WORDS];
-  __shared__ int scan[256];
-  __shared__ unsigned long long s_occ[LAT_C];
-  __shared__ unsigned char s_hx[LAT_C * LAT_C];
-  __shared__ int s_bad;
-  const int i = blockIdx.x, t = threadIdx.x;
-  const int p0 = offsets[i], np = offsets[i + 1] - p0;
-  for (int k = t; k < LAT_BM_WORDS; k += 256) bm[k] = bmT[k] = 0u;
-  if (t == 0) s_bad = 0;
-  __syncthreads();
-  int bad = 0;
-  for (int k = t; k < np; k += 256) {
-    const float x = pts[(size_t)(p0 + k) * 2], y = pts[(size_t)(p0 + k) * 2 + 1];
-    const int xi = (int)x, yi = (int)y;
-    if (!(x == (float)xi && y == (float)yi && xi >= 0 && xi < LAT_N && yi >= 0 && yi < LAT_N)) {
-      bad = 1;
-      continue;
-    }
-    if (k > 0) {   // strictly increasing (row, col): the list is the bitmap's own order, without duplicates
-      const float px = pts[(size_t)(p0 + k - 1) * 2], py = pts[(size_t)(p0 + k - 1) * 2 + 1];
-      if (!(py < y || (py == y && px < x))) bad = 1;
-    }
-    atomicOr(&bm[yi * LAT_W + (xi >> 5)], 1u << (xi & 31));
-    atomicOr(&bmT[xi * LAT_W + (yi >> 5)], 1u << (yi & 31));
-  }
-  if (bad) s_bad = 1;
-  __syncthreads();
-  unsigned char *out = lat + (size_t)i * LAT_BYTES;
-  unsigned *o_bm = reinterpret_cast<unsigned *>(out), *o_bmT = o_bm + LAT_BM_WORDS;
-  int *o_pref = reinterpret_cast<int *>(o_bmT + LAT_BM_WORDS);
-  unsigned char *o_cd = reinterpret_cast<unsigned char *>(o_pref + LAT_N);
-  for (int k = t; k < LAT_BM_WORDS; k += 256) {
-    o_bm[k] = bm[k];
-    o_bmT[k] = bmT[k];
-  }
-  // row prefix: pixels in the rows above (thread = row)
-  int cs = 0;
-  for (int w = 0; w < LAT_W; ++w) cs += __popc(bm[t * LAT_W + w]);
-  scan[t] = cs;
-  __syncthreads();
-  for (int o = 1; o < 256; o <<= 1) {
-    int v = t >= o ? scan[t - o] : 0;
-    __syncthreads();
-    scan[t] += v;
-    __syncthreads();
-  }
-  o_pref[t] = scan[t] - cs;
-  if (t == 255 && scan[255] != np) s_bad = 1;
-  // coarse occupancy (4 x 4 pixel cells) and its Chebyshev distance transform, as in k_grid_build
-  if (t < LAT_C) {
-    unsigned long long m = 0;
-    for (int cx = 0; cx < LAT_C; ++cx) {
-      unsigned any = 0;
-      for (int r = 0; r < 4; ++r) any |= (bm[(4 * t + r) * LAT_W + (cx >> 3)] >> (4 * (cx & 7))) & 0xFu;
-      m |= (unsigned long long)(any != 0) << cx;
-    }
-    s_occ[t] = m;
-  }
-  __syncthreads();
-  for (int k = t; k < LAT_C * LAT_C; k += 256) {
-    const int y = k / LAT_C, x = k % LAT_C;
-    const unsigned long long m = s_occ[y];
-    const unsigned long long left = m & (~0ull >> (63 - x)), right = m >> x;
-    int d = LAT_C;
-    if (left) d = x - (63 - __clzll((long long)left));
-    if (right) d = min(d, __ffsll((long long)right) - 1);
-    s_hx[k] = (unsigned char)d;
-  }
-  __syncthreads();
-  for (int k = t; k < LAT_C * LAT_C; k += 256) {
-    const int y = k / LAT_C, x = k % LAT_C;
-    int best = s_hx[k];
-    for (int dy = 1; dy < best; ++dy) {
-      if (y - dy >= 0) best = min(best, max(dy, (int)s_hx[(y - dy) * LAT_C + x]));
-      if (y + dy < LAT_C) best = min(best, max(dy, (int)s_hx[(y + dy) * LAT_C + x]));
-    }
-    o_cd[k] = (unsigned char)min(best, LAT_C);
-  }
-  __syncthreads();
-  if (t == 0) lat_ok[i] = s_bad ? 0 : 1;
-}
-
-#define LT 512   // threads per CTA of the lattice search (the tables are loaded once per CTA)
-__global__ void __launch_bounds__(LT) k_mesh_ba_lat(int V, const int *__restrict__ offsets, const float *__restrict__ sil_pred,
-                                                    float *__restrict__ vdist, float *__restrict__ d_sil,
-                                                    int *__restrict__ ind_ba, const float *__restrict__ gparam,
-                                                    const float4 *__restrict__ sortedB, const unsigned char *__restrict__ lat,
-                                                    const int *__restrict__ lat_ok) {
-  __shared__ __align__(16) unsigned char s_lat[LAT_BYTES];
-  const int i = blockIdx.y;
-  if (!lat_ok[i]) return;       // this image's points are not a row-major pixel list: k_mesh_ba<true> handles it
-  {
-    const uint4 *src = reinterpret_cast<const uint4 *>(lat + (size_t)i * LAT_BYTES);
-    for (int k = threadIdx.x; k < LAT_BYTES / 16; k += LT) reinterpret_cast<uint4 *>(s_lat)[k] = src[k];
-    __syncthreads();
-  }
-  const unsigned *bm = reinterpret_cast<const unsigned *>(s_lat), *bmT = bm + LAT_BM_WORDS;
-  const int *pref = reinterpret_cast<const int *>(bmT + LAT_BM_WORDS);
-  const unsigned char *cd = reinterpret_cast<const unsigned char *>(pref + LAT_N);
-  const int np = offsets[i + 1] - offsets[i];
-  const int slot = blockIdx.x * LT + threadIdx.x;
-  if (slot >= V) return;
-  // binned vertex order: the lanes of a warp query neighbouring positions
-  const int b = __float_as_int(sortedB[(size_t)i * V + slot].w);
-  const float bx = sil_pred[((size_t)i * V + b) * 2 + 0], by = sil_pred[((size_t)i * V + b) * 2 + 1];
-  const float b2 = __fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by));
-  float best = 3.4e38f;
-  int ai = -1, apx = 0, apy = 0;
-  if (np > 0) {
-    const float *gpB = gparam + ((size_t)i * 2 + 0) * GP_STRIDE;
-    // rounding error bound of the expansion, as in the grid search: magnitudes up to max(|a|^2, |b|^2)
-    const float margin = 32.0f * 5.9604645e-8f * fmaxf(2.0f * (LAT_N - 1) * (LAT_N - 1), gpB[6]);
-    const float qcx = fminf(fmaxf(bx, 0.0f), (float)(LAT_N - 1)), qcy = fminf(fmaxf(by, 0.0f), (float)(LAT_N - 1));
-    const float outside2 = (bx - qcx) * (bx - qcx) + (by - qcy) * (by - qcy);
-    const int gx = (int)rintf(qcx), gy = (int)rintf(qcy);
-    auto cand = [&](int px, int py) {
-      const float ax = (float)px, ay = (float)py;
-      const float a2 = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));
-      const float d = d2_expand(ax, ay, a2, bx, by, b2);
-      if (d <= best) {
-        // rank of the pixel in the row-major list
-        int id = pref[py];
-        const int w = px >> 5;
-        for (int q = 0; q < w; ++q) id += __popc(bm[py * LAT_W + q]);
-        id += __popc(bm[py * LAT_W + w] & ((1u << (px & 31)) - 1u));
-        if (d < best || id < ai) {
-          best = d;
-          ai = id;
-          apx = px;
-          apy = py;
-        }
-      }
-    };
-    // set bits lo..hi of the 256-bit line `line` of table tb; horizontal: line = row, bit = column
-    auto scan_line = [&](const unsigned *tb, int line, int lo, int hi, bool horizontal) {
-      if (best < 1e30f) {
-        // only the chord of the line inside the circle of the best candidate so far (+ the rounding margin) can matter
-        const float off = (float)line - (horizontal ? by : bx), mid = horizontal ? bx : by;
-        const float rem = best + margin - off * off;
-        if (rem < 0.0f) return;
-        const float w = sqrtf(rem) * 1.0001f + 1e-3f;
-        lo = max(lo, (int)ceilf(mid - w));
-        hi = min(hi, (int)floorf(mid + w));
-      }
-      if (lo > hi) return;
-      const int wa = lo >> 5, wb = hi >> 5;
-      for (int w = wa; w <= wb; ++w) {
-        unsigned bits = tb[line * LAT_W + w];
-        if (w == wa) bits &= ~0u << (lo & 31);
-        if (w == wb) bits &= ~0u >> (31 - (hi & 31));
-        while (bits) {
-          const int p = 32 * w + __ffs((int)bits) - 1;
-          bits &= bits - 1;
-          if (horizontal) cand(p, line);
-          else cand(line, p);
-        }
-      }
-    };
-    // every pixel lies in a coarse cell at Chebyshev distance >= c from the query's cell, i.e. on a lattice ring
-    // >= 4 (c - 1) + 1
-    const int c0 = cd[(gy >> 2) * LAT_C + (gx >> 2)];
-    int k = c0 >= 1 ? 4 * (c0 - 1) + 1 : 0;
-    const int kmax = max(max(gx, LAT_N - 1 - gx), max(gy, LAT_N - 1 - gy));
-    if (k == 0) {
-      if (bm[gy * LAT_W + (gx >> 5)] >> (gx & 31) & 1u) cand(gx, gy);
-      k = 1;
-    } else if (c0 >= 2) {
-      // A far query: before the walk, take the nearest pixel of the query's row and of its column (clamped to the
-      // bounding box of the pixels) as first candidates, so that the chord restriction applies from the first ring on.
-      const float *gpA = gparam + ((size_t)i * 2 + 1) * GP_STRIDE;
-      auto nearest_in_line = [&](const unsigned *tb, int line, int pos) {
-        int bp = -1, bd = 1 << 30;
-        for (int w = 0; w < LAT_W; ++w) {
-          const unsigned bits = tb[line * LAT_W + w];
-          if (!bits) continue;
-          const int base = 32 * w;
-          int pl = -1, ph = -1;
-          if (pos >= base + 32) pl = base + 31 - __clz((int)bits);
-          else if (pos < base) ph = base + __ffs((int)bits) - 1;
-          else {
-            const unsigned ml = bits & (~0u >> (31 - (pos - base))), mh = bits & (~0u << (pos - base));
-            if (ml) pl = base + 31 - __clz((int)ml);
-            if (mh) ph = base + __ffs((int)mh) - 1;
-          }
-          if (pl >= 0 && pos - pl < bd) { bd = pos - pl; bp = pl; }
-          if (ph >= 0 && ph - pos < bd) { bd = ph - pos; bp = ph; }
-        }
-        return bp;
-      };
-      const int ry = min(max(gy, (int)gpA[1]), (int)gpA[3]), rx = min(max(gx, (int)gpA[0]), (int)gpA[2]);
-      const int sx = nearest_in_line(bm, ry, gx);
-      if (sx >= 0) cand(sx, ry);
-      const int sy = nearest_in_line(bmT, rx, gy);
-      if (sy >= 0) cand(rx, sy);
-    }
-    for (; k <= kmax; ++k) {
-      // unvisited pixels are on rings >= k: |p - g|_inf >= k and |qc - g|_inf <= 0.5, so |qc - p| >= k - 0.5, and
-      // |q - p|^2 >= |q - qc|^2 + |qc - p|^2 (qc is the projection of q onto the lattice's box)
-      const float lb = (float)k - 0.5f;
-      if (lb * lb * 0.9999f + outside2 > best + margin) break;
-      const int xa = max(gx - k, 0), xb = min(gx + k, LAT_N - 1);
-      if (gy - k >= 0) scan_line(bm, gy - k, xa, xb, true);
-      if (gy + k < LAT_N) scan_line(bm, gy + k, xa, xb, true);
-      const int ya = max(gy - k + 1, 0), yb = min(gy + k - 1, LAT_N - 1);
-      if (gx - k >= 0) scan_line(bmT, gx - k, ya, yb, false);
-      if (gx + k < LAT_N) scan_line(bmT, gx + k, ya, yb, false);
-    }
-  }
-  float dist = 0.f, gxo = 0.f, gyo = 0.f;
-  if (ind_ba) ind_ba[(size_t)i * V + b] = ai;
-  if (ai >= 0) {
-    const float dx = bx - (float)apx, dy = by - (float)apy;
-    dist = sqrtf(dx * dx + dy * dy);
-    if (dist > 0.f) {
-      gxo = dx / dist;
-      gyo = dy / dist;
-    }
-  }
-  if (d_sil) {
-    d_sil[((size_t)i * V + b) * 2 + 0] = gxo;
-    d_sil[((size_t)i * V + b) * 2 + 1] = gyo;
-  }
-  vdist[(size_t)i * V + b] = dist;
-}
-
 // Per-image sum of the vertex->pixel distances in vertex-index order (fixed order: the same
 // bits whichever order the search visited the vertices in).
 __global__ void __launch_bounds__(256) k_mesh_rowsum(int V, const float *__restrict__ vdist, float *__restrict__ part) {
@@ -948,8 +669,9 @@ int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *of
   if (d_sil_pred) CUDA_TRY(cudaMemsetAsync(cnt_scratch, 0, (size_t)B * V * 2 * sizeof(int), c->cur));
   if (c->use_mesh_grid) {
     // grid workspace: per image and set 8 floats + GRID_NC + 1 ints, sorted copies of both point sets
+    const bool use_lat = c->use_mesh_lattice != 0;
     size_t need = (size_t)B * 2 * GP_STRIDE * 4 + (size_t)B * 2 * (GRID_NC + 1) * 4 + ((size_t)B * V + (size_t)P + 16) * 16 + 256 +
-                  (size_t)B * 2 * GRID_AUX_BYTES + 64 + (size_t)B * LAT_BYTES + (size_t)B * 4 + 64;
+                  (size_t)B * 2 * GRID_AUX_BYTES + 128 + mesh_lattice_workspace(B);
     if (need > c->ws_grid_cap) {
       CUDA_TRY(cudaStreamSynchronize(c->stream));
       if (c->ws_grid) CUDA_TRY(cudaFree(c->ws_grid));
@@ -963,21 +685,18 @@ int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *of
     float *gparam = (float *)(sortedA + P + 16);
     int *gstart = (int *)(gparam + (size_t)B * 2 * GP_STRIDE);
     unsigned char *gaux = (unsigned char *)(((uintptr_t)(gstart + (size_t)B * 2 * (GRID_NC + 1)) + 63) & ~(uintptr_t)63);
-    unsigned char *lat = (unsigned char *)(((uintptr_t)(gaux + (size_t)B * 2 * GRID_AUX_BYTES) + 63) & ~(uintptr_t)63);
-    int *lat_ok = (int *)(lat + (size_t)B * LAT_BYTES);
-    const bool use_lat = c->use_mesh_lattice != 0;
-    if (use_lat) LAUNCH(c, "mesh_lattice_build", B, 256, 0, k_lattice_build, pts, offsets, lat, lat_ok);
+    void *lat_ws = (void *)(((uintptr_t)(gaux + (size_t)B * 2 * GRID_AUX_BYTES) + 63) & ~(uintptr_t)63);
+    // vertex -> pixel: images whose points are a row-major pixel list (the reference's where(seg > 0)) are searched on
+    // the pixel lattice (k_mesh_lattice.cu); the CTAs of the binned-grid kernel return at once for those images.
+    int *lat_ok = nullptr;
+    if (use_lat) TRY(launch_mesh_lattice_build(c, B, pts, offsets, lat_ws, gparam, &lat_ok));
     LAUNCH(c, "mesh_grid_build", dim3(2, B), 256, 0, k_grid_build, V, pts, offsets, sil_pred, gparam, gstart, sortedB, sortedA,
-           gaux, use_lat ? lat_ok : (const int *)nullptr);
+           gaux, (const int *)lat_ok);
     LAUNCH(c, "mesh_nn_pixel_to_vertex_grid", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab<true>, V, pts, offsets, sil_pred,
            part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, gparam, gstart, sortedB, gaux);
-    // vertex -> pixel: on the pixel lattice where the points are a row-major pixel list (the reference's where(seg > 0)),
-    // through the binned grid for the other images (its CTAs return at once for the lattice images)
-    if (use_lat)
-      LAUNCH(c, "mesh_nn_vertex_to_pixel_lattice", dim3(cdiv(V, LT), B), LT, 0, k_mesh_ba_lat, V, offsets, sil_pred, c->ws_vdist,
-             d_sil_pred, ind_ba, gparam, sortedB, lat, lat_ok);
     LAUNCH(c, "mesh_nn_vertex_to_pixel_grid", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba<true>, V, pts, offsets, sil_pred,
-           c->ws_vdist, d_sil_pred, ind_ba, gparam, gstart, sortedA, sortedB, gaux, use_lat ? lat_ok : (const int *)nullptr);
+           c->ws_vdist, d_sil_pred, ind_ba, gparam, gstart, sortedA, sortedB, gaux, (const int *)lat_ok);
+    if (use_lat) TRY(launch_mesh_lattice_search(c, B, V, offsets, lat_ws, gparam, sortedB, c->ws_vdist, d_sil_pred, ind_ba));
   } else {
     LAUNCH(c, "mesh_nn_pixel_to_vertex", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab<false>, V, pts, offsets, sil_pred,
            part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, (const float *)nullptr, (const int *)nullptr,

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(SB_THREADS)
   int s0 = blockIdx.x * SB_ST;
   int ns = min(SB_ST, B - s0);
   int tiles_total = cdiv_dev(V, SB_VT);
-  int tiles_per = (tiles_total + VSPLIT - 1) / VSPLIT;
+  int tiles_per = (tiles_total + (int)gridDim.y - 1) / (int)gridDim.y;
   int t_begin = blockIdx.y * tiles_per;
   int t_end = min(tiles_total, t_begin + tiles_per);
 
@@ -390,7 +390,7 @@ int launch_skin_bwd(smplb_ctx *c, int B, const float *A, const float *v_posed, c
     CUDA_TRY(cudaFuncSetAttribute(k_skin_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SkinBwdSmem)));
     c->attr_done |= 1u;
   }
-  dim3 grid(cdiv(B, SB_ST), VSPLIT);
+  dim3 grid(cdiv(B, SB_ST), skin_bwd_splits(B));
   if (mode == 2) {
     LAUNCH(c, "skin_bwd_active", grid, SB_THREADS, sizeof(SkinBwdSmem), k_skin_bwd, B, c->n_act, c->n_act, c->K, c->Vpa,
            c->Vpa, (const int *)nullptr, c->d_act_W, A, v_posed, (const float *)nullptr, d_joints, c->d_acsr_off,

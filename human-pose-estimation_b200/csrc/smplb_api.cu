@@ -224,7 +224,7 @@ static int ensure_ws(smplb_ctx *c, int B) {
   WS_ALLOC(ws_kp, nb * c->K * 2);
   WS_ALLOC(ws_dkp, nb * c->K * 2);
   WS_ALLOC(ws_djoints, nb * c->K * 3);
-  WS_ALLOC(ws_dA, (size_t)VSPLIT * nb * NJ * 12);
+  WS_ALLOC(ws_dA, skin_bwd_part_rows((int)nb) * NJ * 12);
   WS_ALLOC(ws_dx, (size_t)c->ksplit * (nb + 128) * KX);   // split-K partials: up to 16 x (B rounded up to 128) rows
   WS_ALLOC(ws_part, nb);
   WS_ALLOC(ws_cnt, nb);
@@ -911,7 +911,7 @@ static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const fl
   int dx_rows = B;
   if (bwd_tc) TRY(launch_blend_bwd_tc(c, B, c->ws_dp16, c->ws_dx, &ks, &dx_rows));
   else TRY(launch_blend_bwd(c, B, dp, c->ws_dx, compact, ks));
-  TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, VSPLIT, c->ws_dx, ks, dx_rows, nullptr, d_Rs,
+  TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, skin_bwd_splits(B), c->ws_dx, ks, dx_rows, nullptr, d_Rs,
                       d_beta, d_theta));
   return 0;
 }

@@ -14,7 +14,17 @@
 #define NJ 24          // SMPL joints
 #define NPF 207        // pose-feature length, 23 * 9
 #define KX 224         // padded length of x_ext = [pose_feature(207) | beta(NB) | 1 | 0...]
-#define VSPLIT 4       // vertex-range splits of the skinning backward (fixed-order partial sums)
+#define VSPLIT 4       // vertex-range splits of the skinning backward at large batches (fixed-order partial sums)
+#define VSPLIT_MAX 16  // ... and at small ones: CTAs = (B / 16) x splits, so B = 1024 gets 16 splits (1024 CTAs instead of 256)
+static inline int skin_bwd_splits(int B) {
+  if (B >= 4096) return VSPLIT;
+  int s = 16384 / (B > 0 ? B : 1);
+  return s < VSPLIT ? VSPLIT : (s > VSPLIT_MAX ? VSPLIT_MAX : s);
+}
+static inline size_t skin_bwd_part_rows(int max_batch) {   // rows of [24 x 12] the partial-sum buffer needs for any B <= max_batch
+  size_t a = (size_t)VSPLIT * max_batch, b = (size_t)(max_batch < 1024 ? (size_t)VSPLIT_MAX * max_batch : 16384);
+  return a > b ? a : b;
+}
 #define MAXK SMPLB_MAX_KEYPOINTS
 
 struct Tree {
@@ -173,7 +183,7 @@ struct smplb_ctx {
   alignas(64) unsigned char map_dbf[128];
   bool blend_bwd_tc_ok = false;
   int use_blend_bwd_tc = 1;    // smplb_debug_set("blend_bwd_tc", 0): FP32 CUDA-core GEMM (cross-check)
-  float *ws_dA = nullptr;      // [VSPLIT][B][288]
+  float *ws_dA = nullptr;      // [skin_bwd_splits(B)][B][288]
   float *ws_dx = nullptr;      // [ksplit][B][KX]
   float *ws_part = nullptr;    // per-body / per-block float partials
   int *ws_cnt = nullptr;       // per-body int partials
@@ -316,6 +326,11 @@ int launch_fold_bwd(smplb_ctx *c, int B, const float *A, const float *d_joints, 
 int launch_fold_step(smplb_ctx *c, int B, const float *A, const float *cam, const float *kp_gt, float *joints,
                      float *kp_pred, float *part, int *cnt, float *d_cam, float *dA_part, float *dx_part, int ksplit);
 int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long long count_override, float *loss_parts);
+// k_mesh_lattice.cu
+size_t mesh_lattice_workspace(int B);
+int launch_mesh_lattice_build(smplb_ctx *c, int B, const float *pts, const int *offsets, void *ws, float *gparam, int **lat_ok_out);
+int launch_mesh_lattice_search(smplb_ctx *c, int B, int V, const int *offsets, const void *ws, const float *gparam,
+                               const float4 *sortedB, float *vdist, float *d_sil, int *ind_ba);
 // k_gemm_tc.cu
 int tc_make_map(void *map, int is_f32, const void *ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                 uint32_t box_inner, uint32_t box_outer, int swizzle = 1);
