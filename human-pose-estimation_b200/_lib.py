@@ -90,6 +90,25 @@ STEP_KEEP_VERTS = 1
 _lib = None
 
 
+def _point_at_bundled_nccl():
+    """smplb_comm_init dlopens NCCL.  If this interpreter has a PyTorch with its own libnccl.so.2 (the nvidia-nccl wheel),
+    name THAT file in SMPLB_NCCL_LIB: the first libnccl.so.2 mapped into a process serves every later request for the
+    soname, and a torch imported after a comm_init that picked the (older) system library fails to resolve its
+    symbols.  No torch import here; a process without the wheel keeps the system library."""
+    if os.environ.get("SMPLB_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.isfile(cand):
+                os.environ["SMPLB_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def lib():
     """The loaded library; raises if libsmplb.so has not been built
     (`python -c "import __graft_entry__ as g; g.build()"` or `make -C csrc`)."""
@@ -98,6 +117,7 @@ def lib():
         if not os.path.isfile(LIB_PATH):
             raise ImportError("libsmplb.so not found at %s: build it with __graft_entry__.build(); "
                               "there is no CPU fallback" % LIB_PATH)
+        _point_at_bundled_nccl()
         l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
         for name, args in list(SIGNATURES.items()) + list(PRIVATE_SIGNATURES.items()):
             f = getattr(l, name)

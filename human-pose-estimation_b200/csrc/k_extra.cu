@@ -49,36 +49,70 @@ __global__ void __launch_bounds__(1024) k_sil_scan(int B, const int *__restrict_
   if (t == 0) offsets[B] = carry;
 }
 
-// points[offsets[i] + rank] = (x = col, y = row) of the rank-th pixel > 0 in row-major order.
+// points[offsets[i] + rank] = (x = col, y = row) of the rank-th pixel > 0 in row-major order.  Warp w owns a
+// contiguous strip of the image and walks it 128 pixels (one float4 per lane) at a time: a counting pass, the strips'
+// bases from one shared-memory exchange, then a writing pass whose ranks come from a warp scan -- coalesced loads, no
+// block barrier inside the loops (the version with three barriers per 256 pixels took 0.18 ms at B = 1024).
 __global__ void __launch_bounds__(256) k_sil_fill(int H, int W, const float *__restrict__ seg,
                                                   const int *__restrict__ offsets, int cap, float *__restrict__ points) {
   __shared__ int wsum[8];
-  __shared__ int base;
-  int i = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-  int HW = H * W;
+  const int i = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int HW = H * W;
   const float *s = seg + (size_t)i * HW;
-  if (t == 0) base = offsets[i];
+  const int strip = ((HW + 7) / 8 + 127) & ~127;      // pixels per warp, a multiple of 128
+  const int k0 = min(w * strip, HW), k1 = min(k0 + strip, HW);
+  const bool vec = (reinterpret_cast<uintptr_t>(s) & 15) == 0;
+  // the flags of this lane's four pixels k .. k + 3 as bits 0..3
+  auto flags4 = [&](int k) {
+    unsigned f = 0;
+    if (vec && k + 4 <= k1) {
+      const float4 v = *reinterpret_cast<const float4 *>(s + k);
+      f = (unsigned)(v.x > 0.0f) | (unsigned)(v.y > 0.0f) << 1 | (unsigned)(v.z > 0.0f) << 2 | (unsigned)(v.w > 0.0f) << 3;
+    } else {
+      for (int j = 0; j < 4; ++j)
+        if (k + j < k1) f |= (unsigned)(s[k + j] > 0.0f) << j;
+    }
+    return f;
+  };
+  int c = 0;
+  for (int k = k0 + 4 * lane; k < k1; k += 128) c += __popc(flags4(k));
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+  if (lane == 0) wsum[w] = c;
   __syncthreads();
-  for (int k0 = 0; k0 < HW; k0 += 256) {
-    int k = k0 + t;
-    bool on = k < HW && s[k] > 0.0f;
-    unsigned m = __ballot_sync(FULL, on);
-    int rank_in_warp = __popc(m & ((1u << lane) - 1));
-    if (lane == 0) wsum[w] = __popc(m);
-    __syncthreads();
-    int before = 0, total = 0;
-    for (int q = 0; q < 8; ++q) {
-      if (q < w) before += wsum[q];
-      total += wsum[q];
+  int pos = offsets[i];
+  for (int q = 0; q < w; ++q) pos += wsum[q];
+  if (c == 0) return;
+  const bool p8 = (reinterpret_cast<uintptr_t>(points) & 7) == 0;
+  for (int kb = k0; kb < k1; kb += 128) {
+    const int k = kb + 4 * lane;
+    const unsigned f = k < k1 ? flags4(k) : 0u;
+    const int n = __popc(f);
+    int incl = n;                                    // inclusive warp scan of the per-lane counts
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
     }
-    int pos = base + before + rank_in_warp;
-    if (on && pos < cap) {
-      points[2 * (size_t)pos + 0] = (float)(k % W);   // x = column  (ops.py:123: silhouette_gt[:, 2])
-      points[2 * (size_t)pos + 1] = (float)(k / W);   // y = row     (ops.py:124: silhouette_gt[:, 1])
+    int p = pos + incl - n;
+    int row = k / W, col = k - row * W;
+    for (int j = 0; j < 4; ++j) {
+      if (f >> j & 1u) {
+        if (p < cap) {
+          // x = column (ops.py:123: silhouette_gt[:, 2]), y = row (ops.py:124: silhouette_gt[:, 1])
+          if (p8) {
+            *reinterpret_cast<float2 *>(points + 2 * (size_t)p) = make_float2((float)col, (float)row);
+          } else {
+            points[2 * (size_t)p + 0] = (float)col;
+            points[2 * (size_t)p + 1] = (float)row;
+          }
+        }
+        ++p;
+      }
+      if (++col == W) {
+        col = 0;
+        ++row;
+      }
     }
-    __syncthreads();
-    if (t == 0) base += total;
-    __syncthreads();
+    pos += __shfl_sync(FULL, incl, 31);
   }
 }
 

@@ -1498,8 +1498,12 @@ static struct {
 
 static int nccl_load() {
   if (g_nccl.lib) return 0;
-  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  // SMPLB_NCCL_LIB names the library to use.  The Python facade sets it to the NCCL that ships with the process's
+  // PyTorch (when there is one): whichever libnccl.so.2 is mapped first serves every later request for that soname,
+  // and a PyTorch imported AFTER this call needs its own, newer one.
+  const char *names[] = {getenv("SMPLB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   for (const char *n : names) {
+    if (!n || !*n) continue;
     g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
     if (g_nccl.lib) break;
   }
