@@ -2,6 +2,7 @@
 (a typed handle to device memory from smplb_malloc) and pinned host arrays.
 numpy is the only dependency; there is no torch/cupy in the product."""
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -63,12 +64,16 @@ def pinned_empty(shape, dtype=np.float32):
     p = C.c_void_p()
     check(lib().smplb_host_alloc(C.byref(p), max(n, 1)))
     buf = (C.c_char * max(n, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape).view(PinnedArray)
-    _PINNED_KEEP[arr.ctypes.data] = p.value
-    return arr
+    # every view of the array keeps `buf` alive; the page-locked block goes back when the last one is gone
+    weakref.finalize(buf, _host_free, p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape).view(PinnedArray)
 
 
-_PINNED_KEEP = {}
+def _host_free(ptr):
+    try:
+        lib().smplb_host_free(C.c_void_p(ptr))
+    except Exception:
+        pass
 
 
 def _as_f32(x):
