@@ -491,6 +491,13 @@ __global__ void __launch_bounds__(32 * FS_WARPS)
     m = fmaxf(m, fmaxf(fabsf(du0), fmaxf(fabsf(du1), fabsf(du2))));
     const float *uk = u + k * NJ * 3;
     float u4[4] = {uk[0], uk[1], uk[2], cc[k * NJ + j]};
+    if (lane < NJ) {
+      // u_kj has been read: its three floats now stage du_kj (unit row scale) for the coalesced fp16 row below
+      float *d = sU[w] + (k * NJ + j) * 3;
+      d[0] = du0;
+      d[1] = du1;
+      d[2] = du2;
+    }
     float gg[3] = {g0, g1, g2};
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -514,25 +521,14 @@ __global__ void __launch_bounds__(32 * FS_WARPS)
 #pragma unroll
     for (int q = 0; q < 12; ++q) o[q] = acc[q];
   }
-  // du16 row = hi | lo | hi (three blocks of nup halves): stage the fp32 values in the U buffer
-  // (no longer needed) and write the row with coalesced 4-byte stores instead of 2-byte
-  // stores 144 B apart
-  __syncwarp();
-  if (lane < NJ) {
-    for (int k = 0; k < K; ++k) {
-      float g0 = sdj[w][3 * k], g1 = sdj[w][3 * k + 1], g2 = sdj[w][3 * k + 2];
-      int n = (k * NJ + j) * 3;
-      sU[w][n + 0] = (ar[0] * g0 + ar[3] * g1 + ar[6] * g2) * inv;
-      sU[w][n + 1] = (ar[1] * g0 + ar[4] * g1 + ar[7] * g2) * inv;
-      sU[w][n + 2] = (ar[2] * g0 + ar[5] * g1 + ar[8] * g2) * inv;
-    }
-  }
+  // du16 row = hi | lo | hi (three blocks of nup halves) from the staged fp32 values, scaled by the row's power of
+  // two (exact), with coalesced 4-byte stores instead of 2-byte stores 144 B apart
   __syncwarp();
   {
     __half2 *row = reinterpret_cast<__half2 *>(du16 + (size_t)b * (3 * nup));
     const int nu = K * NJ * 3, half_nup = nup / 2;
     for (int i = lane; i < half_nup; i += 32) {
-      float v0 = 2 * i < nu ? sU[w][2 * i] : 0.f, v1 = 2 * i + 1 < nu ? sU[w][2 * i + 1] : 0.f;
+      float v0 = 2 * i < nu ? sU[w][2 * i] * inv : 0.f, v1 = 2 * i + 1 < nu ? sU[w][2 * i + 1] * inv : 0.f;
       __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
       __half2 hi = __halves2half2(h0, h1);
       __half2 lo = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
