@@ -343,8 +343,9 @@ def single_gpu_configs(smpl, model, peaks, sampler):
                  "kernels_ms_per_step": kms,
                  "mesh_search": {"ms": mesh_ms, "reference_pairs_per_step": pairs,
                                  "reference_equivalent_pairs_per_s": pairs / (mesh_ms * 1e-3) if mesh_ms else None,
-                                 "note": "uniform-grid search returning the brute-force scan's indices bit for bit; pairs counted as "
-                                         "the reference's full scan (ops.py:60-71)"},
+                                 "note": "pixel -> vertex on a binned grid, vertex -> pixel on the silhouette bitmap, both returning the "
+                                         "brute-force scan's indices bit for bit; pairs counted as the reference's full scan "
+                                         "(ops.py:60-71)"},
                  "mesh_brute_force": {"images": sub, "ms": ms_bf, "pairs_per_s": pairs_bf / (ms_bf * 1e-3),
                                       "fma_issue_peak_per_s": fma_peak,
                                       "frac_of_fma_issue_peak_at_7_instr_per_pair": 7 * pairs_bf / (ms_bf * 1e-3) / fma_peak},
