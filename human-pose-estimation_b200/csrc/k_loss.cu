@@ -138,19 +138,22 @@ __global__ void k_finalize_loss(float w_kp, float w_mesh, long long count_overri
 // is unchanged, so the result stays bit-identical to the full scan.
 #define GRID_AUX_BYTES (2 * GRID_G * 8 + GRID_NC)   // occ, occT, cdist
 
-// One CTA per (set, image): set 0 = projected vertices, set 1 = silhouette pixels.
+// One CTA per (set, image): set 0 = projected vertices, set 1 = silhouette pixels (the two CTAs of an image run side by
+// side: building the pixel tables in a launch of its own cost as much as this one).
 __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restrict__ pts, const int *__restrict__ offsets,
                                                     const float *__restrict__ sil_pred, float *__restrict__ gparam,
                                                     int *__restrict__ gstart, float4 *__restrict__ sortedB,
                                                     float4 *__restrict__ sortedA, unsigned char *__restrict__ gaux,
-                                                    const int *__restrict__ lat_ok) {
+                                                    unsigned char *__restrict__ lat, int *__restrict__ lat_ok) {
   __shared__ float red[4][256];
   __shared__ int hist[GRID_NC];
   __shared__ int scan[256];
   __shared__ unsigned long long s_occ[GRID_G];
-  __shared__ unsigned char s_hx[GRID_NC];
+  __shared__ unsigned long long s_tmp[GRID_G];
   int sel = blockIdx.x, i = blockIdx.y, t = threadIdx.x;
-  if (sel == 1 && lat_ok && lat_ok[i]) return;   // these pixels are searched on the lattice (k_mesh_lattice.cu), which also wrote their gparam
+  // the pixel set: tables for the lattice search first (k_mesh_lattice.cu); if the points are a row-major pixel list
+  // that is all this image's pixels need, otherwise they are binned like the vertices
+  if (sel == 1 && lat && lattice_build_image(i, pts, offsets, lat, lat_ok, gparam)) return;
   int p0 = offsets[i];
   int n = sel == 0 ? V : offsets[i + 1] - p0;
   const float *src = sel == 0 ? sil_pred + (size_t)i * V * 2 : pts + (size_t)p0 * 2;
@@ -211,29 +214,9 @@ __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restri
       occT[x] = m;
     }
     __syncthreads();
-    // hx[y][x]: distance along the row to the nearest non-empty cell (GRID_G if the row is empty)
-    for (int k = t; k < GRID_NC; k += 256) {
-      const int y = k / GRID_G, x = k % GRID_G;
-      const unsigned long long m = s_occ[y];
-      const unsigned long long left = m & (~0ull >> (63 - x)), right = m >> x;
-      int d = GRID_G;
-      if (left) d = x - (63 - __clzll((long long)left));
-      if (right) d = min(d, __ffsll((long long)right) - 1);
-      s_hx[k] = (unsigned char)d;
-    }
-    __syncthreads();
-    // cdist[y][x] = min over rows y' of max(|y - y'|, hx[y'][x]), walked outwards with early exit
-    for (int k = t; k < GRID_NC; k += 256) {
-      const int y = k / GRID_G, x = k % GRID_G;
-      int best = s_hx[k];
-      for (int dy = 1; dy < best; ++dy) {
-        if (y - dy >= 0) best = min(best, max(dy, (int)s_hx[(y - dy) * GRID_G + x]));
-        if (y + dy < GRID_G) best = min(best, max(dy, (int)s_hx[(y + dy) * GRID_G + x]));
-      }
-      cdist[k] = (unsigned char)min(best, GRID_G);
-    }
+    static_assert(GRID_G == 64, "chebyshev_cells64 is written for 64 x 64 cells");
+    chebyshev_cells64(s_occ, s_tmp, cdist);
   }
-  __syncthreads();
   // exclusive scan of the cell counts: GRID_NC / 256 cells per thread + block scan
   constexpr int CPT = GRID_NC / 256;
   int cs = 0;
@@ -710,10 +693,10 @@ int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *of
     void *lat_ws = (void *)(((uintptr_t)(gaux + (size_t)B * 2 * GRID_AUX_BYTES) + 63) & ~(uintptr_t)63);
     // vertex -> pixel: images whose points are a row-major pixel list (the reference's where(seg > 0)) are searched on
     // the pixel lattice (k_mesh_lattice.cu); the CTAs of the binned-grid kernel return at once for those images.
-    int *lat_ok = nullptr;
-    if (use_lat) TRY(launch_mesh_lattice_build(c, B, pts, offsets, lat_ws, gparam, &lat_ok));
+    unsigned char *lat = use_lat ? (unsigned char *)lat_ws : nullptr;
+    int *lat_ok = use_lat ? (int *)(lat + (size_t)B * LAT_BYTES) : nullptr;
     LAUNCH(c, "mesh_grid_build", dim3(2, B), 256, 0, k_grid_build, V, pts, offsets, sil_pred, gparam, gstart, sortedB, sortedA,
-           gaux, (const int *)lat_ok);
+           gaux, lat, lat_ok);
     LAUNCH(c, "mesh_nn_pixel_to_vertex_grid", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab<true>, V, pts, offsets, sil_pred,
            part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, gparam, gstart, sortedB, gaux);
     LAUNCH(c, "mesh_nn_vertex_to_pixel_grid", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba<true>, V, pts, offsets, sil_pred,

@@ -19,45 +19,6 @@
 // 0.19 ms for the grid build, and the row-major vertex order made THIS kernel slower; dropped.)
 #include "mesh_common.cuh"
 
-// Chebyshev distance (in coarse cells of 4 x 4 lattice points) from every coarse cell to the nearest non-empty one,
-// from a row-major bitmap in shared memory.  256 threads; s_occ / s_hx are scratch.
-__device__ __forceinline__ void coarse_distance(const unsigned *bm, unsigned long long *s_occ, unsigned char *s_hx,
-                                                unsigned char *out_cd) {
-  const int t = threadIdx.x;
-  if (t < LAT_C) {
-    unsigned long long m = 0;
-    for (int cx = 0; cx < LAT_C; ++cx) {
-      unsigned any = 0;
-      for (int r = 0; r < 4; ++r) any |= (bm[(4 * t + r) * LAT_W + (cx >> 3)] >> (4 * (cx & 7))) & 0xFu;
-      m |= (unsigned long long)(any != 0) << cx;
-    }
-    s_occ[t] = m;
-  }
-  __syncthreads();
-  // hx[y][x]: distance along the row to the nearest non-empty cell (LAT_C if the row is empty)
-  for (int k = t; k < LAT_C * LAT_C; k += 256) {
-    const int y = k / LAT_C, x = k % LAT_C;
-    const unsigned long long m = s_occ[y];
-    const unsigned long long left = m & (~0ull >> (63 - x)), right = m >> x;
-    int d = LAT_C;
-    if (left) d = x - (63 - __clzll((long long)left));
-    if (right) d = min(d, __ffsll((long long)right) - 1);
-    s_hx[k] = (unsigned char)d;
-  }
-  __syncthreads();
-  // cd[y][x] = min over rows y' of max(|y - y'|, hx[y'][x]), walked outwards with early exit
-  for (int k = t; k < LAT_C * LAT_C; k += 256) {
-    const int y = k / LAT_C, x = k % LAT_C;
-    int best = s_hx[k];
-    for (int dy = 1; dy < best; ++dy) {
-      if (y - dy >= 0) best = min(best, max(dy, (int)s_hx[(y - dy) * LAT_C + x]));
-      if (y + dy < LAT_C) best = min(best, max(dy, (int)s_hx[(y + dy) * LAT_C + x]));
-    }
-    out_cd[k] = (unsigned char)min(best, LAT_C);
-  }
-  __syncthreads();
-}
-
 // Nearest set bit to `pos` in the 256-bit line `line` of table tb (-1: the line is empty).
 __device__ __forceinline__ int nearest_in_line(const unsigned *tb, int line, int pos) {
   int bp = -1, bd = 1 << 30;
@@ -83,93 +44,6 @@ __device__ __forceinline__ int nearest_in_line(const unsigned *tb, int line, int
     }
   }
   return bp;
-}
-
-// ------------------------------------------------------------------------------ pixel tables
-// One CTA per image: bitmap, transposed bitmap, row prefix, coarse distances (LAT_BYTES), the bounding box of the
-// pixels (gparam of set 1, as k_grid_build writes it) and lat_ok[i].
-__global__ void __launch_bounds__(256) k_lattice_build(const float *__restrict__ pts, const int *__restrict__ offsets,
-                                                       unsigned char *__restrict__ lat, int *__restrict__ lat_ok,
-                                                       float *__restrict__ gparam) {
-  __shared__ unsigned bm[LAT_BM_WORDS], bmT[LAT_BM_WORDS];
-  __shared__ int scan[256];
-  __shared__ unsigned long long s_occ[LAT_C];
-  __shared__ unsigned char s_hx[LAT_C * LAT_C];
-  __shared__ int s_bad, s_box[4];
-  const int i = blockIdx.x, t = threadIdx.x;
-  const int p0 = offsets[i], np = offsets[i + 1] - p0;
-  for (int k = t; k < LAT_BM_WORDS; k += 256) bm[k] = bmT[k] = 0u;
-  if (t == 0) {
-    s_bad = 0;
-    s_box[0] = s_box[1] = LAT_N;
-    s_box[2] = s_box[3] = -1;
-  }
-  __syncthreads();
-  int bad = 0;
-  for (int k = t; k < np; k += 256) {
-    const float x = pts[(size_t)(p0 + k) * 2], y = pts[(size_t)(p0 + k) * 2 + 1];
-    const int xi = (int)x, yi = (int)y;
-    if (!(x == (float)xi && y == (float)yi && xi >= 0 && xi < LAT_N && yi >= 0 && yi < LAT_N)) {
-      bad = 1;
-      continue;
-    }
-    if (k > 0) {   // strictly increasing (row, col): the list is the bitmap's own order, without duplicates
-      const float px = pts[(size_t)(p0 + k - 1) * 2], py = pts[(size_t)(p0 + k - 1) * 2 + 1];
-      if (!(py < y || (py == y && px < x))) bad = 1;
-    }
-    atomicOr(&bm[yi * LAT_W + (xi >> 5)], 1u << (xi & 31));
-    atomicOr(&bmT[xi * LAT_W + (yi >> 5)], 1u << (yi & 31));
-  }
-  if (bad) s_bad = 1;
-  __syncthreads();
-  unsigned char *out = lat + (size_t)i * LAT_BYTES;
-  unsigned *o_bm = reinterpret_cast<unsigned *>(out), *o_bmT = o_bm + LAT_BM_WORDS;
-  int *o_pref = reinterpret_cast<int *>(o_bmT + LAT_BM_WORDS);
-  unsigned char *o_cd = reinterpret_cast<unsigned char *>(o_pref + LAT_N);
-  for (int k = t; k < LAT_BM_WORDS; k += 256) {
-    o_bm[k] = bm[k];
-    o_bmT[k] = bmT[k];
-  }
-  // row prefix: pixels in the rows above (thread = row); bounding box from the non-empty rows / columns
-  int cs = 0, ccol = 0;
-  for (int w = 0; w < LAT_W; ++w) {
-    cs += __popc(bm[t * LAT_W + w]);
-    ccol |= bmT[t * LAT_W + w] != 0u;
-  }
-  if (cs) {
-    atomicMin(&s_box[1], t);
-    atomicMax(&s_box[3], t);
-  }
-  if (ccol) {
-    atomicMin(&s_box[0], t);
-    atomicMax(&s_box[2], t);
-  }
-  scan[t] = cs;
-  __syncthreads();
-  for (int o = 1; o < 256; o <<= 1) {
-    int v = t >= o ? scan[t - o] : 0;
-    __syncthreads();
-    scan[t] += v;
-    __syncthreads();
-  }
-  o_pref[t] = scan[t] - cs;
-  if (t == 255 && scan[255] != np) s_bad = 1;
-  coarse_distance(bm, s_occ, s_hx, o_cd);
-  if (t == 0) {
-    lat_ok[i] = s_bad ? 0 : 1;
-    float *gp = gparam + ((size_t)i * 2 + 1) * GP_STRIDE;
-    const bool any = s_box[2] >= 0;
-    const float x0 = any ? (float)s_box[0] : 0.f, y0 = any ? (float)s_box[1] : 0.f;
-    const float x1 = any ? (float)s_box[2] : 0.f, y1 = any ? (float)s_box[3] : 0.f;
-    gp[0] = x0;
-    gp[1] = y0;
-    gp[2] = x1;
-    gp[3] = y1;
-    gp[4] = 1.0f;
-    gp[5] = 1.0f;
-    gp[6] = x1 * x1 + y1 * y1;   // max |a|^2 (coordinates are >= 0)
-    gp[7] = 0.f;
-  }
 }
 
 // rounding-error bound of the expansion (magnitudes up to max(|a|^2, |b|^2)), as in the grid search of k_loss.cu
@@ -326,16 +200,6 @@ __global__ void __launch_bounds__(LT) k_mesh_ba_lat(int V, const int *__restrict
 
 // ------------------------------------------------------------------------------------- host
 size_t mesh_lattice_workspace(int B) { return (size_t)B * LAT_BYTES + (size_t)B * 4 + 256; }
-
-// Tables of the pixel sets (and their bounding boxes in gparam) + lat_ok[i] for every image, written into `ws`
-// (mesh_lattice_workspace bytes, 64-byte aligned).
-int launch_mesh_lattice_build(smplb_ctx *c, int B, const float *pts, const int *offsets, void *ws, float *gparam, int **lat_ok_out) {
-  unsigned char *lat = (unsigned char *)ws;
-  int *lat_ok = (int *)(lat + (size_t)B * LAT_BYTES);
-  LAUNCH(c, "mesh_lattice_build", B, 256, 0, k_lattice_build, pts, offsets, lat, lat_ok, gparam);
-  *lat_ok_out = lat_ok;
-  return 0;
-}
 
 // sortedB: the vertices in the binned order of k_grid_build (neighbouring lanes query neighbouring positions)
 int launch_mesh_lattice_search(smplb_ctx *c, int B, int V, const int *offsets, const void *ws, const float *gparam,

@@ -32,3 +32,143 @@ __device__ __forceinline__ float d2_expand(float ax, float ay, float a2, float b
 #define LAT_BYTES (2 * LAT_BM_WORDS * 4 + LAT_N * 4 + LAT_C * LAT_C)   // bitmap, transposed bitmap, row prefix, coarse distances
 
 
+
+// Chebyshev distance, in cells, from every cell of a 64 x 64 grid to the nearest occupied one (64 if none is):
+// out[64 y + x] = number of 3 x 3 dilations of the occupancy mask that it takes to reach cell (x, y).  occ[y] holds row y
+// (bit x = cell occupied; destroyed), tmp[64] is scratch; rows are walked by threads 0..63, the whole CTA (256 threads)
+// must call.  (The first version took, per cell, the minimum over rows of max(row distance, distance along that row)
+// with an early exit: 56 % of the build kernel's time for the cells far from every point.)
+__device__ __forceinline__ void chebyshev_cells64(unsigned long long *occ, unsigned long long *tmp, unsigned char *out) {
+  const int t = threadIdx.x;
+  for (int k = t; k < 64 * 64; k += 256) out[k] = (occ[k >> 6] >> (k & 63) & 1ull) ? 0 : 64;
+  // (barrier: the fill above is ordered before the rows' own writes below; nothing occupied: every cell keeps 64)
+  if (__syncthreads_or(t < 64 && occ[t] != 0ull) == 0) return;
+  unsigned long long *cur = occ, *nxt = tmp;
+  for (int k = 1; k < 64; ++k) {
+    bool open = false;
+    if (t < 64) {
+      const unsigned long long a = cur[t];
+      const unsigned long long u = a | (t > 0 ? cur[t - 1] : 0ull) | (t < 63 ? cur[t + 1] : 0ull);
+      const unsigned long long d = u | (u << 1) | (u >> 1);
+      nxt[t] = d;
+      for (unsigned long long nw = d & ~a; nw; nw &= nw - 1) out[64 * t + __ffsll((long long)nw) - 1] = (unsigned char)k;
+      open = d != ~0ull;
+    }
+    const int more = __syncthreads_or(open);
+    unsigned long long *sw = cur;
+    cur = nxt;
+    nxt = sw;
+    if (!more) break;
+  }
+  __syncthreads();
+}
+
+// The same for the coarse cells (4 x 4 lattice points each) of a row-major 256 x 256 bitmap in shared memory.
+__device__ __forceinline__ void coarse_distance(const unsigned *bm, unsigned long long *s_occ, unsigned long long *s_tmp,
+                                                unsigned char *out_cd) {
+  const int t = threadIdx.x;
+  {
+    // thread t: 16 cells of row t / 4
+    const int y = t >> 2, c0 = (t & 3) * 16;
+    unsigned m = 0;
+    for (int cx = c0; cx < c0 + 16; ++cx) {
+      unsigned any = 0;
+      for (int r = 0; r < 4; ++r) any |= (bm[(4 * y + r) * LAT_W + (cx >> 3)] >> (4 * (cx & 7))) & 0xFu;
+      m |= (unsigned)(any != 0) << (cx - c0);
+    }
+    reinterpret_cast<unsigned short *>(s_occ)[4 * y + (t & 3)] = (unsigned short)m;   // little-endian: bits c0 .. c0 + 15 of row y
+  }
+  __syncthreads();
+  chebyshev_cells64(s_occ, s_tmp, out_cd);
+}
+
+// Pixel tables of image i for the lattice search (k_mesh_lattice.cu), built by the 256 threads of one CTA: bitmap,
+// transposed bitmap, row prefix, coarse distances (LAT_BYTES at lat + i * LAT_BYTES), the bounding box of the pixels
+// (gparam of set 1, as k_grid_build writes it) and lat_ok[i] = the points ARE a row-major pixel list (integers in
+// [0, LAT_N)^2, strictly increasing).  Returns lat_ok[i] to every thread.
+__device__ __forceinline__ bool lattice_build_image(int i, const float *__restrict__ pts, const int *__restrict__ offsets,
+                                                    unsigned char *__restrict__ lat, int *__restrict__ lat_ok,
+                                                    float *__restrict__ gparam) {
+  __shared__ unsigned bm[LAT_BM_WORDS], bmT[LAT_BM_WORDS];
+  __shared__ int scan[256];
+  __shared__ unsigned long long s_occ[LAT_C];
+  __shared__ unsigned long long s_tmp[LAT_C];
+  __shared__ int s_bad, s_box[4];
+  const int t = threadIdx.x;
+  const int p0 = offsets[i], np = offsets[i + 1] - p0;
+  for (int k = t; k < LAT_BM_WORDS; k += 256) bm[k] = bmT[k] = 0u;
+  if (t == 0) {
+    s_bad = 0;
+    s_box[0] = s_box[1] = LAT_N;
+    s_box[2] = s_box[3] = -1;
+  }
+  __syncthreads();
+  int bad = 0;
+  for (int k = t; k < np; k += 256) {
+    const float x = pts[(size_t)(p0 + k) * 2], y = pts[(size_t)(p0 + k) * 2 + 1];
+    const int xi = (int)x, yi = (int)y;
+    if (!(x == (float)xi && y == (float)yi && xi >= 0 && xi < LAT_N && yi >= 0 && yi < LAT_N)) {
+      bad = 1;
+      continue;
+    }
+    if (k > 0) {   // strictly increasing (row, col): the list is the bitmap's own order, without duplicates
+      const float px = pts[(size_t)(p0 + k - 1) * 2], py = pts[(size_t)(p0 + k - 1) * 2 + 1];
+      if (!(py < y || (py == y && px < x))) bad = 1;
+    }
+    atomicOr(&bm[yi * LAT_W + (xi >> 5)], 1u << (xi & 31));
+    atomicOr(&bmT[xi * LAT_W + (yi >> 5)], 1u << (yi & 31));
+  }
+  if (bad) s_bad = 1;
+  __syncthreads();
+  unsigned char *out = lat + (size_t)i * LAT_BYTES;
+  unsigned *o_bm = reinterpret_cast<unsigned *>(out), *o_bmT = o_bm + LAT_BM_WORDS;
+  int *o_pref = reinterpret_cast<int *>(o_bmT + LAT_BM_WORDS);
+  unsigned char *o_cd = reinterpret_cast<unsigned char *>(o_pref + LAT_N);
+  for (int k = t; k < LAT_BM_WORDS; k += 256) {
+    o_bm[k] = bm[k];
+    o_bmT[k] = bmT[k];
+  }
+  // row prefix: pixels in the rows above (thread = row); bounding box from the non-empty rows / columns
+  int cs = 0, ccol = 0;
+  for (int w = 0; w < LAT_W; ++w) {
+    cs += __popc(bm[t * LAT_W + w]);
+    ccol |= bmT[t * LAT_W + w] != 0u;
+  }
+  if (cs) {
+    atomicMin(&s_box[1], t);
+    atomicMax(&s_box[3], t);
+  }
+  if (ccol) {
+    atomicMin(&s_box[0], t);
+    atomicMax(&s_box[2], t);
+  }
+  scan[t] = cs;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    int v = t >= o ? scan[t - o] : 0;
+    __syncthreads();
+    scan[t] += v;
+    __syncthreads();
+  }
+  o_pref[t] = scan[t] - cs;
+  if (t == 255 && scan[255] != np) s_bad = 1;
+  coarse_distance(bm, s_occ, s_tmp, o_cd);
+  if (t == 0) {
+    lat_ok[i] = s_bad ? 0 : 1;
+    float *gp = gparam + ((size_t)i * 2 + 1) * GP_STRIDE;
+    const bool any = s_box[2] >= 0;
+    const float x0 = any ? (float)s_box[0] : 0.f, y0 = any ? (float)s_box[1] : 0.f;
+    const float x1 = any ? (float)s_box[2] : 0.f, y1 = any ? (float)s_box[3] : 0.f;
+    gp[0] = x0;
+    gp[1] = y0;
+    gp[2] = x1;
+    gp[3] = y1;
+    gp[4] = 1.0f;
+    gp[5] = 1.0f;
+    gp[6] = x1 * x1 + y1 * y1;   // max |a|^2 (coordinates are >= 0)
+    gp[7] = 0.f;
+  }
+  __syncthreads();
+  return s_bad == 0;
+}
+

@@ -328,7 +328,6 @@ int launch_fold_step(smplb_ctx *c, int B, const float *A, const float *cam, cons
 int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long long count_override, float *loss_parts);
 // k_mesh_lattice.cu
 size_t mesh_lattice_workspace(int B);
-int launch_mesh_lattice_build(smplb_ctx *c, int B, const float *pts, const int *offsets, void *ws, float *gparam, int **lat_ok_out);
 int launch_mesh_lattice_search(smplb_ctx *c, int B, int V, const int *offsets, const void *ws, const float *gparam,
                                const float4 *sortedB, float *vdist, float *d_sil, int *ind_ba);
 // k_gemm_tc.cu
