@@ -579,7 +579,8 @@ static int launch_res_cfg(smplb_ctx *c, int B, const void *x16, const void *A16,
   TRY(tc_make_map(&map_a, 0, A16, 64, (uint64_t)B * 12, 128, 64, C::TN / 2));
   const int n_vp = c->Vp / (2 * FB_VT), n_m = cdiv(B, C::NS);
   const int total = n_vp * n_m;
-  const int max_pairs = c->body_pairs > 0 && c->body_pairs < c->num_sms / 2 ? c->body_pairs : c->num_sms / 2;
+  const int want_pairs = c->body_pairs != 0 ? c->body_pairs : c->pairs_auto;   // (-1 / 0: every SM pair)
+  const int max_pairs = want_pairs > 0 && want_pairs < c->num_sms / 2 ? want_pairs : c->num_sms / 2;
   const int grid = 2 * (total < max_pairs ? total : max_pairs);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

@@ -806,6 +806,14 @@ static int smpl_forward_dev(smplb_ctx *c, int B, const float *beta, const float 
     CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
     c->cur = c->stream2;
   }
+  // A forward-only call: the keypoint path (one tcgen05 GEMM + a per-body kernel, ~25 us) runs on the main stream while
+  // the vertex kernel runs here -- but only if that kernel leaves it SMs (the GEMM needs tensor memory and 160 KB of
+  // shared memory, the vertex kernel takes all of both).  With 10 SM pairs left free the call takes 148 instead of
+  // 185 us at B = 4096, 62 instead of 100 us at B = 1024, 39 instead of 78 us at B = 256 (tools/small_batch_pairs.py;
+  // 66 pairs already lose it: 16 free SMs are not enough).  Not for the training step -- its longer keypoint chain does
+  // not fit into 20 SMs beside the vertex kernel, and with several contexts in flight the SMs are never idle
+  // (tools/pairs_vs_contexts.py) -- nor for batches whose vertex kernel dwarfs the keypoint path.
+  c->pairs_auto = (overlap && !step_d_cam && B <= 8192 && c->num_sms >= 60) ? (c->num_sms - 20) / 2 : 0;
   if (fused) {
     TRY(launch_body_fwd_tc(c, B, c->ws_x16, c->ws_A16, vout));
   } else if (full && chunked) {

@@ -158,7 +158,8 @@ struct smplb_ctx {
   void *ws_A16 = nullptr;      // [B*12][64] fp16, row (b, 4r+d), 16-column windows (k_skin_tc.cu)
   // ---- fused blend + skinning (k_body_tc.cu): verts without the v_posed round trip
   bool body_tc_ok = false;
-  int body_pairs = 0;          // smplb_debug_set("body_pairs", n): CTA pairs of k_body_pair (0 = one per SM pair)
+  int body_pairs = 0;          // smplb_debug_set("body_pairs", n): CTA pairs of the vertex kernel (0 = automatic, -1 = one per SM pair)
+  int pairs_auto = 0;          // set per launch by smpl_forward_dev: pairs to use when body_pairs == 0 (0 = one per SM pair)
   int use_fused = 1;           // smplb_debug_set("fused", 0) selects the two-kernel path (which saves v_posed)
   // ---- workspace, sized for max_batch (grown on demand)
   int ws_batch = 0;
