@@ -469,6 +469,23 @@ def test_fused_blend_skinning_matches_two_kernel_path(smpl_full, full_model):
         assert rel_err(a, b) < 2e-6
 
 
+def test_forward_only_sm_split_does_not_change_verts(smpl_full):
+    """A forward-only call gives the vertex kernel 64 of the 74 SM pairs so that the keypoint path runs beside it
+    (`pairs_auto`); how the super-tiles are dealt to the CTAs must not change a bit of the result."""
+    ctx = smpl_full.ctx
+    inp = synthetic.make_inputs(64, seed=321)
+    res = {}
+    try:
+        for pairs in (0, -1, 17):        # automatic (64), every SM pair, an odd count that straddles vertex tiles
+            ctx.debug_set("body_pairs", pairs)
+            res[pairs] = smpl_full(inp["beta"], inp["theta"], get_skin=True)
+    finally:
+        ctx.debug_set("body_pairs", 0)
+    for pairs in (-1, 17):
+        for a, b in zip(res[0], res[pairs]):
+            assert np.array_equal(a, b), pairs
+
+
 def test_fused_blend_skinning_small_vertex_counts():
     """The CTA-pair kernel needs an even number of 128-vertex tiles: 200 vertices = 2 tiles = one
     pair (its second tile mostly padding), 300 = 3 tiles -> single-CTA fallback, 700 = 6 tiles = 3
