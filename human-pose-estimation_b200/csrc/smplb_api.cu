@@ -440,6 +440,7 @@ extern "C" int smplb_create(smplb_ctx **out, const smplb_model *m, int device, i
   cudaMemset(c->ws_cnt64, 0, 8 * sizeof(long long));
   if ((rc = blend_tc_init(c))) return fail(rc);
   if ((rc = skin_tc_init(c))) return fail(rc);
+  if ((rc = skin_bwd_tc_init(c))) return fail(rc);
   if ((rc = compact_tc_init(c))) return fail(rc);
   if ((rc = body_tc_init(c))) return fail(rc);
   if ((rc = fold_init(c))) return fail(rc);
@@ -456,7 +457,7 @@ extern "C" int smplb_destroy(smplb_ctx *c) {
   free_ws(c);
   void *ptrs[] = {c->d_vt,       c->d_shapedirs, c->d_posedirs, c->d_W,        c->d_JR,       c->d_Dext,   c->d_J0,
                   c->d_Jdirs,    c->d_kcsr_off,  c->d_kcsr_idx, c->d_kcsr_val, c->d_vcsr_off, c->d_vcsr_k, c->d_vcsr_val,
-                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_W16,      c->d_G,        c->d_cc,       c->d_G16,      c->d_Gt16,     c->d_Dt16_act, c->d_W16_act,  c->d_kcsr_slot, c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
+                  c->ws_scal,    c->ws_cnt64,    c->flush_buf,   c->d_Dt16,     c->d_W16,      c->d_WT16,      c->d_G,        c->d_cc,       c->d_G16,      c->d_Gt16,     c->d_Dt16_act, c->d_W16_act,  c->d_kcsr_slot, c->d_act_idx,  c->d_act_W,  c->d_acsr_off,
                   c->d_acsr_k,   c->d_acsr_val,  c->d_Dext_act,   c->ws_silpred, c->ws_dsil,    c->ws_silcnt, c->ws_mesh_part, c->ws_grid,  c->ws_vdist, c->ws_segpts, c->ws_segoff, c->ws_ticket,
                   c->x_mbox,     c->x_status,    c->d_Dbf};
   for (void *p : ptrs)
@@ -643,6 +644,10 @@ extern "C" int smplb_debug_set(smplb_ctx *c, const char *key, int value) {
   }
   if (!strcmp(key, "skin_tc")) {
     c->use_skin_tc = value;
+    return 0;
+  }
+  if (!strcmp(key, "skin_bwd_tc")) {
+    c->use_skin_bwd_tc = value;
     return 0;
   }
   if (!strcmp(key, "mesh_lattice")) {
@@ -906,15 +911,19 @@ static int smpl_backward_dev(smplb_ctx *c, int B, const float *d_verts, const fl
     else RET_IF(true, SMPLB_ESTATE, "v_posed was not saved by the forward");
     c->saved_full = true;
   }
+  int dA_parts = skin_bwd_splits(B);
   if (compact && c->saved_compact)
     TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed_act, nullptr, d_joints, dp, c->ws_dA, 2));
+  else if (!compact && c->skin_bwd_tc_ok && c->use_skin_bwd_tc && c->skin_tc_ok && c->use_skin_tc)
+    // the dense walk with both contractions on the tensor cores (A16 is the forward's operand, still in the workspace)
+    TRY(launch_skin_bwd_tc(c, B, c->ws_A16, c->ws_vposed, d_verts, d_joints, dp, bwd_tc ? c->ws_dp16 : nullptr, c->ws_dA, &dA_parts));
   else
     TRY(launch_skin_bwd(c, B, c->ws_A, c->ws_vposed, d_verts, d_joints, dp, c->ws_dA, compact ? 1 : 0, bwd_tc ? c->ws_dp16 : nullptr));
   int ks = compact ? 4 : c->ksplit;   // the compact contraction is 11x shorter: fewer split-K partials
   int dx_rows = B;
   if (bwd_tc) TRY(launch_blend_bwd_tc(c, B, c->ws_dp16, c->ws_dx, &ks, &dx_rows));
   else TRY(launch_blend_bwd(c, B, dp, c->ws_dx, compact, ks));
-  TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, skin_bwd_splits(B), c->ws_dx, ks, dx_rows, nullptr, d_Rs,
+  TRY(launch_pose_bwd(c, B, c->ws_theta, c->ws_Rs, c->ws_J, c->ws_A, c->ws_dA, dA_parts, c->ws_dx, ks, dx_rows, nullptr, d_Rs,
                       d_beta, d_theta));
   return 0;
 }

@@ -153,6 +153,11 @@ struct smplb_ctx {
   // ---- tcgen05 skinning path (k_skin_tc.cu)
   bool skin_tc_ok = false;
   int use_skin_tc = 1;         // smplb_debug_set("skin_tc", 0) selects the FP32 CUDA-core skinning kernel
+  // ---- tcgen05 skinning backward (k_skin_bwd_tc.cu)
+  bool skin_bwd_tc_ok = false;
+  int use_skin_bwd_tc = 1;     // smplb_debug_set("skin_bwd_tc", 0) selects the FP32 CUDA-core kernel k_skin_bwd for the dense walk
+  void *d_WT16 = nullptr;      // [64][Vp] bf16: W^T hi (rows 0..23) and lo (rows 32..55)
+  alignas(64) unsigned char map_wt[128];   // CUtensorMap of WT16
   void *d_W16 = nullptr;       // [Vp][64] fp16, 16-column windows (k_skin_tc.cu)
   alignas(64) unsigned char map_w[128];   // CUtensorMap of W16
   void *ws_A16 = nullptr;      // [B*12][64] fp16, row (b, 4r+d), 16-column windows (k_skin_tc.cu)
@@ -336,6 +341,10 @@ int tc_make_map(void *map, int is_f32, const void *ptr, uint64_t inner, uint64_t
                 uint32_t box_inner, uint32_t box_outer, int swizzle = 1);
 int launch_gemm_tc(smplb_ctx *c, const char *name, int M, int N, int K, const void *A16, const void *map_b, float *C,
                    int ldc, int ksplit, float scale, int bf16 = 0);
+// k_skin_bwd_tc.cu
+int skin_bwd_tc_init(smplb_ctx *c);
+int launch_skin_bwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, const float *d_verts, const float *d_joints,
+                       float *dp, void *dp16, float *dA_part, int *n_parts);
 // k_skin_tc.cu
 int skin_tc_init(smplb_ctx *c);
 int launch_skin_fwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_posed, float *verts, bool act);

@@ -420,6 +420,38 @@ def test_tcgen05_skinning_matches_fp32_kernel(smpl_full):
     assert rel_err(v1, v0) < 5e-6 and rel_err(j1, j0) < 5e-6
 
 
+def test_tcgen05_skinning_backward_matches_fp32_kernel(smpl_full, full_model):
+    """k_skin_bwd_tc (T = W.A and dA = W^T.(g x [v_posed; 1]) as tcgen05 contractions, bf16 hi / lo operands for the
+    gradient-scaled one) against k_skin_bwd on the FP32 pipes: dense backward with upstream d_verts of mesh-loss
+    magnitude (1e-4: fp16 would underflow), d_joints and d_Rs; ragged batch (chunks of 8) and the ragged last vertex
+    tile; and against the fp64 oracle."""
+    ctx = smpl_full.ctx
+    V = full_model["v_template"].shape[0]
+    o = onp.SMPL(full_model, dtype=np.float64)
+    for B, scale in ((5, 1.0), (61, 1e-4)):
+        inp = synthetic.make_inputs(B, seed=900 + B)
+        rng = np.random.default_rng(B)
+        ups = dict(d_verts=(rng.standard_normal((B, V, 3)) * scale).astype(np.float32),
+                   d_joints=(rng.standard_normal((B, 19, 3)) * scale).astype(np.float32),
+                   d_Rs=(rng.standard_normal((B, 24, 3, 3)) * scale).astype(np.float32))
+        res = {}
+        try:
+            for mode in (1, 0):
+                ctx.debug_set("skin_bwd_tc", mode)
+                smpl_full(inp["beta"], inp["theta"], get_skin=True)
+                res[mode] = [np.array(x) for x in smpl_full.backward(**ups)]
+        finally:
+            ctx.debug_set("skin_bwd_tc", 1)
+        for a, b in zip(res[1], res[0]):
+            assert np.isfinite(a).all()
+            assert rel_err(a, b) < 3e-5, (B, scale)
+        n = min(B, 3)
+        ref = onp.smpl_backward(o, inp["beta"][:n].astype(np.float64), inp["theta"][:n].astype(np.float64),
+                                **{k: v[:n].astype(np.float64) for k, v in ups.items()})
+        for a, b in zip(res[1], ref):
+            assert rel_err(a[:n], b) < TOL
+
+
 def test_fused_blend_skinning_matches_two_kernel_path(smpl_full, full_model):
     """k_body_res / k_body_pair / k_body_tc (blend + skinning in one kernel, v_posed stays in TMEM) against k_blend_tc +
     k_skin_tc: the same fp16 operands and fp32 accumulation, so the two may differ only by fp32
