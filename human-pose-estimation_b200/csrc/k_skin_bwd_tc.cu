@@ -33,7 +33,9 @@
 #define SBT_S 8
 #define SBT_N (12 * SBT_S)                     // 96
 #define SBT_NJ 32                              // MMA 2's N: 24 joints padded
-#define SBT_THREADS 352
+#define SBT_SPW 2                              // samples per epilogue warp and tile
+#define SBT_EW (4 * SBT_S / SBT_SPW)           // epilogue warps: SBT_S / SBT_SPW per TMEM lane quarter
+#define SBT_THREADS (32 * (3 + SBT_EW))
 #define SBT_A_BYTES (SBT_N * 128)              // 12 KB: A16 rows of the chunk
 #define SBT_W_BYTES (SBT_VT * 128)             // 16 KB: W16 tile
 #define SBT_WT_PART (SBT_NJ * 128)             // 4 KB: 32 joints x 64 vertices of one (hi / lo, k-block)
@@ -89,15 +91,15 @@ __global__ void __launch_bounds__(SBT_THREADS, 1)
       mbar_init(full_wt + 8 * i, 1);
       mbar_init(empty_wt + 8 * i, 1);
       mbar_init(tmem_full + 8 * i, 1);
-      mbar_init(tmem_empty + 8 * i, 8);   // one arrival per epilogue warp
+      mbar_init(tmem_empty + 8 * i, SBT_EW);   // one arrival per epilogue warp
     }
-    mbar_init(x_full, 8);
+    mbar_init(x_full, SBT_EW);
     mbar_init(x_empty, 1);
     mbar_init(d2_full, 1);
-    mbar_init(d2_empty, 8);
+    mbar_init(d2_empty, SBT_EW);
     for (int i = 0; i < SBT_PSTAGES; ++i) {
       mbar_init(full_p + 8 * i, 1);
-      mbar_init(empty_p + 8 * i, 8);
+      mbar_init(empty_p + 8 * i, SBT_EW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(SBT_THREADS, 1)
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 2 + SBT_EW) {
     // =========================== v_posed tile producer ===========================
     if (lane == 0) {
       int stage = 0, phase = 0;
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(SBT_THREADS, 1)
   } else {
     // =========================== epilogue (warps 2..9) ===========================
     const int q = warp & 3;                       // vertices 32 q .. 32 q + 31 of the tile (TMEM lane quarter)
-    const int half = (warp - 2) >> 2;             // samples 4 half .. 4 half + 3 of the chunk
+    const int half = (warp - 2) >> 2;             // samples SPW half .. SPW half + SPW - 1 of the chunk
     const int vl = 32 * q + lane;                 // vertex within the tile = column of the X operand
     // byte offset of column vl inside a 128-byte row of its k-block, before the swizzle XOR with the row
     const uint32_t x_part = sbase + SBT_SM_X + (vl >> 6) * SBT_X_PART;
@@ -254,35 +256,58 @@ __global__ void __launch_bounds__(SBT_THREADS, 1)
       for (int vt = vt0; vt < vt1; ++vt) {
         const int v = vt * SBT_VT + vl;
         const bool v_ok = v < V;
-        mbar_wait(full_p + 8 * pst, pphase);
-        const float *ptile = reinterpret_cast<const float *>(smem + SBT_SM_P + pst * SBT_P_BYTES) + vl;
+        // the upstream gradient of this thread's (vertex, 4 samples) first: global loads that depend on nothing the
+        // MMAs produce, issued before any wait (all twelve d_verts loads in flight together; the joint-regressor term
+        // only exists for the few vertices with an entry, its row bounds are read once per tile)
+        float g[SBT_SPW][3], p[SBT_SPW][3];
+        int e0 = 0, e1 = 0;
+        if (v_ok && d_joints) {
+          e0 = voff[v];
+          e1 = voff[v + 1];
+        }
+#pragma unroll
+        for (int si = 0; si < SBT_SPW; ++si) {
+          const int b = ch * SBT_S + SBT_SPW * half + si;
+          g[si][0] = g[si][1] = g[si][2] = 0.f;
+          if (v_ok && b < B && d_verts) {
+            const float *dv = d_verts + ((size_t)b * V + v) * 3;
+            g[si][0] = dv[0];
+            g[si][1] = dv[1];
+            g[si][2] = dv[2];
+          }
+        }
+        for (int e = e0; e < e1; ++e) {
+          const int k = vk[e];
+          const float wv = vval[e];
+#pragma unroll
+          for (int si = 0; si < SBT_SPW; ++si) {
+            const int b = ch * SBT_S + SBT_SPW * half + si;
+            if (b < B) {
+              const float *dj = d_joints + ((size_t)b * K + k) * 3;
+              g[si][0] = fmaf(wv, dj[0], g[si][0]);
+              g[si][1] = fmaf(wv, dj[1], g[si][1]);
+              g[si][2] = fmaf(wv, dj[2], g[si][2]);
+            }
+          }
+        }
         mbar_wait(tmem_full + 8 * acc, acc_phase);
         tc_fence_after();
-        uint32_t r[48];                           // T of this warp's 4 samples
-        const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16) + acc * SBT_N + half * 48;
-        tc_ld_32x32(trow, r);
-        tc_ld_32x16(trow + 32, r + 32);
-        float g[4][3], p[4][3];
+        uint32_t r[12 * SBT_SPW];                 // T of this warp's samples
+        const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16) + acc * SBT_N + half * (12 * SBT_SPW);
+        if (SBT_SPW == 4) {
+          tc_ld_32x32(trow, r);
+          tc_ld_32x16(trow + 32, r + 32);
+        } else {
+          tc_ld_32x16(trow, r);
+          tc_ld_32x8(trow + 16, r + 16);
+        }
+        mbar_wait(full_p + 8 * pst, pphase);
+        const float *ptile = reinterpret_cast<const float *>(smem + SBT_SM_P + pst * SBT_P_BYTES) + vl;
 #pragma unroll
-        for (int si = 0; si < 4; ++si) {
-          const int sl = 4 * half + si, b = ch * SBT_S + sl;
-          g[si][0] = g[si][1] = g[si][2] = 0.f;
+        for (int si = 0; si < SBT_SPW; ++si) {
+          const int sl = SBT_SPW * half + si, b = ch * SBT_S + sl;
           p[si][0] = p[si][1] = p[si][2] = 0.f;
           if (v_ok && b < B) {
-            if (d_verts) {
-              const float *dv = d_verts + ((size_t)b * V + v) * 3;
-              g[si][0] = dv[0];
-              g[si][1] = dv[1];
-              g[si][2] = dv[2];
-            }
-            if (d_joints)
-              for (int e = voff[v]; e < voff[v + 1]; ++e) {
-                const float *dj = d_joints + ((size_t)b * K + vk[e]) * 3;
-                const float wv = vval[e];
-                g[si][0] = fmaf(wv, dj[0], g[si][0]);
-                g[si][1] = fmaf(wv, dj[1], g[si][1]);
-                g[si][2] = fmaf(wv, dj[2], g[si][2]);
-              }
             const float *pr = ptile + sl * SBT_VT;       // [xyz][sample][vertex]
             p[si][0] = pr[0];
             p[si][1] = pr[SBT_S * SBT_VT];
@@ -298,8 +323,8 @@ __global__ void __launch_bounds__(SBT_THREADS, 1)
         }
         // dp = T_R^T g
 #pragma unroll
-        for (int si = 0; si < 4; ++si) {
-          const int b = ch * SBT_S + 4 * half + si;
+        for (int si = 0; si < SBT_SPW; ++si) {
+          const int b = ch * SBT_S + SBT_SPW * half + si;
           if (!(v_ok && b < B)) continue;
           const uint32_t *T = r + 12 * si;
           float d[3];
@@ -328,8 +353,8 @@ __global__ void __launch_bounds__(SBT_THREADS, 1)
         // X[(s, r, d), v] = g_r [p; 1]_d -> bf16 hi / lo into the MMA 2 operand (the previous tile's MMA 2 must be done)
         mbar_wait(x_empty, (xcount & 1) ^ 1);
 #pragma unroll
-        for (int si = 0; si < 4; ++si) {
-          const float one = (v_ok && ch * SBT_S + 4 * half + si < B) ? 1.0f : 0.0f;
+        for (int si = 0; si < SBT_SPW; ++si) {
+          const float one = (v_ok && ch * SBT_S + SBT_SPW * half + si < B) ? 1.0f : 0.0f;
           const float ph[4] = {p[si][0], p[si][1], p[si][2], one};
 #pragma unroll
           for (int rr = 0; rr < 3; ++rr)
@@ -338,7 +363,7 @@ __global__ void __launch_bounds__(SBT_THREADS, 1)
               const float x = g[si][rr] * ph[dd];
               const __nv_bfloat16 hi = __float2bfloat16_rn(x);
               const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-              const uint32_t row = (uint32_t)((4 * half + si) * 12 + 4 * rr + dd);
+              const uint32_t row = (uint32_t)((SBT_SPW * half + si) * 12 + 4 * rr + dd);
               const uint32_t addr = x_part + row * 128 + ((x_chunk ^ (row & 7)) << 4) + x_in;
               asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__bfloat16_as_ushort(hi)) : "memory");
               asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr + 2 * SBT_X_PART), "h"(__bfloat16_as_ushort(lo)) : "memory");
