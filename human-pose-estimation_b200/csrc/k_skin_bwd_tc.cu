@@ -447,11 +447,19 @@ int launch_skin_bwd_tc(smplb_ctx *c, int B, const void *A16, const float *v_pose
   TRY(tc_make_map(&map_a, 0, A16, 64, (uint64_t)B * 12, 128, 64, SBT_N));
   TRY(tc_make_map(&map_p, 1, v_posed, (uint64_t)c->pitch, (uint64_t)B, (uint64_t)c->pitch * 4, SBT_VT, SBT_S, /*swizzle=*/0));
   const int n_vt = c->Vp / SBT_VT, n_ch = cdiv(B, SBT_S);
-  // vertex ranges per chunk: enough units to fill the SMs a few times over, at most skin_bwd_splits(B) partials
-  int VS = cdiv(4 * c->num_sms, n_ch);
-  VS = VS < 1 ? 1 : VS;
-  VS = VS > skin_bwd_splits(B) ? skin_bwd_splits(B) : VS;
-  VS = VS > n_vt ? n_vt : VS;
+  // Vertex ranges per chunk (= partial sums per sample, at most skin_bwd_splits(B)): units go round-robin over the SMs,
+  // so pick the split whose last round is fullest (B = 1024: 8 splits = 1024 units = 6.9 rounds; 5 splits would be
+  // 4.3 rounds, the SMs with a fifth unit finishing 25 % after the others), with at least 3 vertex tiles per unit.
+  int VS = 1;
+  double best_eff = 0.0;
+  for (int vs = 1; vs <= skin_bwd_splits(B) && vs * 3 <= n_vt; ++vs) {
+    const int units = n_ch * vs;
+    const double eff = (double)units / ((double)cdiv(units, c->num_sms) * c->num_sms);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      VS = vs;
+    }
+  }
   const int n_units = n_ch * VS;
   const int grid = n_units < c->num_sms ? n_units : c->num_sms;
   LAUNCH(c, "skin_bwd_tc", grid, SBT_THREADS, SBT_SM_TOTAL, k_skin_bwd_tc, *(const CUtensorMap *)c->map_w, map_a, map_p,
