@@ -161,8 +161,12 @@ __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restri
   float *gp = gparam + ((size_t)i * 2 + sel) * GP_STRIDE;
   int *gs = gstart + ((size_t)i * 2 + sel) * (GRID_NC + 1);
   float mnx = 3.4e38f, mny = 3.4e38f, mxx = -3.4e38f, mxy = -3.4e38f;
+  // (points are read as 8-byte pairs, four iterations' loads in flight: these loops were bound by one load latency each)
+  const float2 *src2 = reinterpret_cast<const float2 *>(src);
+#pragma unroll 4
   for (int k = t; k < n; k += 256) {
-    float x = src[2 * k], y = src[2 * k + 1];
+    const float2 pt = src2[k];
+    float x = pt.x, y = pt.y;
     mnx = fminf(mnx, x);
     mny = fminf(mny, y);
     mxx = fmaxf(mxx, x);
@@ -190,8 +194,10 @@ __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restri
   float ext = fmaxf(x1 - x0, y1 - y0);
   float h = ext > 0.f ? ext / GRID_G : 1.0f;
   float inv_h = 1.0f / h;
+#pragma unroll 4
   for (int k = t; k < n; k += 256) {
-    float x = src[2 * k], y = src[2 * k + 1];
+    const float2 pt = src2[k];
+    float x = pt.x, y = pt.y;
     int cx = min(GRID_G - 1, max(0, (int)((x - x0) * inv_h)));
     int cy = min(GRID_G - 1, max(0, (int)((y - y0) * inv_h)));
     atomicAdd(&hist[cy * GRID_G + cx], 1);
@@ -239,8 +245,10 @@ __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restri
   }
   if (t == 255) gs[GRID_NC] = n;
   __syncthreads();
+#pragma unroll 4
   for (int k = t; k < n; k += 256) {
-    float x = src[2 * k], y = src[2 * k + 1];
+    const float2 pt = src2[k];
+    float x = pt.x, y = pt.y;
     int cx = min(GRID_G - 1, max(0, (int)((x - x0) * inv_h)));
     int cy = min(GRID_G - 1, max(0, (int)((y - y0) * inv_h)));
     int pos = atomicAdd(&hist[cy * GRID_G + cx], 1);

@@ -104,19 +104,33 @@ __device__ __forceinline__ bool lattice_build_image(int i, const float *__restri
   }
   __syncthreads();
   int bad = 0;
-  for (int k = t; k < np; k += 256) {
-    const float x = pts[(size_t)(p0 + k) * 2], y = pts[(size_t)(p0 + k) * 2 + 1];
-    const int xi = (int)x, yi = (int)y;
-    if (!(x == (float)xi && y == (float)yi && xi >= 0 && xi < LAT_N && yi >= 0 && yi < LAT_N)) {
-      bad = 1;
-      continue;
+  {
+    // 8-byte point loads, four iterations in flight; the previous point of the list comes from the neighbouring lane
+    const float2 *p2 = reinterpret_cast<const float2 *>(pts) + p0;
+    const int lane = t & 31;
+#pragma unroll 4
+    for (int k0 = 0; k0 < np; k0 += 256) {
+      const int k = k0 + t;
+      const bool in = k < np;
+      const float2 pt = in ? p2[k] : make_float2(0.f, 0.f);
+      float px = __shfl_up_sync(0xffffffffu, pt.x, 1), py = __shfl_up_sync(0xffffffffu, pt.y, 1);
+      if (lane == 0 && in && k > 0) {
+        const float2 pv = p2[k - 1];
+        px = pv.x;
+        py = pv.y;
+      }
+      if (!in) continue;
+      const float x = pt.x, y = pt.y;
+      const int xi = (int)x, yi = (int)y;
+      if (!(x == (float)xi && y == (float)yi && xi >= 0 && xi < LAT_N && yi >= 0 && yi < LAT_N)) {
+        bad = 1;
+        continue;
+      }
+      // strictly increasing (row, col): the list is the bitmap's own order, without duplicates
+      if (k > 0 && !(py < y || (py == y && px < x))) bad = 1;
+      atomicOr(&bm[yi * LAT_W + (xi >> 5)], 1u << (xi & 31));
+      atomicOr(&bmT[xi * LAT_W + (yi >> 5)], 1u << (yi & 31));
     }
-    if (k > 0) {   // strictly increasing (row, col): the list is the bitmap's own order, without duplicates
-      const float px = pts[(size_t)(p0 + k - 1) * 2], py = pts[(size_t)(p0 + k - 1) * 2 + 1];
-      if (!(py < y || (py == y && px < x))) bad = 1;
-    }
-    atomicOr(&bm[yi * LAT_W + (xi >> 5)], 1u << (xi & 31));
-    atomicOr(&bmT[xi * LAT_W + (yi >> 5)], 1u << (yi & 31));
   }
   if (bad) s_bad = 1;
   __syncthreads();
