@@ -145,15 +145,22 @@ __global__ void __launch_bounds__(256) k_grid_build(int V, const float *__restri
                                                     int *__restrict__ gstart, float4 *__restrict__ sortedB,
                                                     float4 *__restrict__ sortedA, unsigned char *__restrict__ gaux,
                                                     unsigned char *__restrict__ lat, int *__restrict__ lat_ok) {
-  __shared__ float red[4][256];
-  __shared__ int hist[GRID_NC];
-  __shared__ int scan[256];
-  __shared__ unsigned long long s_occ[GRID_G];
-  __shared__ unsigned long long s_tmp[GRID_G];
+  // One buffer, two views (a CTA bins points OR builds the lattice tables; a pixel set that is not a pixel list does the
+  // second, then the first): 22.5 KB instead of 40 KB lets 8 CTAs share an SM, i.e. the 2 B CTAs run in fewer rounds.
+  __shared__ __align__(16) unsigned char s_raw[GRID_NC * 4 + 4 * 256 * 4 + 256 * 4 + 2 * GRID_G * 8];
+  int *hist = reinterpret_cast<int *>(s_raw);                                           // [GRID_NC]       | bm, bmT
+  float(*red)[256] = reinterpret_cast<float(*)[256]>(s_raw + GRID_NC * 4);              // [4][256]
+  int *scan = reinterpret_cast<int *>(s_raw + GRID_NC * 4 + 4096);                      // [256]
+  unsigned long long *s_occ = reinterpret_cast<unsigned long long *>(s_raw + GRID_NC * 4 + 4096 + 1024);   // [GRID_G]
+  unsigned long long *s_tmp = s_occ + GRID_G;                                           // [GRID_G]
+  static_assert(2 * LAT_BM_WORDS * 4 <= GRID_NC * 4 && LAT_C == GRID_G, "the lattice tables fit the histogram's space");
   int sel = blockIdx.x, i = blockIdx.y, t = threadIdx.x;
   // the pixel set: tables for the lattice search first (k_mesh_lattice.cu); if the points are a row-major pixel list
   // that is all this image's pixels need, otherwise they are binned like the vertices
-  if (sel == 1 && lat && lattice_build_image(i, pts, offsets, lat, lat_ok, gparam)) return;
+  if (sel == 1 && lat &&
+      lattice_build_image(i, pts, offsets, lat, lat_ok, gparam, reinterpret_cast<unsigned *>(s_raw),
+                          reinterpret_cast<unsigned *>(s_raw) + LAT_BM_WORDS, scan, s_occ, s_tmp))
+    return;
   int p0 = offsets[i];
   int n = sel == 0 ? V : offsets[i + 1] - p0;
   const float *src = sel == 0 ? sil_pred + (size_t)i * V * 2 : pts + (size_t)p0 * 2;

@@ -86,13 +86,11 @@ __device__ __forceinline__ void coarse_distance(const unsigned *bm, unsigned lon
 // transposed bitmap, row prefix, coarse distances (LAT_BYTES at lat + i * LAT_BYTES), the bounding box of the pixels
 // (gparam of set 1, as k_grid_build writes it) and lat_ok[i] = the points ARE a row-major pixel list (integers in
 // [0, LAT_N)^2, strictly increasing).  Returns lat_ok[i] to every thread.
+// Scratch (shared memory of the caller): bm, bmT [LAT_BM_WORDS] each, scan [256], s_occ, s_tmp [LAT_C] each.
 __device__ __forceinline__ bool lattice_build_image(int i, const float *__restrict__ pts, const int *__restrict__ offsets,
                                                     unsigned char *__restrict__ lat, int *__restrict__ lat_ok,
-                                                    float *__restrict__ gparam) {
-  __shared__ unsigned bm[LAT_BM_WORDS], bmT[LAT_BM_WORDS];
-  __shared__ int scan[256];
-  __shared__ unsigned long long s_occ[LAT_C];
-  __shared__ unsigned long long s_tmp[LAT_C];
+                                                    float *__restrict__ gparam, unsigned *bm, unsigned *bmT, int *scan,
+                                                    unsigned long long *s_occ, unsigned long long *s_tmp) {
   __shared__ int s_bad, s_box[4];
   const int t = threadIdx.x;
   const int p0 = offsets[i], np = offsets[i + 1] - p0;
