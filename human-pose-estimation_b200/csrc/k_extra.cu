@@ -8,20 +8,43 @@
 
 #define FULL 0xffffffffu
 
-// counts[i] = #{seg[i] > 0}
-__global__ void __launch_bounds__(256) k_sil_count(int HW, const float *__restrict__ seg, int *__restrict__ counts) {
-  __shared__ int red[256];
-  int i = blockIdx.x, t = threadIdx.x;
+// counts[i] = #{seg[i] > 0}; bits (may be NULL): the flags as a bitmap, bit k of image i = seg[i][k] > 0 (words per
+// image = ceil(HW / 32)) -- the fill reads 6 MB of flags instead of the 205 MB of masks a second time.
+__global__ void __launch_bounds__(256) k_sil_count(int HW, const float *__restrict__ seg, int *__restrict__ counts,
+                                                   unsigned *__restrict__ bits) {
+  __shared__ int red[8];
+  const int i = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
   const float *s = seg + (size_t)i * HW;
+  const int words = (HW + 31) / 32;
+  const bool vec = (reinterpret_cast<uintptr_t>(s) & 15) == 0;
   int c = 0;
-  for (int k = t; k < HW; k += 256) c += s[k] > 0.0f;
-  red[t] = c;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (t < o) red[t] += red[t + o];
-    __syncthreads();
+  // a warp walks 128 pixels (one float4 per lane) at a time; 8 lanes' nibbles make one 32-bit word
+  for (int k0 = 128 * w; k0 < HW; k0 += 128 * 8) {
+    const int k = k0 + 4 * lane;
+    unsigned f = 0;
+    if (vec && k + 4 <= HW) {
+      const float4 v = *reinterpret_cast<const float4 *>(s + k);
+      f = (unsigned)(v.x > 0.0f) | (unsigned)(v.y > 0.0f) << 1 | (unsigned)(v.z > 0.0f) << 2 | (unsigned)(v.w > 0.0f) << 3;
+    } else {
+      for (int j = 0; j < 4; ++j)
+        if (k + j < HW) f |= (unsigned)(s[k + j] > 0.0f) << j;
+    }
+    c += __popc(f);
+    unsigned word = f << (4 * (lane & 7));
+    word |= __shfl_xor_sync(FULL, word, 1);
+    word |= __shfl_xor_sync(FULL, word, 2);
+    word |= __shfl_xor_sync(FULL, word, 4);
+    const int wi = (k0 >> 5) + (lane >> 3);
+    if (bits && (lane & 7) == 0 && wi < words) bits[(size_t)i * words + wi] = word;
   }
-  if (t == 0) counts[i] = red[0];
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+  if (lane == 0) red[w] = c;
+  __syncthreads();
+  if (t == 0) {
+    int tot = 0;
+    for (int q = 0; q < 8; ++q) tot += red[q];
+    counts[i] = tot;
+  }
 }
 
 // offsets = exclusive scan of counts (single block, B <= any: sequential chunks of 1024)
@@ -49,53 +72,37 @@ __global__ void __launch_bounds__(1024) k_sil_scan(int B, const int *__restrict_
   if (t == 0) offsets[B] = carry;
 }
 
-// points[offsets[i] + rank] = (x = col, y = row) of the rank-th pixel > 0 in row-major order.  Warp w owns a
-// contiguous strip of the image and walks it 128 pixels (one float4 per lane) at a time: a counting pass, the strips'
-// bases from one shared-memory exchange, then a writing pass whose ranks come from a warp scan -- coalesced loads, no
-// block barrier inside the loops (the version with three barriers per 256 pixels took 0.18 ms at B = 1024).
-__global__ void __launch_bounds__(256) k_sil_fill(int H, int W, const float *__restrict__ seg,
-                                                  const int *__restrict__ offsets, int cap, float *__restrict__ points) {
+// points[offsets[i] + rank] = (x = col, y = row) of the rank-th pixel > 0 in row-major order, from the bitmap k_sil_count
+// wrote.  A warp owns a contiguous run of words and takes them one at a time, LANE = BIT: the lanes whose bit is set
+// write consecutive points, so every store instruction covers one contiguous run of up to 256 bytes (with a run of
+// words per thread the 32 lanes of a store wrote to 32 different places: 0.11 ms at B = 1024 whether the flags came from
+// the masks or from the bitmap).
+__global__ void __launch_bounds__(256) k_sil_fill_bits(int H, int W, const unsigned *__restrict__ bits,
+                                                       const int *__restrict__ offsets, int cap, float *__restrict__ points) {
   __shared__ int wsum[8];
   const int i = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int HW = H * W;
-  const float *s = seg + (size_t)i * HW;
-  const int strip = ((HW + 7) / 8 + 127) & ~127;      // pixels per warp, a multiple of 128
-  const int k0 = min(w * strip, HW), k1 = min(k0 + strip, HW);
-  const bool vec = (reinterpret_cast<uintptr_t>(s) & 15) == 0;
-  // the flags of this lane's four pixels k .. k + 3 as bits 0..3
-  auto flags4 = [&](int k) {
-    unsigned f = 0;
-    if (vec && k + 4 <= k1) {
-      const float4 v = *reinterpret_cast<const float4 *>(s + k);
-      f = (unsigned)(v.x > 0.0f) | (unsigned)(v.y > 0.0f) << 1 | (unsigned)(v.z > 0.0f) << 2 | (unsigned)(v.w > 0.0f) << 3;
-    } else {
-      for (int j = 0; j < 4; ++j)
-        if (k + j < k1) f |= (unsigned)(s[k + j] > 0.0f) << j;
-    }
-    return f;
-  };
+  const int HW = H * W, words = (HW + 31) / 32;
+  const unsigned *bw = bits + (size_t)i * words;
+  const int per = (words + 7) / 8;
+  const int w0 = min(w * per, words), w1 = min(w0 + per, words);
   int c = 0;
-  for (int k = k0 + 4 * lane; k < k1; k += 128) c += __popc(flags4(k));
+  for (int k = w0 + lane; k < w1; k += 32) c += __popc(bw[k]);
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
   if (lane == 0) wsum[w] = c;
   __syncthreads();
+  if (c == 0) return;
   int pos = offsets[i];
   for (int q = 0; q < w; ++q) pos += wsum[q];
-  if (c == 0) return;
   const bool p8 = (reinterpret_cast<uintptr_t>(points) & 7) == 0;
-  for (int kb = k0; kb < k1; kb += 128) {
-    const int k = kb + 4 * lane;
-    const unsigned f = k < k1 ? flags4(k) : 0u;
-    const int n = __popc(f);
-    int incl = n;                                    // inclusive warp scan of the per-lane counts
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    int p = pos + incl - n;
-    int row = k / W, col = k - row * W;
-    for (int j = 0; j < 4; ++j) {
-      if (f >> j & 1u) {
+  for (int k0 = w0; k0 < w1; k0 += 32) {
+    const unsigned mine = k0 + lane < w1 ? bw[k0 + lane] : 0u;     // 32 words per load, handed out by shuffle
+    const int nw = min(32, w1 - k0);
+    for (int j = 0; j < nw; ++j) {
+      const unsigned word = __shfl_sync(FULL, mine, j);
+      if (word >> lane & 1u) {
+        const int p = pos + __popc(word & ((1u << lane) - 1u));
+        const int k = 32 * (k0 + j) + lane;
+        const int row = k / W, col = k - row * W;
         if (p < cap) {
           // x = column (ops.py:123: silhouette_gt[:, 2]), y = row (ops.py:124: silhouette_gt[:, 1])
           if (p8) {
@@ -105,14 +112,9 @@ __global__ void __launch_bounds__(256) k_sil_fill(int H, int W, const float *__r
             points[2 * (size_t)p + 1] = (float)row;
           }
         }
-        ++p;
       }
-      if (++col == W) {
-        col = 0;
-        ++row;
-      }
+      pos += __popc(word);
     }
-    pos += __shfl_sync(FULL, incl, 31);
   }
 }
 
@@ -327,17 +329,33 @@ int launch_critic_gp(smplb_ctx *c, int M, int K, long long M_total, const float 
   return 0;
 }
 
-int launch_silhouette_csr(smplb_ctx *c, int B, int H, int W, const float *seg, float *points, int cap, int *offsets,
-                          int *counts_scratch) {
-  LAUNCH(c, "sil_count", B, 256, 0, k_sil_count, H * W, seg, counts_scratch);
-  LAUNCH(c, "sil_scan", 1, 1024, 0, k_sil_scan, B, counts_scratch, offsets);
-  if (cap > 0) LAUNCH(c, "sil_fill", B, 256, 0, k_sil_fill, H, W, seg, offsets, cap, points);
+// the flags of B images as a bitmap in the context's workspace (grown on demand)
+static int ensure_segbits(smplb_ctx *c, int B, int H, int W) {
+  const size_t need = (size_t)B * ((size_t)(H * W + 31) / 32);
+  if (need > c->ws_segbits_cap) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->ws_segbits) CUDA_TRY(cudaFree(c->ws_segbits));
+    c->ws_segbits = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&c->ws_segbits, need * 4));
+    c->ws_segbits_cap = need;
+  }
   return 0;
 }
 
-// the fill alone, once the offsets (and the total) are known
+int launch_silhouette_csr(smplb_ctx *c, int B, int H, int W, const float *seg, float *points, int cap, int *offsets,
+                          int *counts_scratch) {
+  TRY(ensure_segbits(c, B, H, W));
+  LAUNCH(c, "sil_count", B, 256, 0, k_sil_count, H * W, seg, counts_scratch, c->ws_segbits);
+  LAUNCH(c, "sil_scan", 1, 1024, 0, k_sil_scan, B, counts_scratch, offsets);
+  if (cap > 0) LAUNCH(c, "sil_fill", B, 256, 0, k_sil_fill_bits, H, W, c->ws_segbits, offsets, cap, points);
+  return 0;
+}
+
+// the fill alone, once the offsets (and the total) are known: from the bitmap the last launch_silhouette_csr of the same
+// masks left in the workspace
 int launch_silhouette_fill(smplb_ctx *c, int B, int H, int W, const float *seg, float *points, int cap, const int *offsets) {
-  LAUNCH(c, "sil_fill", B, 256, 0, k_sil_fill, H, W, seg, offsets, cap, points);
+  (void)seg;
+  LAUNCH(c, "sil_fill", B, 256, 0, k_sil_fill_bits, H, W, c->ws_segbits, offsets, cap, points);
   return 0;
 }
 

@@ -207,6 +207,8 @@ struct smplb_ctx {
   float *ws_segpts = nullptr;      // smplb_step_seg: the compacted silhouette points [P][2] ...
   int *ws_segoff = nullptr;        // ... and their offsets [B + 1]
   size_t ws_segpts_cap = 0, ws_segoff_cap = 0;
+  unsigned *ws_segbits = nullptr;  // where(seg > 0) as a bitmap, written by k_sil_count for the fill [B][ceil(HW / 32)]
+  size_t ws_segbits_cap = 0;
   int use_mesh_lattice = 1;        // smplb_debug_set("mesh_lattice", 0): vertex -> pixel search through the binned grid for every image
   int use_mesh_grid = 1;           // smplb_debug_set("mesh_grid", 0): brute-force scan (the reference's own algorithm)
   size_t ws_mesh_part_cap = 0;
