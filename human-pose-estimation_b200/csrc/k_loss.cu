@@ -675,7 +675,7 @@ int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long l
 
 #define MESH_AB_BLOCKS 32
 int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *offsets, int P, const float *sil_pred,
-                     float *loss, float *d_sil_pred, int *cnt_scratch, float *part_scratch, int *ind_ab, int *ind_ba) {
+                     float *loss, float *d_sil_pred, int *cnt_scratch, float *part_scratch, int *ind_ab, int *ind_ba, bool finish_grad) {
   int n_ba_blocks = cdiv(V, MT);
   float *part_ab = part_scratch;
   float *part_ba = part_scratch + (size_t)B * MESH_AB_BLOCKS;
@@ -728,7 +728,7 @@ int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *of
   LAUNCH(c, "mesh_rowsum", B, 256, 0, k_mesh_rowsum, V, c->ws_vdist, part_ba);
   float denom = (float)(3 + V);
   LAUNCH(c, "mesh_finish", 1, 1024, 0, k_mesh_finish, B * MESH_AB_BLOCKS, part_ab, B, part_ba, denom, loss);
-  if (d_sil_pred) {
+  if (d_sil_pred && finish_grad) {   // (the step's k_proj_bwd applies (d_sil + cnt) / denom itself)
     size_t n = (size_t)B * V * 2;
     LAUNCH(c, "mesh_grad_finish", (unsigned)((n + 255) / 256), 256, 0, k_mesh_grad_finish, n, denom, cnt_scratch,
            d_sil_pred);

@@ -327,10 +327,13 @@ __global__ void k_proj(size_t total, int N, const float *__restrict__ X, const f
 
 // Projection backward.  CTA = one body; d_X = s g (z = 0), d_cam = (sum g.(xy+t), s sum g).
 // g = d_out * gscale [/ *den] [* 0.5 im_size].  Fixed-order block reduction (deterministic).
+// cnt != NULL: d_out is the mesh loss's raw gradient and (d_out + cnt) / denom is what k_mesh_grad_finish would have
+// left there (the same operations, so the same bits) -- the step skips that pass over B x V x 2.
 __global__ void __launch_bounds__(256) k_proj_bwd(int N, const float *__restrict__ X, const float *__restrict__ cam,
                                                   const float *__restrict__ d_out, int pixel, float im_w, float im_h,
                                                   float gscale, const long long *__restrict__ den, int accumulate_cam,
-                                                  float *__restrict__ d_X, float *__restrict__ d_cam) {
+                                                  float *__restrict__ d_X, float *__restrict__ d_cam,
+                                                  const int *__restrict__ cnt, float denom) {
   __shared__ float red[3][256];
   int b = blockIdx.x;
   float sc = gscale;
@@ -347,7 +350,12 @@ __global__ void __launch_bounds__(256) k_proj_bwd(int N, const float *__restrict
   float a_s = 0.f, a_x = 0.f, a_y = 0.f;
   for (int n = threadIdx.x; n < N; n += 256) {
     size_t i = (size_t)b * N + n;
-    float gx = d_out[i * 2 + 0] * fx, gy = d_out[i * 2 + 1] * fy;
+    float ox = d_out[i * 2 + 0], oy = d_out[i * 2 + 1];
+    if (cnt) {
+      ox = (ox + (float)cnt[i * 2 + 0]) / denom;
+      oy = (oy + (float)cnt[i * 2 + 1]) / denom;
+    }
+    float gx = ox * fx, gy = oy * fy;
     if (d_X) {
       d_X[i * 3 + 0] = s * gx;
       d_X[i * 3 + 1] = s * gy;
@@ -431,8 +439,8 @@ int launch_proj(smplb_ctx *c, int B, int N, const float *X, const float *cam, in
 
 int launch_proj_bwd(smplb_ctx *c, int B, int N, const float *X, const float *cam, const float *d_out, int pixel,
                     float im_w, float im_h, float gscale, const long long *den, int accumulate_cam, float *d_X,
-                    float *d_cam) {
+                    float *d_cam, const int *cnt, float denom) {
   LAUNCH(c, "proj_bwd", B, 256, 0, k_proj_bwd, N, X, cam, d_out, pixel, im_w, im_h, gscale, den, accumulate_cam, d_X,
-         d_cam);
+         d_cam, cnt, denom);
   return 0;
 }

@@ -1396,7 +1396,7 @@ static int step_core(smplb_ctx *c, int B, const float *beta, const float *theta,
     TRY(join_verts(c));
     TRY(launch_proj(c, B, c->V, vbuf, dcam, 1, img_size, img_size, c->ws_silpred));
     TRY(launch_mesh_loss(c, B, c->V, dpts, doff, P, c->ws_silpred, c->ws_scal + 2, bwd ? c->ws_dsil : nullptr,
-                         c->ws_silcnt, c->ws_mesh_part, nullptr, nullptr));
+                         c->ws_silcnt, c->ws_mesh_part, nullptr, nullptr, /*finish_grad=*/false));
     TRY(launch_finalize_loss(c, w_kp, w_mesh, (long long)kp_count_override, 1, oloss));
   } else {
     // the path's one exchange: {kp numerator, mesh sum} summed over the batch shards, everything on
@@ -1406,7 +1406,7 @@ static int step_core(smplb_ctx *c, int B, const float *beta, const float *theta,
       TRY(join_verts(c));
       TRY(launch_proj(c, B, c->V, vbuf, dcam, 1, img_size, img_size, c->ws_silpred));
       TRY(launch_mesh_loss(c, B, c->V, dpts, doff, P, c->ws_silpred, c->ws_scal + 2, bwd ? c->ws_dsil : nullptr,
-                           c->ws_silcnt, c->ws_mesh_part, nullptr, nullptr));
+                           c->ws_silcnt, c->ws_mesh_part, nullptr, nullptr, /*finish_grad=*/false));
     }
     if (cnt_aside && c->cur != c->stream3) {
       CUDA_TRY(cudaStreamWaitEvent(c->cur, c->ev_cnt, 0));   // den (written on stream3) before its first reader here
@@ -1456,8 +1456,9 @@ static int step_core(smplb_ctx *c, int B, const float *beta, const float *theta,
       const float *dverts = nullptr;
       if (have_mesh) {
         TRY(ensure_buf(c, &c->ws_dverts, (size_t)c->ws_batch * c->V3, false));
+        // (the mesh loss left its gradient unfinished: (d_sil + integer sign sums) / (3 + V) is applied here)
         TRY(launch_proj_bwd(c, B, c->V, vbuf, dcam, c->ws_dsil, 1, img_size, img_size, w_mesh, nullptr, 1, c->ws_dverts,
-                            odc));
+                            odc, c->ws_silcnt, (float)(3 + c->V)));
         dverts = c->ws_dverts;
       }
       TRY(smpl_backward_dev(c, B, dverts, c->ws_djoints, nullptr, odb, odt));

@@ -370,7 +370,7 @@ int launch_proj(smplb_ctx *c, int B, int N, const float *X, const float *cam, in
                 float *out);
 int launch_proj_bwd(smplb_ctx *c, int B, int N, const float *X, const float *cam, const float *d_out, int pixel,
                     float im_w, float im_h, float gscale, const long long *den, int accumulate_cam, float *d_X,
-                    float *d_cam);
+                    float *d_cam, const int *cnt = nullptr, float denom = 1.0f);
 // k_extra.cu
 int launch_silhouette_csr(smplb_ctx *c, int B, int H, int W, const float *seg, float *points, int cap, int *offsets,
                           int *counts_scratch);
@@ -390,7 +390,7 @@ int launch_kp_loss(smplb_ctx *c, int B, int K, const float *kp_gt, const float *
 int launch_reduce_kp(smplb_ctx *c, int B, const float *part, const int *cnt, float *abs_sum, long long *num_present,
                      float *cnt_as_float);
 int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *offsets, int P, const float *sil_pred,
-                     float *loss, float *d_sil_pred, int *cnt_scratch, float *part_scratch, int *ind_ab, int *ind_ba);
+                     float *loss, float *d_sil_pred, int *cnt_scratch, float *part_scratch, int *ind_ab, int *ind_ba, bool finish_grad = true);
 int launch_finalize_loss(smplb_ctx *c, float w_kp, float w_mesh, long long count_override, int have_mesh,
                          float *loss_parts);
 int launch_gp_colsum(smplb_ctx *c, int M, const float *g0, const float *g1, const float *g2, const float *g3,
