@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(LT) k_mesh_ba_lat(int V, const int *__restrict
     // every pixel lies in a coarse cell at Chebyshev distance >= c from the query's cell, i.e. on a lattice ring
     // >= 4 (c - 1) + 1
     const int c0 = cd[(gy >> 2) * LAT_C + (gx >> 2)];
-    int k = c0 >= 1 ? 4 * (c0 - 1) + 1 : 0;
+    // (a cell c0 cells away along some axis starts 4 c0 - o lattice points away, o = g's offset inside its own cell
+    // towards it: at least 4 c0 - 3, and 4 c0 - max(o_x, 3 - o_x, o_y, 3 - o_y) whichever the direction)
+    int k = c0 >= 1 ? 4 * c0 - max(max(gx & 3, 3 - (gx & 3)), max(gy & 3, 3 - (gy & 3))) : 0;
     const int kmax = max(max(gx, LAT_N - 1 - gx), max(gy, LAT_N - 1 - gy));
     if (k == 0) {
       // Rings 0 and 1 together, without loops (most queries lie inside the silhouette and end here): the 3 x 3 block of
