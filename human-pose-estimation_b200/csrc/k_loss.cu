@@ -673,11 +673,19 @@ int launch_reduce_finalize(smplb_ctx *c, int B, float w_kp, float w_mesh, long l
   return 0;
 }
 
-#define MESH_AB_BLOCKS 32
+#define MESH_AB_BLOCKS 32   // most CTAs per image of the pixel -> vertex kernels (= partial sums per image reserved)
+// CTAs per image: a CTA's warps walk their 256-pixel chunks independently and meet only in the final block sum, so a few
+// CTAs with several chunks each lose less to the slowest query of a chunk than one chunk per CTA (0.67 -> 0.56 ms at
+// B = 1024 going from 32 to 8); small batches keep more CTAs to fill the SMs.
+static inline int mesh_ab_blocks(const smplb_ctx *c, int B) {
+  int n = cdiv(4 * c->num_sms, B > 0 ? B : 1);
+  return n < 8 ? 8 : (n > MESH_AB_BLOCKS ? MESH_AB_BLOCKS : n);
+}
 int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *offsets, int P, const float *sil_pred,
                      float *loss, float *d_sil_pred, int *cnt_scratch, float *part_scratch, int *ind_ab, int *ind_ba, bool finish_grad) {
   int n_ba_blocks = cdiv(V, MT);
   float *part_ab = part_scratch;
+  const int ab_blocks = mesh_ab_blocks(c, B);
   float *part_ba = part_scratch + (size_t)B * MESH_AB_BLOCKS;
   if ((size_t)B * V > c->ws_vdist_cap) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -712,13 +720,13 @@ int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *of
     int *lat_ok = use_lat ? (int *)(lat + (size_t)B * LAT_BYTES) : nullptr;
     LAUNCH(c, "mesh_grid_build", dim3(2, B), 256, 0, k_grid_build, V, pts, offsets, sil_pred, gparam, gstart, sortedB, sortedA,
            gaux, lat, lat_ok);
-    LAUNCH(c, "mesh_nn_pixel_to_vertex_grid", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab<true>, V, pts, offsets, sil_pred,
+    LAUNCH(c, "mesh_nn_pixel_to_vertex_grid", dim3(ab_blocks, B), MT, 0, k_mesh_ab<true>, V, pts, offsets, sil_pred,
            part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, gparam, gstart, sortedB, gaux);
     LAUNCH(c, "mesh_nn_vertex_to_pixel_grid", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba<true>, V, pts, offsets, sil_pred,
            c->ws_vdist, d_sil_pred, ind_ba, gparam, gstart, sortedA, sortedB, gaux, (const int *)lat_ok);
     if (use_lat) TRY(launch_mesh_lattice_search(c, B, V, offsets, lat_ws, gparam, sortedB, c->ws_vdist, d_sil_pred, ind_ba));
   } else {
-    LAUNCH(c, "mesh_nn_pixel_to_vertex", dim3(MESH_AB_BLOCKS, B), MT, 0, k_mesh_ab<false>, V, pts, offsets, sil_pred,
+    LAUNCH(c, "mesh_nn_pixel_to_vertex", dim3(ab_blocks, B), MT, 0, k_mesh_ab<false>, V, pts, offsets, sil_pred,
            part_ab, d_sil_pred ? cnt_scratch : (int *)nullptr, ind_ab, (const float *)nullptr, (const int *)nullptr,
            (const float4 *)nullptr, (const unsigned char *)nullptr);
     LAUNCH(c, "mesh_nn_vertex_to_pixel", dim3(n_ba_blocks, B), MT, 0, k_mesh_ba<false>, V, pts, offsets, sil_pred,
@@ -727,7 +735,7 @@ int launch_mesh_loss(smplb_ctx *c, int B, int V, const float *pts, const int *of
   }
   LAUNCH(c, "mesh_rowsum", B, 256, 0, k_mesh_rowsum, V, c->ws_vdist, part_ba);
   float denom = (float)(3 + V);
-  LAUNCH(c, "mesh_finish", 1, 1024, 0, k_mesh_finish, B * MESH_AB_BLOCKS, part_ab, B, part_ba, denom, loss);
+  LAUNCH(c, "mesh_finish", 1, 1024, 0, k_mesh_finish, B * ab_blocks, part_ab, B, part_ba, denom, loss);
   if (d_sil_pred && finish_grad) {   // (the step's k_proj_bwd applies (d_sil + cnt) / denom itself)
     size_t n = (size_t)B * V * 2;
     LAUNCH(c, "mesh_grad_finish", (unsigned)((n + 255) / 256), 256, 0, k_mesh_grad_finish, n, denom, cnt_scratch,
